@@ -1,0 +1,286 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (run in the build container only).
+
+    python -m oracle.make_golden            # needs /root/reference mounted
+
+The reference publishes no golden vectors or known-answer tests for this path,
+so these fixtures are minted here by importing the reference's own code
+(model/diffusion_1d.py through oracle/ref_shim.py; the objective closures of
+inference/inverse_design_diffusion_1d.py:211-258 are compiled straight out of the reference
+file with `ast`, never copied into this repository) and running it on seeded inputs with the
+deterministic random-init weights of `cindm_b200.model.params.init_unet_params(seed=0,
+randomize_affine=True)`.  The fixtures travel to the GPU box; the reference does not.
+"""
+import ast
+import contextlib
+import io
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+from cindm_b200.model.params import init_unet_params  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+HORIZON = 24
+
+
+def reference_objective_namespace():
+    """Compile get_design_fn / get_eval_fn* out of the reference driver without importing it."""
+    path = os.path.join(ref_shim.REFERENCE_ROOT, "inference", "inverse_design_diffusion_1d.py")
+    tree = ast.parse(open(path).read())
+    wanted = {"get_design_fn", "get_eval_fn", "get_eval_fn_std", "get_eval_fn_loss_each"}
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    assert {n.name for n in body} == wanted
+    ns = {"torch": torch, "np": np}
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+    return ns
+
+
+def build_reference(sd):
+    m = ref_shim.load()
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = m.TemporalUnet1D(horizon=HORIZON, transition_dim=8, cond_dim=False, dim=64,
+                               dim_mults=(1, 2, 4, 8), attention=True)
+        dif = m.GaussianDiffusion1D(net, image_size=HORIZON, conditioned_steps=0, timesteps=1000,
+                                    sampling_timesteps=1000, loss_type="l1")
+    net.load_state_dict(sd)
+    dif.eval()
+    return m, net, dif
+
+
+def seeded(shape, seed, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g, dtype=dtype)
+
+
+def gen_schedule(dif):
+    from oracle.sampler_ref import SCHEDULE_KEYS
+    sd = dif.state_dict()
+    np.savez_compressed(os.path.join(GOLDEN, "schedule.npz"), **{k: sd[k].numpy() for k in SCHEDULE_KEYS})
+
+
+def gen_unet(net):
+    out = {}
+    x = seeded((4, HORIZON, 8), 11)
+    out["x"] = x.numpy()
+    for t in (0, 37, 999):
+        with torch.no_grad():
+            out[f"eps_t{t}"] = net(x, torch.full((4,), t, dtype=torch.long), None).numpy()
+    # layer-by-layer activations for the first two slices at t=37 (forward hooks on the reference)
+    taps = {}
+    hooks = []
+
+    def add(name, mod):
+        hooks.append(mod.register_forward_hook(lambda _m, _i, o, name=name: taps.__setitem__(name, o.detach().clone())))
+
+    add("temb", net.time_mlp)
+    for i, stage in enumerate(net.downs):
+        for j, mod in enumerate(stage):
+            if len(list(mod.parameters())) > 0:
+                add(f"downs.{i}.{j}", mod)
+    add("mid_block1", net.mid_block1)
+    add("mid_attn", net.mid_attn)
+    add("mid_block2", net.mid_block2)
+    for i, stage in enumerate(net.ups):
+        for j, mod in enumerate(stage):
+            if len(list(mod.parameters())) > 0:
+                add(f"ups.{i}.{j}", mod)
+    add("final_conv.0", net.final_conv[0])
+    with torch.no_grad():
+        net(x[:2], torch.full((2,), 37, dtype=torch.long), None)
+    for h in hooks:
+        h.remove()
+    for k, v in taps.items():
+        out["tap:" + k] = v.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "unet_forward.npz"), **out)
+
+
+COMPOSE_CASES = {          # name: (n_bodies, n_composed, compose_start_step, mode, B, t)
+    "c1_2body_w1": (2, 0, 10, "mean-inside", 2, 500),
+    "c2_2body_w3": (2, 2, 10, "mean-inside", 2, 250),
+    "c3_4body_w1": (4, 0, 10, "mean-inside", 2, 999),
+    "c4_8body_w3": (8, 2, 10, "mean-inside", 2, 3),
+    "sum_4body_w2_s4": (4, 1, 4, "sum-inside", 3, 700),
+}
+
+
+def gen_compose(m, dif):
+    out = {}
+    for name, (n, nc, start, mode, b, t) in COMPOSE_CASES.items():
+        x = seeded((b, HORIZON + nc * start, 4 * n), 100 + n + nc)
+        m.grad_mean_list.clear()
+        with torch.no_grad():
+            pred = dif.model_predictions(x, None, torch.full((b,), t, dtype=torch.long), None,
+                                         compose_mode=mode, n_composed=nc, compose_start_step=start,
+                                         single_model_step=HORIZON, compose_n_bodies=n)
+        out[name + ":x"] = x.numpy()
+        out[name + ":eps"] = pred.pred_noise.numpy()
+        out[name + ":x_start"] = pred.pred_x_start.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "composed_eps.npz"), **out)
+
+
+INDEX_CASES = [(2, 0, 10), (2, 2, 10), (2, 3, 10), (4, 0, 10), (4, 2, 10), (8, 0, 10), (8, 2, 10), (3, 1, 4), (4, 1, 23)]
+
+
+def gen_index_maps(m, dif):
+    """Recover gather / scatter / cover maps from the reference by probing it with a coded stub model."""
+    real_model = dif.model
+    out = {}
+    try:
+        for (n, nc, start) in INDEX_CASES:
+            t_total = HORIZON + nc * start
+            f = 4 * n
+            w, p = nc + 1, n * (n - 1) // 2
+            x = (torch.arange(t_total * f, dtype=torch.float64).reshape(1, t_total, f) + 1.0)
+            gathered = []
+            state = {"active": -1, "call": 0}
+
+            def stub(xs, tt, cond):
+                gathered.append(xs.clone())
+                k = state["call"]
+                state["call"] += 1
+                if k == state["active"]:
+                    return torch.arange(HORIZON * 8, dtype=torch.float64).reshape(1, HORIZON, 8) + 1.0
+                return torch.zeros(1, HORIZON, 8, dtype=torch.float64)
+
+            class _Probe(torch.nn.Module):
+                def forward(self, xs, tt, cond):
+                    return stub(xs, tt, cond)
+
+            dif.model = _Probe()
+            gather = None
+            scatter = -np.ones((w * p, HORIZON * 8), dtype=np.int64)
+            cover = np.zeros(t_total, dtype=np.int64)
+            for call in range(w * p):
+                state["active"], state["call"] = call, 0
+                gathered.clear()
+                m.grad_mean_list.clear()
+                with torch.no_grad():
+                    pred = dif.model_predictions(x, None, torch.zeros(1, dtype=torch.long), None,
+                                                 compose_mode="mean-inside", n_composed=nc,
+                                                 compose_start_step=start, single_model_step=HORIZON,
+                                                 compose_n_bodies=n).pred_noise[0]
+                if gather is None:
+                    gather = np.stack([(g[0] - 1.0).numpy().astype(np.int64).reshape(-1) for g in gathered])
+                # every coded output element is code(h, c) / (n-1) / cover(t) with code = h*8 + c + 1.
+                # Windows are whole rows, so h = t - first nonzero row, and the largest code of a row
+                # (c = 7) identifies cover(t).
+                nz = pred.nonzero()
+                assert len(nz) == HORIZON * 8
+                t_first = int(nz[:, 0].min())
+                for h in range(HORIZON):
+                    tt = t_first + h
+                    row = pred[tt] * (n - 1)
+                    cv = int(round((h * 8 + 8) / row.max().item()))
+                    assert 1 <= cv <= w
+                    assert cover[tt] in (0, cv)
+                    cover[tt] = cv
+                    cols = row.nonzero().reshape(-1).tolist()
+                    assert len(cols) == 8
+                    for ff in cols:
+                        code = row[ff].item() * cv
+                        c = int(round(code)) - 1 - h * 8
+                        assert abs(code - round(code)) < 1e-6 and 0 <= c < 8
+                        assert scatter[call, h * 8 + c] == -1
+                        scatter[call, h * 8 + c] = tt * f + ff
+            key = f"n{n}_nc{nc}_s{start}"
+            out[key + ":gather"] = gather.astype(np.int32)     # [W*P, 24*8] flat index t*F+f into x
+            out[key + ":scatter"] = scatter.astype(np.int32)   # [W*P, 24*8] flat index t*F+f into eps
+            out[key + ":cover"] = cover.astype(np.int32)       # [T_total]
+    finally:
+        dif.model = real_model
+    np.savez_compressed(os.path.join(GOLDEN, "index_maps.npz"), **out)
+
+
+def gen_design_grad(ns):
+    out = {}
+    cases = {"L2_n4": (4, 44, "L2", 0.2, 0.2), "L2sq_n2": (2, 24, "L2square", 0.4, 0.1),
+             "L2_n8_nocons": (8, 34, "L2", 0.6, 0.0)}
+    for name, (n, t_total, mode, coef, cc) in cases.items():
+        x = seeded((3, t_total, 4 * n), 7 + n) * 0.7
+        target = torch.tensor([0.5, 0.5], dtype=float)
+        fn = ns["get_design_fn"](target, last_n_step=1, coef=coef, time_consistency_coef=cc, design_fn_mode=mode)
+        xc = x.clone().requires_grad_()
+        val = fn(xc)
+        (g,) = torch.autograd.grad(val, xc)
+        out[name + ":x"] = x.numpy()
+        out[name + ":grad"] = g.numpy()
+        out[name + ":value"] = np.float64(val.item())
+        out[name + ":eval"] = np.float64(ns["get_eval_fn"](target, last_n_step=1)(x))
+        out[name + ":eval_std"] = np.float64(ns["get_eval_fn_std"](target, last_n_step=1)(x))
+        out[name + ":eval_each"] = ns["get_eval_fn_loss_each"](target, last_n_step=1)(x).numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "design_grad.npz"), **out)
+
+
+TRAJ_CASES = {   # name: (n, nc, start, guidance, compose_mode, coef, cc, B, steps)
+    "rec2_4body_w2": (4, 1, 10, "standard-recurrence-2", "mean-inside", 0.2, 0.2, 2, (999, 998, 500, 1, 0)),
+    "std_2body_w3": (2, 2, 10, "standard", "mean-inside", 0.4, 0.1, 2, (999, 600, 0)),
+    "alpha_rec2_4body": (4, 0, 10, "standard-alpha-recurrence-2", "sum-inside", 0.2, 0.2, 2, (800, 1)),
+}
+
+
+def gen_trajectories(m, dif, ns):
+    out = {}
+    real_randn_like = torch.randn_like
+    for name, (n, nc, start, guidance, mode, coef, cc, b, steps) in TRAJ_CASES.items():
+        target = torch.tensor([0.5, 0.5], dtype=float)
+        fn = ns["get_design_fn"](target, last_n_step=1, coef=coef, time_consistency_coef=cc, design_fn_mode="L2")
+        img = seeded((b, HORIZON + nc * start, 4 * n), 900 + n)
+        out[name + ":x_init"] = img.numpy()
+        noises = []
+        gen = torch.Generator().manual_seed(4242 + n)
+
+        def logged_randn_like(t, **kw):
+            z = torch.randn(t.shape, generator=gen, dtype=t.dtype)
+            noises.append(z)
+            return z
+
+        torch.randn_like = logged_randn_like
+        try:
+            for si, t in enumerate(steps):
+                m.grad_mean_list.clear()
+                img, x0 = dif.p_sample_compose_inside(
+                    img, None, t, None, design_fn=fn, design_guidance=guidance, compose_mode=mode,
+                    n_composed=nc, compose_start_step=start, single_model_step=HORIZON, compose_n_bodies=n)
+                out[f"{name}:img_after_{si}"] = img.numpy()
+                out[f"{name}:x0_after_{si}"] = x0.numpy()
+        finally:
+            torch.randn_like = real_randn_like
+        out[name + ":noise"] = torch.stack(noises).numpy()
+        out[name + ":steps"] = np.asarray(steps, dtype=np.int32)
+    np.savez_compressed(os.path.join(GOLDEN, "trajectories.npz"), **out)
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    sd = init_unet_params(seed=0, randomize_affine=True)
+    m, net, dif = build_reference(sd)
+    ns = reference_objective_namespace()
+    gen_schedule(dif)
+    gen_unet(net)
+    gen_compose(m, dif)
+    gen_index_maps(m, dif)
+    gen_design_grad(ns)
+    gen_trajectories(m, dif, ns)
+    meta = {
+        "weights": "cindm_b200.model.params.init_unet_params(seed=0, randomize_affine=True)",
+        "torch": torch.__version__,
+        "compose_cases": {k: list(v) for k, v in COMPOSE_CASES.items()},
+        "traj_cases": {k: [list(x) if isinstance(x, tuple) else x for x in v] for k, v in TRAJ_CASES.items()},
+        "index_cases": INDEX_CASES,
+    }
+    json.dump(meta, open(os.path.join(GOLDEN, "meta.json"), "w"), indent=1)
+    for fn in sorted(os.listdir(GOLDEN)):
+        print(fn, os.path.getsize(os.path.join(GOLDEN, fn)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,110 @@
+"""CPU: the oracle (oracle/*.py) against the golden vectors minted from the unmodified reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sampler_ref, unet_ref
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+META = json.load(open(os.path.join(HERE, "golden", "meta.json")))
+
+
+def rel_l2(a, b):
+    a = torch.as_tensor(a, dtype=torch.float64)
+    b = torch.as_tensor(b, dtype=torch.float64)
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def test_schedule_tables_bit_exact(golden):
+    g = golden("schedule.npz")
+    tabs = sampler_ref.cosine_schedule_tables()
+    for k in sampler_ref.SCHEDULE_KEYS:
+        assert np.array_equal(tabs[k].numpy(), g[k]), k
+    # the known-answer values quoted in SURVEY.md section 8(c)
+    assert abs(float(g["betas"][0]) - 4.1284e-5) < 1e-8
+    assert float(g["betas"][999]) == pytest.approx(0.999)
+    assert float(g["posterior_log_variance_clipped"][0]) == pytest.approx(-46.0517, abs=1e-3)
+
+
+def test_unet_forward_matches_reference(golden, test_weights):
+    g = golden("unet_forward.npz")
+    x = torch.from_numpy(g["x"])
+    for t in (0, 37, 999):
+        y = unet_ref.unet_forward(test_weights, x, torch.full((x.shape[0],), t, dtype=torch.long))
+        assert rel_l2(y, g[f"eps_t{t}"]) < 1e-6, t
+
+
+def test_unet_layer_taps_match_reference(golden, test_weights):
+    g = golden("unet_forward.npz")
+    x = torch.from_numpy(g["x"])[:2]
+    taps = {}
+    unet_ref.unet_forward(test_weights, x, torch.full((2,), 37, dtype=torch.long), taps=taps)
+    names = [k[4:] for k in g.files if k.startswith("tap:")]
+    assert len(names) == 32
+    for name in names:
+        assert name in taps, name
+        assert rel_l2(taps[name], g["tap:" + name]) < 1e-6, name
+
+
+@pytest.mark.parametrize("case", sorted(META["compose_cases"]))
+def test_composed_eps_matches_reference(golden, test_weights, case):
+    n, nc, start, mode, b, t = META["compose_cases"][case]
+    g = golden("composed_eps.npz")
+    x = torch.from_numpy(g[case + ":x"])
+    eps = sampler_ref.composed_eps(test_weights, x, t, nc, start, n, mode)
+    assert rel_l2(eps, g[case + ":eps"]) < 1e-6
+
+
+@pytest.mark.parametrize("n,nc,start", [tuple(c) for c in META["index_cases"]])
+def test_index_maps_bit_exact(golden, n, nc, start):
+    g = golden("index_maps.npz")
+    key = f"n{n}_nc{nc}_s{start}"
+    maps = sampler_ref.index_maps(n, nc, start)
+    f = 4 * n
+    gather = g[key + ":gather"].reshape(nc + 1, -1, 24, 8)
+    scatter = g[key + ":scatter"].reshape(nc + 1, -1, 24, 8)
+    assert np.array_equal(g[key + ":cover"], np.asarray(maps["cover"], dtype=np.int32))
+    for kk, t0 in enumerate(maps["win_t0"]):
+        for p, (ii, jj) in enumerate(maps["pairs"]):
+            for h in range(24):
+                want = [(t0 + h) * f + c for c in maps["gather_cols"][p]]
+                assert gather[kk, p, h].tolist() == want
+                # eps_pair[..., :4] -> receiver ii, [..., 4:] -> receiver jj, same rows
+                assert scatter[kk, p, h].tolist() == want
+
+
+def test_design_objective_and_gradient(golden):
+    g = golden("design_grad.npz")
+    cases = {"L2_n4": ("L2", 0.2, 0.2), "L2sq_n2": ("L2square", 0.4, 0.1), "L2_n8_nocons": ("L2", 0.6, 0.0)}
+    target = torch.tensor([0.5, 0.5], dtype=torch.float64)
+    for name, (mode, coef, cc) in cases.items():
+        x = torch.from_numpy(g[name + ":x"])
+        fn = sampler_ref.make_design_fn(target, 1, coef, cc, mode)
+        assert float(fn(x)) == pytest.approx(float(g[name + ":value"]), rel=1e-12)
+        grad = sampler_ref.design_grad_autograd(fn, x)
+        assert grad.dtype == torch.float32
+        assert np.array_equal(grad.numpy(), g[name + ":grad"])
+        assert sampler_ref.eval_objective(x, target) == pytest.approx(float(g[name + ":eval"]), rel=1e-12)
+        each = sampler_ref.eval_objective_each(x, target)
+        assert np.allclose(each.numpy(), g[name + ":eval_each"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("case", sorted(META["traj_cases"]))
+def test_teacher_forced_steps_match_reference(golden, test_weights, case):
+    n, nc, start, guidance, mode, coef, cc, b, steps = META["traj_cases"][case]
+    g = golden("trajectories.npz")
+    tabs = sampler_ref.cosine_schedule_tables()
+    fn = sampler_ref.make_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, coef, cc, "L2")
+    noise = list(torch.from_numpy(g[case + ":noise"]))
+    img = torch.from_numpy(g[case + ":x_init"])
+    for si, t in enumerate(steps):
+        img, x0 = sampler_ref.p_sample_step(
+            test_weights, tabs, img, t, lambda shape: noise.pop(0), n_composed=nc, compose_start_step=start,
+            compose_n_bodies=n, compose_mode=mode, design_fn=fn, design_guidance=guidance)
+        assert rel_l2(x0, g[f"{case}:x0_after_{si}"]) < 1e-5, (si, t)
+        assert rel_l2(img, g[f"{case}:img_after_{si}"]) < 1e-5, (si, t)
+        img = torch.from_numpy(g[f"{case}:img_after_{si}"])      # teacher forcing
+    assert not noise
