@@ -1,0 +1,309 @@
+// extern "C" boundary of libcindm_b200.so (declared in include/cindm_b200.h).
+#include <cmath>
+#include <cstring>
+
+#include "engine.h"
+
+namespace cindm {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+int nbody_rollout(const double* state0, double* traj, int B, int n, int n_steps, int stride, cudaStream_t st);
+int score_designs(const float* pred, float* mae, float* objective, int B, int T, int n, double tx, double ty,
+                  cudaStream_t st);
+
+}  // namespace cindm
+
+using namespace cindm;
+
+namespace {
+template <typename T>
+__global__ void tap_to_f32_cf(const T* __restrict__ in, float* __restrict__ out, long long S, int C, int H) {
+    long long total = S * C * H;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int h = (int)(i % H);
+        long long r = i / H;
+        int c = (int)(r % C);
+        long long s = r / C;
+        out[i] = to_f32<T>(in[(s * H + h) * C + c]);       // channels-last -> channels-first
+    }
+}
+}  // namespace
+
+#define API_BEGIN try {
+#define API_END                                                             \
+    }                                                                       \
+    catch (const std::exception& ex) { return fail(-1, std::string("exception: ") + ex.what()); } \
+    catch (...) { return fail(-1, "unknown exception"); }
+
+extern "C" {
+
+const char* cindm_last_error(void) { return g_last_error.c_str(); }
+int cindm_version(void) { return 100; }
+
+int cindm_create(const cindm_config* cfg, cindm_engine** out) {
+    API_BEGIN
+    if (!cfg || !out) return fail(-2, "null argument");
+    if (cfg->dim != 64) return fail(-2, "only Unet_dim=64 is built (dim_mults (1,2,4,8))");
+    if (cfg->horizon != 24) return fail(-2, "only horizon=24 (the 2-body 24-step model) is built");
+    if (cfg->transition_dim != 8) return fail(-2, "transition_dim must be 8 (two bodies x 4 features)");
+    if (cfg->timesteps < 1 || cfg->timesteps > 65535) return fail(-2, "timesteps out of range");
+    cindm_engine* e = new cindm_engine();
+    e->cfg = *cfg;
+    *out = e;
+    return 0;
+    API_END
+}
+
+int cindm_destroy(cindm_engine* e) {
+    API_BEGIN
+    if (!e) return 0;
+    cudaDeviceSynchronize();
+    for (void* p : e->allocations) cudaFree(p);
+    for (void* p : e->tap_allocs) cudaFree(p);
+    if (e->ws.base) cudaFree(e->ws.base);
+    if (e->sched_dev) cudaFree(e->sched_dev);
+    if (e->sb.x_alt) cudaFree(e->sb.x_alt);
+    if (e->sb.pred) cudaFree(e->sb.pred);
+    if (e->sb.eps) cudaFree(e->sb.eps);
+    if (e->sb.t_dev) cudaFree(e->sb.t_dev);
+    delete e;
+    return 0;
+    API_END
+}
+
+int cindm_load_weight(cindm_engine* e, const char* name, const float* host, const int64_t* shape, int ndim) {
+    API_BEGIN
+    if (!e || !name || !host || !shape) return fail(-2, "null argument");
+    if (e->finalized) return fail(-4, "weights already finalized");
+    HostTensor t;
+    int64_t n = 1;
+    for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= shape[i]; }
+    t.data.assign(host, host + n);
+    e->host_weights[name] = std::move(t);
+    return 0;
+    API_END
+}
+
+int cindm_finalize_weights(cindm_engine* e, void* stream) {
+    API_BEGIN
+    if (!e) return fail(-2, "null engine");
+    return finalize_weights(e, (cudaStream_t)stream);
+    API_END
+}
+
+int cindm_set_schedule(cindm_engine* e, const float* tables13, int timesteps) {
+    API_BEGIN
+    if (!e || !tables13) return fail(-2, "null argument");
+    if (timesteps != e->cfg.timesteps) return fail(-2, "schedule length does not match the engine's timesteps");
+    size_t n = (size_t)TAB_COUNT * timesteps;
+    e->sched_host.assign(tables13, tables13 + n);
+    if (!e->sched_dev) CINDM_CHECK_CUDA(cudaMalloc(&e->sched_dev, n * sizeof(float)));
+    CINDM_CHECK_CUDA(cudaMemcpy(e->sched_dev, tables13, n * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+    API_END
+}
+
+int cindm_reserve(cindm_engine* e, int64_t max_slices, int precision) {
+    API_BEGIN
+    if (!e) return fail(-2, "null engine");
+    return reserve_workspace(e, max_slices, precision);
+    API_END
+}
+
+int64_t cindm_workspace_bytes(int64_t max_slices, int precision) { return workspace_bytes(max_slices, precision, 24); }
+
+int cindm_schedule_tables(int timesteps, float* out) {
+    API_BEGIN
+    if (!out || timesteps < 1) return fail(-2, "bad argument");
+    const int T = timesteps;
+    const double s = 0.008;
+    std::vector<double> ac(T + 1), betas(T), acp(T), acp_prev(T);
+    for (int i = 0; i <= T; ++i) {
+        double x = (double)i;     // torch.linspace(0, T, T+1) is exact for integers
+        double c = cos(((x / T) + s) / (1 + s) * M_PI * 0.5);
+        ac[i] = c * c;
+    }
+    double ac0 = ac[0];
+    for (int i = 0; i <= T; ++i) ac[i] /= ac0;
+    double run = 1.0;
+    for (int i = 0; i < T; ++i) {
+        double b = 1.0 - ac[i + 1] / ac[i];
+        b = b < 0.0 ? 0.0 : (b > 0.999 ? 0.999 : b);
+        betas[i] = b;
+        acp_prev[i] = run;
+        run *= (1.0 - b);
+        acp[i] = run;
+    }
+    auto put = [&](int tab, int i, double v) { out[(size_t)tab * T + i] = (float)v; };
+    for (int i = 0; i < T; ++i) {
+        double b = betas[i], a = acp[i], ap = acp_prev[i];
+        double pv = b * (1.0 - ap) / (1.0 - a);
+        put(TAB_BETAS, i, b);
+        put(TAB_ACP, i, a);
+        put(TAB_ACP_PREV, i, ap);
+        put(TAB_SQRT_ACP, i, sqrt(a));
+        put(TAB_SQRT_1M_ACP, i, sqrt(1.0 - a));
+        put(TAB_LOG_1M_ACP, i, log(1.0 - a));
+        put(TAB_SQRT_RECIP_ACP, i, sqrt(1.0 / a));
+        put(TAB_SQRT_RECIPM1_ACP, i, sqrt(1.0 / a - 1.0));
+        put(TAB_POST_VAR, i, pv);
+        put(TAB_POST_LOGVAR, i, log(pv < 1e-20 ? 1e-20 : pv));
+        put(TAB_POST_C1, i, b * sqrt(ap) / (1.0 - a));
+        put(TAB_POST_C2, i, (1.0 - ap) * sqrt(1.0 - b) / (1.0 - a));
+        put(TAB_LOSS_W, i, 1.0);
+    }
+    return 0;
+    API_END
+}
+
+int cindm_build_index_maps(int n, int nc, int start, int H, int32_t* win_t0, int32_t* pair_i, int32_t* pair_j,
+                           int32_t* cover) {
+    API_BEGIN
+    if (n < 2 || nc < 0 || start <= 0 || H <= 0) return fail(-2, "bad argument");
+    const int T = H + nc * start;
+    if (win_t0)
+        for (int kk = 0; kk <= nc; ++kk) win_t0[kk] = kk * start;
+    int p = 0;
+    for (int ii = 0; ii < n; ++ii)
+        for (int jj = ii + 1; jj < n; ++jj, ++p) {
+            if (pair_i) pair_i[p] = ii;
+            if (pair_j) pair_j[p] = jj;
+        }
+    if (cover)
+        for (int t = 0; t < T; ++t) {
+            int c = 0;
+            for (int kk = 0; kk <= nc; ++kk) c += (t >= kk * start && t < kk * start + H) ? 1 : 0;
+            cover[t] = c;
+        }
+    return 0;
+    API_END
+}
+
+int cindm_compose_gather(const float* x, float* slices, int B, int n, int nc, int start, int H, void* stream) {
+    API_BEGIN
+    if (n < 2 || nc < 0 || start <= 0) return fail(-2, "bad composition parameters");
+    return launch_compose_gather(x, slices, B, n, nc, start, H, (cudaStream_t)stream);
+    API_END
+}
+
+int cindm_compose_scatter_mean(const float* eps_pair, float* eps, int B, int n, int nc, int start, int H, int mode,
+                               void* stream) {
+    API_BEGIN
+    if (n < 2 || nc < 0 || start <= 0) return fail(-2, "bad composition parameters");
+    if (mode != CINDM_COMPOSE_MEAN_INSIDE && mode != CINDM_COMPOSE_SUM_INSIDE) return fail(-2, "bad compose mode");
+    return launch_compose_scatter(eps_pair, eps, B, n, nc, start, H, mode, (cudaStream_t)stream);
+    API_END
+}
+
+int cindm_unet_forward(cindm_engine* e, const float* slices, int64_t S, int t, float* eps_pair, int precision,
+                       int conv_engine, void* stream) {
+    API_BEGIN
+    if (!e) return fail(-2, "null engine");
+    CINDM_TRY(reserve_workspace(e, S > e->ws.max_slices ? S : e->ws.max_slices, precision));
+    return unet_forward(e, slices, S, t, nullptr, eps_pair, precision, conv_engine, (cudaStream_t)stream);
+    API_END
+}
+
+int cindm_unet_enable_taps(cindm_engine* e, int enable) {
+    if (!e) return fail(-2, "null engine");
+    e->taps_enabled = enable != 0;
+    return 0;
+}
+
+
+int cindm_unet_read_tap(cindm_engine* e, const char* name, float* host, int64_t capacity, int64_t* s, int64_t* c,
+                        int64_t* h) {
+    API_BEGIN
+    if (!e || !name) return fail(-2, "null argument");
+    auto it = e->taps.find(name);
+    if (it == e->taps.end()) return fail(-7, std::string("no such tap: ") + name);
+    const Tap& tp = it->second;
+    if (s) *s = tp.s;
+    if (c) *c = tp.c;
+    if (h) *h = tp.h;
+    int64_t n = tp.s * tp.c * tp.h;
+    if (!host) return 0;
+    if (capacity < n) return fail(-2, "tap buffer too small");
+    float* tmp = nullptr;
+    CINDM_CHECK_CUDA(cudaMalloc(&tmp, n * sizeof(float)));
+    int blocks = (int)((n + 255) / 256);
+    if (tp.precision == PREC_F32) tap_to_f32_cf<float><<<blocks, 256>>>((const float*)tp.ptr, tmp, tp.s, tp.c, tp.h);
+    else if (tp.precision == PREC_F16) tap_to_f32_cf<__half><<<blocks, 256>>>((const __half*)tp.ptr, tmp, tp.s, tp.c, tp.h);
+    else tap_to_f32_cf<__nv_bfloat16><<<blocks, 256>>>((const __nv_bfloat16*)tp.ptr, tmp, tp.s, tp.c, tp.h);
+    cudaError_t ce = cudaMemcpy(host, tmp, n * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(tmp);
+    if (ce != cudaSuccess) return fail(-100, cudaGetErrorString(ce));
+    return 0;
+    API_END
+}
+
+int cindm_composed_eps(cindm_engine* e, const float* x, float* eps, int B, int n, int nc, int start, int mode, int t,
+                       int precision, int conv_engine, void* stream) {
+    API_BEGIN
+    if (!e) return fail(-2, "null engine");
+    if (n < 2 || nc < 0 || start <= 0) return fail(-2, "bad composition parameters");
+    const int64_t S = (int64_t)(nc + 1) * (n * (n - 1) / 2) * B;
+    CINDM_TRY(reserve_workspace(e, S > e->ws.max_slices ? S : e->ws.max_slices, precision));
+    return composed_eps(e, x, eps, B, n, nc, start, mode, t, nullptr, precision, conv_engine, (cudaStream_t)stream);
+    API_END
+}
+
+int cindm_design_grad(const float* x, float* g, int B, int T, int n, const cindm_objective* obj, void* stream) {
+    API_BEGIN
+    if (!obj) return fail(-2, "null objective");
+    if (T < 2) return fail(-2, "need at least two time steps");
+    return launch_design_grad(x, g, B, T, n, *obj, (cudaStream_t)stream);
+    API_END
+}
+
+int cindm_posterior_update(cindm_engine* e, const float* x, const float* eps, const float* noise, float* x_out,
+                           float* pred_out, float* x0_out, int B, int T, int n, int t, int renoise,
+                           const cindm_objective* obj, void* stream) {
+    API_BEGIN
+    if (!e) return fail(-2, "null engine");
+    if (t < 0 || t >= e->cfg.timesteps) return fail(-2, "timestep out of range");
+    UpdateLaunch u;
+    u.x = x; u.eps = eps; u.x_out = x_out; u.pred_out = pred_out; u.x0_out = x0_out;
+    u.B = B; u.T = T; u.n = n; u.sched = e->sched_dev; u.timesteps = e->cfg.timesteps;
+    u.t_host = t; u.renoise = renoise; u.noise = noise; u.t_start = t; u.draws_per_step = 1; u.draw = 0;
+    if (obj) u.obj = *obj;
+    else { memset(&u.obj, 0, sizeof(u.obj)); u.obj.guidance = CINDM_GUIDE_NONE; }
+    return launch_update(u, (cudaStream_t)stream);
+    API_END
+}
+
+int cindm_sample(cindm_engine* e, const cindm_sample_config* cfg, float* x, const float* noise, float* x0_out,
+                 void* stream) {
+    API_BEGIN
+    if (!e || !cfg || !x) return fail(-2, "null argument");
+    return sample_loop(e, *cfg, x, noise, x0_out, (cudaStream_t)stream);
+    API_END
+}
+
+int cindm_fill_initial_noise(float* x, int B, int T, int n, uint64_t seed, int64_t cand_off, int timesteps,
+                             void* stream) {
+    API_BEGIN
+    return launch_fill_noise(x, B, T, n, seed, cand_off, timesteps, 0xFFFF, (cudaStream_t)stream);
+    API_END
+}
+
+int cindm_nbody_rollout(const double* state0, double* traj, int B, int n, int n_steps, int stride, void* stream) {
+    API_BEGIN
+    return nbody_rollout(state0, traj, B, n, n_steps, stride, (cudaStream_t)stream);
+    API_END
+}
+
+int cindm_score_designs(const float* pred, float* mae, float* objective, int B, int T, int n, double tx, double ty,
+                        void* stream) {
+    API_BEGIN
+    return score_designs(pred, mae, objective, B, T, n, tx, ty, (cudaStream_t)stream);
+    API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,67 @@
+// Shared declarations for the cindm_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+
+namespace cindm {
+
+// Storage / operand precision of the U-Net activations.  Accumulation is always fp32.
+enum Precision { PREC_F32 = 0, PREC_F16 = 1, PREC_BF16 = 2 };
+
+void set_error(const std::string& msg);          // capi.cu; message returned by cindm_last_error()
+int fail(int code, const std::string& msg);      // records msg, returns code
+
+#define CINDM_CHECK_CUDA(expr)                                                              \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return ::cindm::fail(-100, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+#define CINDM_CHECK_LAUNCH()                                                                      \
+    do {                                                                                          \
+        cudaError_t _e = cudaGetLastError();                                                      \
+        if (_e != cudaSuccess)                                                                    \
+            return ::cindm::fail(-101, std::string("kernel launch (") + __FILE__ + ":" +          \
+                                           std::to_string(__LINE__) + "): " + cudaGetErrorString(_e)); \
+    } while (0)
+
+#define CINDM_TRY(expr)            \
+    do {                           \
+        int _rc = (expr);          \
+        if (_rc != 0) return _rc;  \
+    } while (0)
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// x * tanh(softplus(x)) exactly as torch evaluates nn.Mish in fp32 (reference model/diffusion_1d.py:210).
+__device__ __forceinline__ float mish_exact(float x) { return x * tanhf(log1pf(expf(x))); }
+
+// Same function with one ex2 and one rcp: tanh(log(1+w)) = (w^2+2w)/(w^2+2w+2), w = e^x.
+__device__ __forceinline__ float mish_fast(float x) {
+    float w = __expf(fminf(x, 20.0f));
+    float n = w * (w + 2.0f);
+    float r = __fdividef(n, n + 2.0f);
+    return x > 20.0f ? x : x * r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace cindm

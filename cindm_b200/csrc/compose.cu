@@ -1,0 +1,102 @@
+// The composition operator of GaussianDiffusion1D.model_predictions (reference
+// model/diffusion_1d.py:959-1001) as two bandwidth-bound kernels over precomputed index maps:
+//   gather : x[B][T][4n]            -> slices[(kk*P+p)*B + b][24][8]
+//   scatter: eps_pair[S][24][8]     -> eps[B][T][4n]   (mean over senders, mean over covering windows)
+// Both move 16-byte (one body's x,y,vx,vy) vectors; no atomics: every output element gathers
+// its own contributions in a fixed order, so the result is deterministic.
+#include "engine.h"
+
+namespace cindm {
+
+// pair index of (ii < jj) in lexicographic order
+__host__ __device__ __forceinline__ int pair_index(int ii, int jj, int n) {
+    return ii * (2 * n - ii - 1) / 2 + (jj - ii - 1);
+}
+
+__global__ void __launch_bounds__(256) compose_gather_kernel(const float4* __restrict__ x, float4* __restrict__ slices,
+                                                             int B, int n, int W, int start, int H, int T) {
+    // one thread per (slice, row, body-half): 16 bytes
+    const int P = n * (n - 1) / 2;
+    const long long total = (long long)W * P * B * H * 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int half = (int)(i & 1);
+        long long r = i >> 1;
+        int h = (int)(r % H);
+        long long s = r / H;
+        int b = (int)(s % B);
+        int wp = (int)(s / B);
+        int p = wp % P, kk = wp / P;
+        // invert the lexicographic pair index
+        int ii = 0, rem = p;
+        while (rem >= n - 1 - ii) { rem -= n - 1 - ii; ++ii; }
+        int jj = ii + 1 + rem;
+        int body = half ? jj : ii;
+        slices[i] = x[((long long)b * T + kk * start + h) * n + body];
+    }
+}
+
+__global__ void __launch_bounds__(256) compose_scatter_kernel(const float4* __restrict__ eps_pair, float4* __restrict__ eps,
+                                                              int B, int n, int W, int start, int H, int T, int mode) {
+    // one thread per (b, t, receiver): 16 bytes out, (n-1) * cover(t) 16-byte reads
+    const int P = n * (n - 1) / 2;
+    const long long total = (long long)B * T * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int r = (int)(i % n);
+        long long bt = i / n;
+        int t = (int)(bt % T);
+        int b = (int)(bt / T);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int cover = 0;
+        for (int kk = 0; kk < W; ++kk) {
+            int h = t - kk * start;
+            if (h < 0 || h >= H) continue;
+            ++cover;
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s = 0; s < n; ++s) {
+                if (s == r) continue;
+                int ii = r < s ? r : s, jj = r < s ? s : r;
+                int p = pair_index(ii, jj, n);
+                int half = (r == ii) ? 0 : 1;          // eps[..., :4] -> smaller index, [..., 4:] -> larger
+                long long slice = ((long long)kk * P + p) * B + b;
+                float4 v = eps_pair[(slice * H + h) * 2 + half];
+                w.x += v.x; w.y += v.y; w.z += v.z; w.w += v.w;
+            }
+            if (mode == CINDM_COMPOSE_MEAN_INSIDE) {
+                float d = (float)(n - 1);
+                w.x /= d; w.y /= d; w.z /= d; w.w /= d;
+            }
+            acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+        }
+        // mean-inside: / mask.sum(0) = cover;  sum-inside: / mask.mean(0) = cover / W   (:996, :999)
+        float div = mode == CINDM_COMPOSE_MEAN_INSIDE ? (float)cover : (float)cover / (float)W;
+        acc.x /= div; acc.y /= div; acc.z /= div; acc.w /= div;
+        eps[i] = acc;
+    }
+}
+
+int launch_compose_gather(const float* x, float* slices, int B, int n, int nc, int start, int H, cudaStream_t st) {
+    const int W = nc + 1, T = H + nc * start, P = n * (n - 1) / 2;
+    long long total = (long long)W * P * B * H * 2;
+    if (total == 0) return 0;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    compose_gather_kernel<<<blocks, 256, 0, st>>>((const float4*)x, (float4*)slices, B, n, W, start, H, T);
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
+int launch_compose_scatter(const float* eps_pair, float* eps, int B, int n, int nc, int start, int H, int mode,
+                           cudaStream_t st) {
+    const int W = nc + 1, T = H + nc * start;
+    long long total = (long long)B * T * n;
+    if (total == 0) return 0;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    compose_scatter_kernel<<<blocks, 256, 0, st>>>((const float4*)eps_pair, (float4*)eps, B, n, W, start, H, T, mode);
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace cindm

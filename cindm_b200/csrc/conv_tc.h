@@ -1,0 +1,26 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for 16-bit activations (see conv_tc.cu).
+#pragma once
+#include "engine.h"
+
+namespace cindm {
+
+enum { EPI_BIAS = 0, EPI_GN_MISH = 1 };
+
+struct ConvTcLaunch {
+    const void* in0 = nullptr; int c0 = 0;      // [S][H][c0] 16-bit
+    const void* in1 = nullptr; int c1 = 0;      // optional channel-concatenated second input
+    const ConvW* w = nullptr;                   // taps in {1, 5}, stride 1, pad taps/2
+    const NormW* gn = nullptr;                  // EPI_GN_MISH
+    const float* add_vec = nullptr;             // per-channel vector added after the activation
+    const int* t_dev = nullptr;                 // if set, add_vec is a [timesteps][cout] table indexed by *t_dev
+    const void* add_res = nullptr;              // residual tensor [S][H][cout] added last
+    void* out = nullptr;                        // [S][H][cout] 16-bit
+    int64_t S = 0;
+    int H = 0;
+    int prec = PREC_F16;
+    int epilogue = EPI_BIAS;
+};
+
+int launch_conv_tc(const ConvTcLaunch& a, cudaStream_t st);
+
+}  // namespace cindm

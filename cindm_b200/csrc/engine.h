@@ -1,0 +1,172 @@
+// Engine state: weights (fp32 masters + repacked operands), time-bias tables, workspace.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "../../include/cindm_b200.h"
+
+namespace cindm {
+
+struct HostTensor {
+    std::vector<int64_t> shape;
+    std::vector<float> data;
+};
+
+// One convolution's parameters.  `w` is the fp32 operand of the SIMT kernels, laid out
+// [tap][cin][cout]; `w16[p]` (p = PREC_F16 / PREC_BF16) is the K-major tensor-core operand
+// [tap][cout][cin] consumed through a TMA descriptor.
+struct ConvW {
+    int cin = 0, cout = 0, taps = 0;
+    float* w = nullptr;
+    float* bias = nullptr;        // [cout] or null
+    void* w16[3] = {nullptr, nullptr, nullptr};
+};
+
+struct NormW {
+    float* gamma = nullptr;
+    float* beta = nullptr;
+};
+
+struct ResBlockW {               // ResidualTemporalBlock, reference model/diffusion_1d.py:483-511
+    ConvW conv0, conv1, res;
+    NormW gn0, gn1;
+    bool has_res = false;
+    float* time_bias = nullptr;  // [timesteps][cout]: Linear(Mish(time_mlp(t))) precomputed per t
+    std::string name;
+};
+
+struct AttnW {                   // Residual(PreNorm(LayerNorm, LinearAttentionTemporal)) :272-291
+    float* g = nullptr;          // [C]
+    ConvW qkv, out;
+    std::string name;
+};
+
+struct Workspace {
+    int64_t max_slices = 0;
+    int precision = -1;
+    void* act[3] = {nullptr, nullptr, nullptr};
+    void* skip[3] = {nullptr, nullptr, nullptr};
+    void* res = nullptr;
+    void* ln = nullptr;
+    void* qkv = nullptr;
+    void* att = nullptr;
+    float* scratch = nullptr;    // fp32 pre-norm conv output (SIMT path)
+    float* slices = nullptr;     // [S][24][8] gathered model inputs
+    float* eps_pair = nullptr;   // [S][24][8] per-slice model outputs
+    void* base = nullptr;        // single allocation everything above points into
+    size_t bytes = 0;
+};
+
+struct SampleBuffers {           // sized by cindm_sample on first use
+    size_t elems = 0;
+    float* x_alt = nullptr;
+    float* pred = nullptr;
+    float* eps = nullptr;
+    int* t_dev = nullptr;
+};
+
+struct Tap {
+    void* ptr;
+    int c, h;
+    int precision;               // element type of ptr
+    int64_t s;
+};
+
+}  // namespace cindm
+
+struct cindm_engine {
+    cindm_config cfg;
+    std::map<std::string, cindm::HostTensor> host_weights;
+    bool finalized = false;
+
+    // device weights
+    std::vector<void*> allocations;
+    cindm::ResBlockW downs_rb[4][2], ups_rb[3][2], mid_rb[2];
+    cindm::AttnW downs_at[4], ups_at[3], mid_at;
+    cindm::ConvW down_conv[3], up_conv[3];
+    cindm::ConvW final_block;
+    cindm::NormW final_gn;
+    cindm::ConvW final_out;
+    float* temb_table = nullptr;           // [timesteps][dim]
+
+    // schedule (device, 13 x timesteps) and host copy
+    float* sched_dev = nullptr;
+    std::vector<float> sched_host;
+
+    cindm::Workspace ws;
+    cindm::SampleBuffers sb;
+
+    bool taps_enabled = false;
+    std::map<std::string, cindm::Tap> taps;
+    std::vector<void*> tap_allocs;
+};
+
+namespace cindm {
+
+// schedule table indices (order of cindm_schedule_tables)
+enum {
+    TAB_BETAS = 0, TAB_ACP, TAB_ACP_PREV, TAB_SQRT_ACP, TAB_SQRT_1M_ACP, TAB_LOG_1M_ACP, TAB_SQRT_RECIP_ACP,
+    TAB_SQRT_RECIPM1_ACP, TAB_POST_VAR, TAB_POST_LOGVAR, TAB_POST_C1, TAB_POST_C2, TAB_LOSS_W, TAB_COUNT
+};
+
+// ---- launchers (each returns 0 or a negative error code) -------------------------------------
+
+struct ConvLaunch {
+    const void* in0 = nullptr; int c0 = 0;      // [S][Hin][c0]
+    const void* in1 = nullptr; int c1 = 0;      // optional channel-concatenated second input
+    const ConvW* w = nullptr;
+    const void* res = nullptr;                  // optional residual [S][Hout][cout], same type as out
+    void* out = nullptr;
+    int64_t S = 0;
+    int Hin = 0, Hout = 0, stride = 1, pad = 0, transposed = 0;
+    int in_prec = PREC_F32, out_prec = PREC_F32;
+};
+int launch_conv_simt(const ConvLaunch& a, cudaStream_t st);
+
+// GroupNorm(8) + Mish over fp32 pre-norm activations, then + per-channel vector or + residual tensor
+// add_vec: per-channel vector; when t_dev != nullptr the row (*t_dev) of a [timesteps][C] table at add_vec
+int launch_gn_mish(const float* in, const NormW& gn, const float* add_vec, const int* t_dev, const void* add_res,
+                   void* out, int64_t S, int H, int C, int out_prec, cudaStream_t st);
+int launch_layernorm(const void* in, const float* g, void* out, int64_t rows, int C, int prec, cudaStream_t st);
+int launch_attn_core(const void* qkv, void* out, int64_t S, int n, int prec, cudaStream_t st);
+int launch_time_tables(cindm_engine* e, cudaStream_t st);
+
+// t_dev == nullptr: use the host value t; else the device integer *t_dev (CUDA-graph replay)
+int unet_forward(cindm_engine* e, const float* slices, int64_t S, int t, const int* t_dev, float* eps_pair,
+                 int precision, int conv_engine, cudaStream_t st);
+
+int launch_compose_gather(const float* x, float* slices, int B, int n, int nc, int start, int H, cudaStream_t st);
+int launch_compose_scatter(const float* eps_pair, float* eps, int B, int n, int nc, int start, int H, int mode,
+                           cudaStream_t st);
+int launch_design_grad(const float* x, float* g, int B, int T, int n, const cindm_objective& obj, cudaStream_t st);
+
+struct UpdateLaunch {
+    const float* x = nullptr; const float* eps = nullptr;
+    float* x_out = nullptr; float* pred_out = nullptr; float* x0_out = nullptr;
+    int B = 0, T = 0, n = 0;
+    const float* sched = nullptr; int timesteps = 0;   // device tables [13][timesteps]
+    const int* t_dev = nullptr; int t_host = 0;        // *t_dev (if non-null) overrides t_host
+    int renoise = 0;                                   // 1: recurrence re-noise, 0: final posterior noise
+    // noise source: explicit tensor (noise + ((t_start - t)*draws_per_step + draw) * B*T*4n), or Philox
+    const float* noise = nullptr; int t_start = 0, draws_per_step = 0, draw = 0;
+    int use_philox = 0; uint64_t seed = 0; int64_t cand_off = 0;
+    cindm_objective obj;
+};
+int launch_update(const UpdateLaunch& u, cudaStream_t st);
+int launch_fill_noise(float* x, int B, int T, int n, uint64_t seed, int64_t cand_off, int t, int draw,
+                      cudaStream_t st);
+int launch_step_counter(int* t_dev, int delta, cudaStream_t st);
+
+int finalize_weights(cindm_engine* e, cudaStream_t st);
+int reserve_workspace(cindm_engine* e, int64_t S, int prec);
+int64_t workspace_bytes(int64_t S, int prec, int horizon);
+int composed_eps(cindm_engine* e, const float* x, float* eps, int B, int n, int nc, int start, int mode, int t,
+                 const int* t_dev, int prec, int conv_engine, cudaStream_t st);
+int sample_loop(cindm_engine* e, const cindm_sample_config& cfg, float* x, const float* noise, float* x0_out,
+                cudaStream_t st);
+
+size_t elem_size(int prec);
+
+}  // namespace cindm

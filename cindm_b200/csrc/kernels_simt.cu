@@ -1,0 +1,402 @@
+// SIMT (fp32 FMA) kernels of the temporal U-Net: the parity-grade path, plus the small
+// per-slice operators (GroupNorm+Mish, channel LayerNorm, linear attention core) that both
+// precisions share.  Activations are channels-last: [S][H][C].
+#include "engine.h"
+
+namespace cindm {
+
+size_t elem_size(int prec) { return prec == PREC_F32 ? 4 : 2; }
+
+// ------------------------------------------------------------------------------------------
+// conv1d as a tiled fp32 GEMM:  out[s][j][co] = bias[co] + sum_{tap,ci} W[tap][ci][co] * in[s][pos(j,tap)][ci]
+//   normal     : pos = j*stride + tap - pad                       (nn.Conv1d, reference :95, :206, :499)
+//   transposed : pos = (j + pad - tap)/stride when divisible       (nn.ConvTranspose1d, reference :103)
+// Tile 64 rows (flattened s*Hout+j) x 64 output channels, K chunks of 16, 256 threads x (4x4).
+// ------------------------------------------------------------------------------------------
+struct ConvParams {
+    const void* in0; const void* in1; const float* w; const float* bias; const void* res; void* out;
+    long long rows;          // S * Hout
+    int c0, c1, cin, cout, taps, Hin, Hout, stride, pad, transposed;
+};
+
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(256) conv1d_simt_kernel(ConvParams p) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Bs[16][64];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const long long row0 = (long long)blockIdx.x * 64;
+    const int co0 = blockIdx.y * 64;
+
+    // A-load role: 4 consecutive input channels of one row
+    const int a_row = tid >> 2, a_ci = (tid & 3) * 4;
+    const long long arow = row0 + a_row;
+    const bool arow_ok = arow < p.rows;
+    const long long a_s = arow_ok ? arow / p.Hout : 0;
+    const int a_j = arow_ok ? (int)(arow - a_s * p.Hout) : 0;
+    // B-load role: 4 consecutive output channels of one input channel
+    const int b_ci = tid >> 4, b_co = (tid & 15) * 4;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int tap = 0; tap < p.taps; ++tap) {
+        int pos;
+        bool pos_ok;
+        if (!p.transposed) {
+            pos = a_j * p.stride + tap - p.pad;
+            pos_ok = pos >= 0 && pos < p.Hin;
+        } else {
+            int q = a_j + p.pad - tap;
+            pos_ok = q >= 0 && (q % p.stride) == 0;
+            pos = q / p.stride;
+            pos_ok = pos_ok && pos < p.Hin;
+        }
+        pos_ok = pos_ok && arow_ok;
+        for (int ci0 = 0; ci0 < p.cin; ci0 += 16) {
+            // ---- stage A (transposed into As[ci][row]) ----
+            float av[4] = {0.f, 0.f, 0.f, 0.f};
+            if (pos_ok && ci0 + a_ci < p.cin) {
+                int ci = ci0 + a_ci;
+                const InT* src;
+                int cw, cbase;
+                if (ci < p.c0) { src = (const InT*)p.in0; cw = p.c0; cbase = ci; }
+                else           { src = (const InT*)p.in1; cw = p.c1; cbase = ci - p.c0; }
+                const InT* ptr = src + ((a_s * p.Hin + pos) * (long long)cw + cbase);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (ci + q < p.cin) av[q] = to_f32<InT>(ptr[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) As[a_ci + q][a_row] = av[q];
+            // ---- stage B ----
+            {
+                int ci = ci0 + b_ci;
+                float bv[4] = {0.f, 0.f, 0.f, 0.f};
+                if (ci < p.cin) {
+                    const float* wp = p.w + ((long long)tap * p.cin + ci) * p.cout + co0 + b_co;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (co0 + b_co + q < p.cout) bv[q] = wp[q];
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) Bs[b_ci][b_co + q] = bv[q];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) {
+                float a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+    // ---- epilogue ----
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        long long r = row0 + ty * 4 + i;
+        if (r >= p.rows) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int co = co0 + tx * 4 + j;
+            if (co >= p.cout) continue;
+            float v = acc[i][j];
+            if (p.bias) v += p.bias[co];
+            if (p.res) v += to_f32<OutT>(((const OutT*)p.res)[r * p.cout + co]);
+            ((OutT*)p.out)[r * p.cout + co] = from_f32<OutT>(v);
+        }
+    }
+}
+
+template <typename InT, typename OutT>
+static int conv_dispatch2(const ConvParams& p, cudaStream_t st) {
+    dim3 grid(ceil_div(p.rows, 64), ceil_div(p.cout, 64));
+    conv1d_simt_kernel<InT, OutT><<<grid, 256, 0, st>>>(p);
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
+template <typename InT>
+static int conv_dispatch1(const ConvParams& p, int out_prec, cudaStream_t st) {
+    switch (out_prec) {
+        case PREC_F32: return conv_dispatch2<InT, float>(p, st);
+        case PREC_F16: return conv_dispatch2<InT, __half>(p, st);
+        case PREC_BF16: return conv_dispatch2<InT, __nv_bfloat16>(p, st);
+    }
+    return fail(-2, "conv: bad output precision");
+}
+
+int launch_conv_simt(const ConvLaunch& a, cudaStream_t st) {
+    ConvParams p;
+    p.in0 = a.in0; p.in1 = a.in1; p.c0 = a.c0; p.c1 = a.in1 ? a.c1 : 0;
+    p.w = a.w->w; p.bias = a.w->bias; p.res = a.res; p.out = a.out;
+    p.cin = a.w->cin; p.cout = a.w->cout; p.taps = a.w->taps;
+    p.Hin = a.Hin; p.Hout = a.Hout; p.stride = a.stride; p.pad = a.pad; p.transposed = a.transposed;
+    p.rows = a.S * a.Hout;
+    if (p.c0 + p.c1 != p.cin) return fail(-2, "conv: input channels do not match the weight");
+    if (p.in1 && (p.c0 % 16) != 0) return fail(-2, "conv: concat split must be a multiple of 16 channels");
+    if (p.rows == 0) return 0;
+    switch (a.in_prec) {
+        case PREC_F32: return conv_dispatch1<float>(p, a.out_prec, st);
+        case PREC_F16: return conv_dispatch1<__half>(p, a.out_prec, st);
+        case PREC_BF16: return conv_dispatch1<__nv_bfloat16>(p, a.out_prec, st);
+    }
+    return fail(-2, "conv: bad input precision");
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm(8 groups, eps 1e-5, affine) + Mish + (per-channel vector | residual tensor).
+// One warp per (slice, group); the group's H * C/8 values are read twice (mean, then centred
+// variance) — the statistics the reference's nn.GroupNorm on [S,C,1,H] computes (:207-209).
+// ------------------------------------------------------------------------------------------
+template <typename OutT>
+__global__ void __launch_bounds__(256) gn_mish_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, const float* __restrict__ add_vec,
+                                                      const int* __restrict__ t_dev,
+                                                      const OutT* __restrict__ add_res, OutT* __restrict__ out,
+                                                      long long S, int H, int C) {
+    if (add_vec && t_dev) add_vec += (long long)(*t_dev) * C;
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gw >= S * 8) return;
+    const long long s = gw >> 3;
+    const int g = (int)(gw & 7);
+    const int cpg = C >> 3;
+    const int count = H * cpg;
+    const float* base = in + s * (long long)H * C + g * cpg;
+    float sum = 0.f;
+    for (int e = lane; e < count; e += 32) {
+        int h = e / cpg, c = e - h * cpg;
+        sum += base[h * C + c];
+    }
+    const float mean = warp_sum(sum) / (float)count;
+    float sq = 0.f;
+    for (int e = lane; e < count; e += 32) {
+        int h = e / cpg, c = e - h * cpg;
+        float d = base[h * C + c] - mean;
+        sq = fmaf(d, d, sq);
+    }
+    const float var = warp_sum(sq) / (float)count;
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    for (int e = lane; e < count; e += 32) {
+        int h = e / cpg, c = e - h * cpg;
+        int ch = g * cpg + c;
+        float v = (base[h * C + c] - mean) * rstd * gamma[ch] + beta[ch];
+        v = mish_exact(v);
+        long long o = (s * H + h) * (long long)C + ch;
+        if (add_vec) v += add_vec[ch];
+        if (add_res) v += to_f32<OutT>(add_res[o]);
+        out[o] = from_f32<OutT>(v);
+    }
+}
+
+int launch_gn_mish(const float* in, const NormW& gn, const float* add_vec, const int* t_dev, const void* add_res,
+                   void* out, int64_t S, int H, int C, int out_prec, cudaStream_t st) {
+    if (S == 0) return 0;
+    int blocks = ceil_div(S * 8, 8);
+    switch (out_prec) {
+        case PREC_F32:
+            gn_mish_kernel<float><<<blocks, 256, 0, st>>>(in, gn.gamma, gn.beta, add_vec, t_dev, (const float*)add_res,
+                                                         (float*)out, S, H, C);
+            break;
+        case PREC_F16:
+            gn_mish_kernel<__half><<<blocks, 256, 0, st>>>(in, gn.gamma, gn.beta, add_vec, t_dev, (const __half*)add_res,
+                                                          (__half*)out, S, H, C);
+            break;
+        case PREC_BF16:
+            gn_mish_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(in, gn.gamma, gn.beta, add_vec, t_dev,
+                                                                 (const __nv_bfloat16*)add_res,
+                                                                 (__nv_bfloat16*)out, S, H, C);
+            break;
+        default: return fail(-2, "gn_mish: bad precision");
+    }
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Channel LayerNorm (gain only, biased variance, eps 1e-5): reference LayerNorm :123-132.
+// One warp per (slice, position) row of C channels.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ in, const float* __restrict__ g,
+                                                        T* __restrict__ out, long long rows, int C) {
+    const int lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const T* x = in + r * C;
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) sum += to_f32<T>(x[c]);
+    const float mean = warp_sum(sum) / (float)C;
+    float sq = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        float d = to_f32<T>(x[c]) - mean;
+        sq = fmaf(d, d, sq);
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)C + 1e-5f);
+    for (int c = lane; c < C; c += 32) out[r * C + c] = from_f32<T>((to_f32<T>(x[c]) - mean) * rstd * g[c]);
+}
+
+int launch_layernorm(const void* in, const float* g, void* out, int64_t rows, int C, int prec, cudaStream_t st) {
+    if (rows == 0) return 0;
+    int blocks = ceil_div(rows, 8);
+    switch (prec) {
+        case PREC_F32: layernorm_kernel<float><<<blocks, 256, 0, st>>>((const float*)in, g, (float*)out, rows, C); break;
+        case PREC_F16: layernorm_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)in, g, (__half*)out, rows, C); break;
+        case PREC_BF16:
+            layernorm_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in, g, (__nv_bfloat16*)out, rows, C);
+            break;
+        default: return fail(-2, "layernorm: bad precision");
+    }
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Linear attention core (4 heads x 32), reference LinearAttentionTemporal.forward :281-291:
+//   q *= 32^-0.5;  k = softmax_n(k);  ctx[d][e] = sum_n k[d][n] v[e][n];  out[e][n] = sum_d ctx[d][e] q[d][n]
+// qkv: [S][n][384] (q | k | v, each head-major 4 x 32);  out: [S][n][128].  One CTA per slice.
+// ------------------------------------------------------------------------------------------
+template <typename T, int NMAX>
+__global__ void __launch_bounds__(128) attn_core_kernel(const T* __restrict__ qkv, T* __restrict__ out, int n) {
+    extern __shared__ float attn_smem[];
+    float (*sq)[NMAX + 1] = reinterpret_cast<float (*)[NMAX + 1]>(attn_smem);
+    float (*sk)[NMAX + 1] = sq + 128;
+    float (*sv)[NMAX + 1] = sk + 128;
+    float (*ctx)[32][33] = reinterpret_cast<float (*)[32][33]>(attn_smem + 3 * 128 * (NMAX + 1));
+    const long long s = blockIdx.x;
+    const int tid = threadIdx.x;
+    const T* src = qkv + s * (long long)n * 384;
+    for (int i = tid; i < n * 384; i += 128) {
+        int pos = i / 384, c = i - pos * 384;
+        float v = to_f32<T>(src[i]);
+        if (c < 128) sq[c][pos] = v * 0.17677669529663687f;      // 32^-0.5
+        else if (c < 256) sk[c - 128][pos] = v;
+        else sv[c - 256][pos] = v;
+    }
+    __syncthreads();
+    {   // softmax over positions for k row `tid`
+        float m = -INFINITY;
+        for (int j = 0; j < n; ++j) m = fmaxf(m, sk[tid][j]);
+        float sum = 0.f;
+        for (int j = 0; j < n; ++j) {
+            float e = expf(sk[tid][j] - m);
+            sk[tid][j] = e;
+            sum += e;
+        }
+        float inv = 1.0f / sum;
+        for (int j = 0; j < n; ++j) sk[tid][j] *= inv;
+    }
+    __syncthreads();
+    const int h = tid >> 5, d = tid & 31;
+    for (int e = 0; e < 32; ++e) {
+        float a = 0.f;
+        for (int j = 0; j < n; ++j) a = fmaf(sk[tid][j], sv[h * 32 + e][j], a);
+        ctx[h][d][e] = a;
+    }
+    __syncthreads();
+    T* dst = out + s * (long long)n * 128;
+    for (int j = 0; j < n; ++j) {
+        float a = 0.f;
+#pragma unroll 8
+        for (int dd = 0; dd < 32; ++dd) a = fmaf(ctx[h][dd][d], sq[h * 32 + dd][j], a);
+        dst[j * 128 + tid] = from_f32<T>(a);
+    }
+}
+
+int launch_attn_core(const void* qkv, void* out, int64_t S, int n, int prec, cudaStream_t st) {
+    if (S == 0) return 0;
+    if (n > 24) return fail(-2, "attention core supports at most 24 positions");
+    const size_t smem = (3 * 128 * 25 + 4 * 32 * 33) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_kernel<float, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_kernel<__half, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_kernel<__nv_bfloat16, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    switch (prec) {
+        case PREC_F32: attn_core_kernel<float, 24><<<(unsigned)S, 128, smem, st>>>((const float*)qkv, (float*)out, n); break;
+        case PREC_F16: attn_core_kernel<__half, 24><<<(unsigned)S, 128, smem, st>>>((const __half*)qkv, (__half*)out, n); break;
+        case PREC_BF16:
+            attn_core_kernel<__nv_bfloat16, 24><<<(unsigned)S, 128, smem, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, n);
+            break;
+        default: return fail(-2, "attn: bad precision");
+    }
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Time embedding tables.  `time` is identical for every slice of a forward (reference
+// p_sample_compose_inside :1287 builds torch.full((b,), t)), so time_mlp (:537-542) and every
+// block's Mish->Linear (:493-497) depend on t only: evaluate them once for t = 0..T-1.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) temb_table_kernel(const float* __restrict__ w1, const float* __restrict__ b1,
+                                                         const float* __restrict__ w3, const float* __restrict__ b3,
+                                                         float* __restrict__ table, int dim) {
+    extern __shared__ float sm[];
+    float* emb = sm;            // [dim]
+    float* hid = sm + dim;      // [4*dim]
+    const int t = blockIdx.x;
+    const int half = dim / 2;
+    const float step = (float)(-(log(10000.0) / (double)(half - 1)));
+    for (int i = threadIdx.x; i < half; i += blockDim.x) {
+        float f = expf((float)i * step);
+        float a = (float)t * f;
+        emb[i] = sinf(a);
+        emb[half + i] = cosf(a);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 4 * dim; o += blockDim.x) {
+        float a = b1[o];
+        for (int i = 0; i < dim; ++i) a = fmaf(w1[o * dim + i], emb[i], a);
+        hid[o] = mish_exact(a);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < dim; o += blockDim.x) {
+        float a = b3[o];
+        for (int i = 0; i < 4 * dim; ++i) a = fmaf(w3[o * 4 * dim + i], hid[i], a);
+        table[(long long)t * dim + o] = a;
+    }
+}
+
+__global__ void __launch_bounds__(128) block_time_bias_kernel(const float* __restrict__ temb, const float* __restrict__ w,
+                                                              const float* __restrict__ b, float* __restrict__ out,
+                                                              int dim, int cout) {
+    extern __shared__ float sm[];
+    const int t = blockIdx.x;
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) sm[i] = mish_exact(temb[(long long)t * dim + i]);
+    __syncthreads();
+    for (int o = threadIdx.x; o < cout; o += blockDim.x) {
+        float a = b[o];
+        for (int i = 0; i < dim; ++i) a = fmaf(w[o * dim + i], sm[i], a);
+        out[(long long)t * cout + o] = a;
+    }
+}
+
+int launch_temb_table(const float* w1, const float* b1, const float* w3, const float* b3, float* table, int dim,
+                      int timesteps, cudaStream_t st) {
+    temb_table_kernel<<<timesteps, 256, 5 * dim * sizeof(float), st>>>(w1, b1, w3, b3, table, dim);
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
+int launch_block_time_bias(const float* temb, const float* w, const float* b, float* out, int dim, int cout,
+                           int timesteps, cudaStream_t st) {
+    block_time_bias_kernel<<<timesteps, 128, dim * sizeof(float), st>>>(temb, w, b, out, dim, cout);
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace cindm

@@ -1,0 +1,340 @@
+// Guidance gradient, fused DDPM update and the reverse-diffusion loop.
+//
+// One DDPM step of p_sample_compose_inside (reference model/diffusion_1d.py:1189-1376, SURVEY
+// Appendix B) is:   repeat R x { eps = compose(x);  pred = mu(x, eps) - g(x);  x = renoise(pred) }
+// then out = pred + sigma_t * noise.   Here everything after `eps` is ONE kernel per evaluation
+// (x0 + clamp + posterior mean + closed-form objective gradient + re-noise / final noise), the
+// noise comes either from a caller-supplied tensor (parity runs) or from Philox4x32-10 keyed by
+// (seed, global candidate id, t, draw) so results do not depend on how candidates are sharded,
+// and the whole step is captured once in a CUDA graph and replayed with a device-resident t.
+#include "engine.h"
+
+namespace cindm {
+
+// ---------------------------------------------------------------- Philox4x32-10 + Box-Muller
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+    uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+    uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+    uint32_t c[4] = {c0, c1, c2, c3};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    const float two_pow_m32 = 2.3283064365386963e-10f;
+    float u0 = fmaf((float)c[0], two_pow_m32, 0.5f * two_pow_m32);
+    float u1 = fmaf((float)c[1], two_pow_m32, 0.5f * two_pow_m32);
+    float u2 = fmaf((float)c[2], two_pow_m32, 0.5f * two_pow_m32);
+    float u3 = fmaf((float)c[3], two_pow_m32, 0.5f * two_pow_m32);
+    u0 = fminf(u0, 0.99999994f); u2 = fminf(u2, 0.99999994f);
+    float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
+    float s0, c0f, s1, c1f;
+    __sincosf(6.283185307179586f * u1, &s0, &c0f);
+    __sincosf(6.283185307179586f * u3, &s1, &c1f);
+    return make_float4(r0 * c0f, r0 * s0, r1 * c1f, r1 * s1);
+}
+
+// counter layout: (element/4 within the candidate, global candidate id lo, candidate hi, (t << 16) | draw)
+__device__ __forceinline__ float4 noise4(uint64_t seed, long long cand, int vec_in_cand, int t, int draw) {
+    return philox_normal4(seed, (uint32_t)vec_in_cand, (uint32_t)cand, (uint32_t)((unsigned long long)cand >> 32),
+                          ((uint32_t)t << 16) | (uint32_t)(draw & 0xFFFF));
+}
+
+__global__ void __launch_bounds__(256) fill_noise_kernel(float4* __restrict__ x, long long nvec, int vec_per_cand,
+                                                         uint64_t seed, long long cand_off, int t, int draw) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        long long b = i / vec_per_cand;
+        int v = (int)(i - b * vec_per_cand);
+        x[i] = noise4(seed, cand_off + b, v, t, draw);
+    }
+}
+
+int launch_fill_noise(float* x, int B, int T, int n, uint64_t seed, int64_t cand_off, int t, int draw, cudaStream_t st) {
+    long long nvec = (long long)B * T * n;
+    if (nvec == 0) return 0;
+    int blocks = (int)((nvec + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    fill_noise_kernel<<<blocks, 256, 0, st>>>((float4*)x, nvec, T * n, seed, cand_off, t, draw);
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
+__global__ void step_counter_kernel(int* t, int delta) { *t += delta; }
+int launch_step_counter(int* t_dev, int delta, cudaStream_t st) {
+    step_counter_kernel<<<1, 1, 0, st>>>(t_dev, delta);
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---------------------------------------------------------------- objective gradient (closed form)
+// J = coef * sum_b sum_j d(p[b,T-1,j], target) + cc * sum_b mean_t sum_{j,xy} (p[t+1]-p[t])^2
+//   d = ||.||_2 (L2) or ||.||^2 (L2square); the distance term is evaluated in fp64 because the
+//   driver's target tensor is fp64 (inference/inverse_design_diffusion_1d.py:281), the consistency
+//   term in fp32; velocities get no gradient.  Returns (dJ/dx, dJ/dy) of body j at (b, t).
+__device__ __forceinline__ float2 objective_grad(const float* __restrict__ x, long long bt_base, int t, int T, int F,
+                                                 int j, float px, float py, const cindm_objective& o) {
+    float gx = 0.f, gy = 0.f;
+    if (o.consistency_coef > 0.f) {
+        const float k = o.consistency_coef / (float)(T - 1);
+        if (t >= 1) {
+            const float* q = x + bt_base - F + 4 * j;
+            gx = __fmul_rn(__fmul_rn(__fsub_rn(px, q[0]), 2.0f), k);
+            gy = __fmul_rn(__fmul_rn(__fsub_rn(py, q[1]), 2.0f), k);
+        }
+        if (t <= T - 2) {
+            const float* q = x + bt_base + F + 4 * j;
+            gx = __fsub_rn(gx, __fmul_rn(__fmul_rn(__fsub_rn(q[0], px), 2.0f), k));
+            gy = __fsub_rn(gy, __fmul_rn(__fmul_rn(__fsub_rn(q[1], py), 2.0f), k));
+        }
+    }
+    if (t == T - 1) {
+        double dx = (double)px - o.target_x, dy = (double)py - o.target_y;
+        double lx, ly;
+        if (o.mode == CINDM_OBJ_L2) {
+            double nrm = sqrt(dx * dx + dy * dy);
+            lx = (double)o.coef * dx / nrm;          // 0/0 -> NaN, as autograd produces
+            ly = (double)o.coef * dy / nrm;
+        } else {
+            lx = (double)o.coef * 2.0 * dx;
+            ly = (double)o.coef * 2.0 * dy;
+        }
+        gx = __fadd_rn(gx, (float)lx);
+        gy = __fadd_rn(gy, (float)ly);
+    }
+    return make_float2(gx, gy);
+}
+
+__global__ void __launch_bounds__(256) design_grad_kernel(const float* __restrict__ x, float* __restrict__ g, int B, int T,
+                                                          int n, cindm_objective o) {
+    const long long total = (long long)B * T * n;
+    const int F = 4 * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int j = (int)(i % n);
+        long long bt = i / n;
+        int t = (int)(bt % T);
+        float4 v = reinterpret_cast<const float4*>(x)[i];
+        float2 gr = objective_grad(x, bt * F, t, T, F, j, v.x, v.y, o);
+        reinterpret_cast<float4*>(g)[i] = make_float4(gr.x, gr.y, 0.f, 0.f);
+    }
+}
+
+int launch_design_grad(const float* x, float* g, int B, int T, int n, const cindm_objective& obj, cudaStream_t st) {
+    long long total = (long long)B * T * n;
+    if (total == 0) return 0;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    design_grad_kernel<<<blocks, 256, 0, st>>>(x, g, B, T, n, obj);
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---------------------------------------------------------------- fused DDPM update
+struct UpdateParams {
+    const float* x; const float* eps; const float* noise; float* x_out; float* pred_out; float* x0_out;
+    const float* sched; const int* t_dev;
+    long long cand_off; unsigned long long seed;
+    int B, T, n, timesteps, t_host, renoise, t_start, draws_per_step, draw, use_philox;
+    cindm_objective obj;
+};
+
+__global__ void __launch_bounds__(256) ddpm_update_kernel(UpdateParams p) {
+    const int t = p.t_dev ? *p.t_dev : p.t_host;
+    const int TS = p.timesteps;
+    // coefficients, read from the fp32 buffers exactly as `extract` does (reference :454-462)
+    const float A = p.sched[TAB_SQRT_RECIP_ACP * TS + t];
+    const float Bc = p.sched[TAB_SQRT_RECIPM1_ACP * TS + t];
+    const float c1 = p.sched[TAB_POST_C1 * TS + t];
+    const float c2 = p.sched[TAB_POST_C2 * TS + t];
+    float gscale = 0.f;
+    if (p.obj.guidance == CINDM_GUIDE_STANDARD) gscale = 1.f;
+    else if (p.obj.guidance == CINDM_GUIDE_STANDARD_ALPHA)
+        gscale = __fdiv_rn(p.sched[TAB_BETAS * TS + t], __fsqrt_rn(p.sched[TAB_ACP_PREV * TS + t]));
+    float na, nb;   // out = na * pred + nb * noise
+    if (p.renoise) {
+        float ratio = __fdiv_rn(p.sched[TAB_ACP * TS + t], p.sched[TAB_ACP_PREV * TS + t]);   // fp32 ratio (:1366)
+        na = __fsqrt_rn(ratio);
+        nb = __fsqrt_rn(__fsub_rn(1.0f, ratio));
+    } else {
+        na = 1.0f;
+        nb = (t > 0) ? expf(__fmul_rn(0.5f, p.sched[TAB_POST_LOGVAR * TS + t])) : 0.f;       // no noise at t == 0
+    }
+    const bool have_noise = nb != 0.f && (p.noise != nullptr || p.use_philox);
+    const float4* noise = nullptr;
+    if (p.noise)
+        noise = reinterpret_cast<const float4*>(
+            p.noise + ((long long)(p.t_start - t) * p.draws_per_step + p.draw) * ((long long)p.B * p.T * p.n * 4));
+
+    const long long total = (long long)p.B * p.T * p.n;
+    const int F = 4 * p.n;
+    const int vec_per_cand = p.T * p.n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int j = (int)(i % p.n);
+        long long bt = i / p.n;
+        int tt = (int)(bt % p.T);
+        long long b = bt / p.T;
+        float4 xv = reinterpret_cast<const float4*>(p.x)[i];
+        float4 ev = reinterpret_cast<const float4*>(p.eps)[i];
+        float xs[4] = {xv.x, xv.y, xv.z, xv.w}, es[4] = {ev.x, ev.y, ev.z, ev.w};
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
+        if (gscale != 0.f) {
+            float2 gr = objective_grad(p.x, bt * F, tt, p.T, F, j, xv.x, xv.y, p.obj);
+            g[0] = gr.x; g[1] = gr.y;
+            if (p.obj.guidance == CINDM_GUIDE_STANDARD_ALPHA) { g[0] = __fmul_rn(gscale, g[0]); g[1] = __fmul_rn(gscale, g[1]); }
+        }
+        float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (have_noise) nz = noise ? noise[i] : noise4(p.seed, p.cand_off + b, (int)(i - b * vec_per_cand), t, p.draw);
+        float ns[4] = {nz.x, nz.y, nz.z, nz.w};
+        float x0[4], pr[4], out[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float v = __fsub_rn(__fmul_rn(A, xs[q]), __fmul_rn(Bc, es[q]));                 // (:914-918)
+            v = fminf(fmaxf(v, -1.0f), 1.0f);                                               // clamp_(-1, 1) (:1039)
+            x0[q] = v;
+            float mu = __fadd_rn(__fmul_rn(c1, v), __fmul_rn(c2, xs[q]));                   // (:943-946)
+            pr[q] = __fsub_rn(mu, g[q]);                                                    // (:1349)
+            out[q] = have_noise ? __fadd_rn(__fmul_rn(na, pr[q]), __fmul_rn(nb, ns[q])) : __fmul_rn(na, pr[q]);
+        }
+        reinterpret_cast<float4*>(p.x_out)[i] = make_float4(out[0], out[1], out[2], out[3]);
+        if (p.pred_out) reinterpret_cast<float4*>(p.pred_out)[i] = make_float4(pr[0], pr[1], pr[2], pr[3]);
+        if (p.x0_out) reinterpret_cast<float4*>(p.x0_out)[i] = make_float4(x0[0], x0[1], x0[2], x0[3]);
+    }
+}
+
+int launch_update(const UpdateLaunch& u, cudaStream_t st) {
+    if (!u.sched) return fail(-4, "schedule tables not set (cindm_set_schedule)");
+    if (u.x == u.x_out) return fail(-2, "ddpm update cannot run in place (the consistency gradient is a stencil in t)");
+    UpdateParams p;
+    p.x = u.x; p.eps = u.eps; p.noise = u.noise; p.x_out = u.x_out; p.pred_out = u.pred_out; p.x0_out = u.x0_out;
+    p.sched = u.sched; p.t_dev = u.t_dev; p.cand_off = u.cand_off; p.seed = u.seed;
+    p.B = u.B; p.T = u.T; p.n = u.n; p.timesteps = u.timesteps; p.t_host = u.t_host; p.renoise = u.renoise;
+    p.t_start = u.t_start; p.draws_per_step = u.draws_per_step; p.draw = u.draw; p.use_philox = u.use_philox;
+    p.obj = u.obj;
+    long long total = (long long)u.B * u.T * u.n;
+    if (total == 0) return 0;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    ddpm_update_kernel<<<blocks, 256, 0, st>>>(p);
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---------------------------------------------------------------- composed epsilon + loop
+int composed_eps(cindm_engine* e, const float* x, float* eps, int B, int n, int nc, int start, int mode, int t,
+                 const int* t_dev, int prec, int conv_engine, cudaStream_t st) {
+    const int H = e->cfg.horizon;
+    if (n < 2) return fail(-2, "compose_n_bodies must be at least 2");
+    if (nc < 0 || start <= 0) return fail(-2, "bad composition window parameters");
+    const int64_t S = (int64_t)(nc + 1) * (n * (n - 1) / 2) * B;
+    if (S > e->ws.max_slices || e->ws.precision != prec)
+        return fail(-6, "workspace not reserved for this slice count / precision (call cindm_reserve)");
+    CINDM_TRY(launch_compose_gather(x, e->ws.slices, B, n, nc, start, H, st));
+    CINDM_TRY(unet_forward(e, e->ws.slices, S, t, t_dev, e->ws.eps_pair, prec, conv_engine, st));
+    return launch_compose_scatter(e->ws.eps_pair, eps, B, n, nc, start, H, mode, st);
+}
+
+static int ensure_sample_buffers(cindm_engine* e, size_t elems) {
+    SampleBuffers& sb = e->sb;
+    if (!sb.t_dev) CINDM_CHECK_CUDA(cudaMalloc(&sb.t_dev, sizeof(int)));
+    if (sb.elems >= elems) return 0;
+    CINDM_CHECK_CUDA(cudaDeviceSynchronize());
+    if (sb.x_alt) cudaFree(sb.x_alt);
+    if (sb.pred) cudaFree(sb.pred);
+    if (sb.eps) cudaFree(sb.eps);
+    sb.x_alt = sb.pred = sb.eps = nullptr;
+    CINDM_CHECK_CUDA(cudaMalloc(&sb.x_alt, elems * sizeof(float)));
+    CINDM_CHECK_CUDA(cudaMalloc(&sb.pred, elems * sizeof(float)));
+    CINDM_CHECK_CUDA(cudaMalloc(&sb.eps, elems * sizeof(float)));
+    sb.elems = elems;
+    return 0;
+}
+
+// Issue the kernels of ONE DDPM step.  x lives in bufs[cur]; returns (through cur) where the result is.
+static int issue_step(cindm_engine* e, const cindm_sample_config& c, float* bufs[2], int& cur, const float* noise,
+                      float* x0_out, int t, const int* t_dev, cudaStream_t st) {
+    const int T = e->cfg.horizon + c.n_composed * c.compose_start_step;
+    const int iters = c.recurrence > 0 ? c.recurrence : 1;
+    const int draws = c.recurrence > 0 ? c.recurrence + 1 : 1;
+    for (int r = 0; r < iters; ++r) {
+        CINDM_TRY(composed_eps(e, bufs[cur], e->sb.eps, c.batch, c.n_bodies, c.n_composed, c.compose_start_step,
+                               c.compose_mode, t, t_dev, c.precision, c.conv_engine, st));
+        const bool last = r == iters - 1;
+        UpdateLaunch u;
+        u.x = bufs[cur]; u.eps = e->sb.eps; u.x_out = bufs[cur ^ 1];
+        u.pred_out = nullptr; u.x0_out = last ? x0_out : nullptr;
+        u.B = c.batch; u.T = T; u.n = c.n_bodies; u.sched = e->sched_dev; u.timesteps = e->cfg.timesteps;
+        u.t_dev = t_dev; u.t_host = t;
+        u.noise = noise; u.t_start = c.t_start; u.draws_per_step = draws;
+        u.use_philox = noise == nullptr; u.seed = c.seed; u.cand_off = c.candidate_offset;
+        u.obj = c.objective;
+        // the reference re-noises after the last recurrence too and then discards it (:1365-1370):
+        // the last evaluation goes straight to the final posterior noise (draw id R)
+        u.renoise = (c.recurrence > 0 && !last) ? 1 : 0;
+        u.draw = (c.recurrence > 0 && last) ? c.recurrence : r;
+        CINDM_TRY(launch_update(u, st));
+        cur ^= 1;
+    }
+    return 0;
+}
+
+int sample_loop(cindm_engine* e, const cindm_sample_config& c, float* x, const float* noise, float* x0_out,
+                cudaStream_t st) {
+    if (!e->finalized) return fail(-4, "weights not finalized");
+    if (!e->sched_dev) return fail(-4, "schedule tables not set (cindm_set_schedule)");
+    if (c.t_start >= e->cfg.timesteps || c.t_end < 0 || c.t_end > c.t_start) return fail(-2, "bad timestep range");
+    if (c.compose_start_step >= e->cfg.horizon) return fail(-2, "compose_start_step must be < horizon");   // (:1679)
+    if (c.batch <= 0) return fail(-2, "batch must be positive");
+    const int T = e->cfg.horizon + c.n_composed * c.compose_start_step;
+    const size_t elems = (size_t)c.batch * T * c.n_bodies * 4;
+    const int64_t S = (int64_t)(c.n_composed + 1) * (c.n_bodies * (c.n_bodies - 1) / 2) * c.batch;
+    CINDM_TRY(reserve_workspace(e, S > e->ws.max_slices ? S : e->ws.max_slices, c.precision));
+    CINDM_TRY(ensure_sample_buffers(e, elems));
+    float* bufs[2] = {x, e->sb.x_alt};
+    int cur = 0;
+    const int n_steps = c.t_start - c.t_end + 1;
+
+    if (!c.use_graph) {
+        for (int t = c.t_start; t >= c.t_end; --t)
+            CINDM_TRY(issue_step(e, c, bufs, cur, noise, x0_out, t, nullptr, st));
+    } else {
+        // One graph = two DDPM steps when a step flips the ping-pong parity, so that every replay
+        // starts with x in bufs[0]; t is read from device memory and decremented inside the graph.
+        const int iters = c.recurrence > 0 ? c.recurrence : 1;
+        const int steps_per_graph = (iters % 2) ? 2 : 1;
+        CINDM_CHECK_CUDA(cudaMemcpyAsync(e->sb.t_dev, &c.t_start, sizeof(int), cudaMemcpyHostToDevice, st));
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        CINDM_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        int rc = 0, gcur = 0;
+        for (int k = 0; k < steps_per_graph && rc == 0; ++k) {
+            rc = issue_step(e, c, bufs, gcur, noise, x0_out, 0, e->sb.t_dev, st);
+            if (rc == 0) rc = launch_step_counter(e->sb.t_dev, -1, st);
+        }
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return fail(-100, std::string("graph capture: ") + cudaGetErrorString(ce));
+        CINDM_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        int done = 0;
+        for (; done + steps_per_graph <= n_steps; done += steps_per_graph) {
+            ce = cudaGraphLaunch(exec, st);
+            if (ce != cudaSuccess) break;
+        }
+        cudaStreamSynchronize(st);
+        cudaGraphExecDestroy(exec);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return fail(-100, std::string("graph launch: ") + cudaGetErrorString(ce));
+        for (int t = c.t_start - done; t >= c.t_end; --t)       // odd remainder, issued directly
+            CINDM_TRY(issue_step(e, c, bufs, cur, noise, x0_out, t, nullptr, st));
+    }
+    if (cur != 0) CINDM_CHECK_CUDA(cudaMemcpyAsync(x, e->sb.x_alt, elems * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+}  // namespace cindm

@@ -1,0 +1,168 @@
+/*
+ * cindm_b200 — C ABI of the B200-native (sm_100a) compositional-sampling hot path of CinDM.
+ *
+ * The reference (AI4Science-WestlakeU/cindm) has no FFI layer: its "operator API" for this
+ * path is the Python class surface of model/diffusion_1d.py.  Each entry point below names
+ * the reference code it replaces (file:line under /root/reference).  The Python mirror of
+ * that class surface lives in cindm_b200/model/diffusion_1d.py and calls these functions
+ * through ctypes (see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative code on failure; the message is
+ *     available from cindm_last_error() (thread-local).  Nothing throws across the boundary.
+ *   - all tensors are row-major, contiguous, fp32 at the boundary.  Pointers named *_dev
+ *     are device pointers owned by the caller; the library owns only what cindm_create /
+ *     cindm_reserve allocated.  Step functions never allocate (CUDA-graph capturable).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - layouts: design x[B][T][4n] (features per body: x, y, vx, vy); model slices
+ *     [S][24][8] with slice id s = (kk*P + pair)*B + b  (kk window, pair lexicographic ii<jj).
+ */
+#ifndef CINDM_B200_H
+#define CINDM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cindm_engine cindm_engine;
+
+/* precision of the U-Net activations / GEMM operands (accumulation is always fp32) */
+enum { CINDM_PREC_F32 = 0, CINDM_PREC_F16 = 1, CINDM_PREC_BF16 = 2 };
+/* conv engine: SIMT FMA kernels, or tcgen05 tensor-core kernels (16-bit precisions only) */
+enum { CINDM_CONV_SIMT = 0, CINDM_CONV_TCGEN05 = 1 };
+/* composition reduce: "mean-inside" / "sum-inside" (model/diffusion_1d.py:994-999) */
+enum { CINDM_COMPOSE_MEAN_INSIDE = 0, CINDM_COMPOSE_SUM_INSIDE = 1 };
+/* design objective: get_design_fn design_fn_mode (inference/inverse_design_diffusion_1d.py:215-222) */
+enum { CINDM_OBJ_L2 = 0, CINDM_OBJ_L2SQUARE = 1 };
+/* guidance scaling: "standard*" (g) or "standard-alpha*" (beta_t/sqrt(abar_prev_t) * g) (:1321-1324) */
+enum { CINDM_GUIDE_NONE = 0, CINDM_GUIDE_STANDARD = 1, CINDM_GUIDE_STANDARD_ALPHA = 2 };
+
+typedef struct {
+    int horizon;        /* 24: TemporalUnet1D(horizon=...)            model/diffusion_1d.py:521 */
+    int transition_dim; /* 8 : two bodies x (x,y,vx,vy)                                     :522 */
+    int dim;            /* 64: Unet_dim                                                     :524 */
+    int timesteps;      /* 1000: GaussianDiffusion1D(timesteps=...)                         :810 */
+} cindm_config;
+
+typedef struct {
+    double target_x, target_y; /* pos_target (fp64 in the driver, inverse_design_diffusion_1d.py:281) */
+    float coef;                /* design_coef */
+    float consistency_coef;    /* time_consistency_coef */
+    int mode;                  /* CINDM_OBJ_* */
+    int guidance;              /* CINDM_GUIDE_* */
+} cindm_objective;
+
+typedef struct {
+    int batch;              /* B candidates on this device */
+    int n_bodies;           /* compose_n_bodies */
+    int n_composed;         /* extra windows; W = n_composed + 1 */
+    int compose_start_step; /* window stride */
+    int compose_mode;       /* CINDM_COMPOSE_* */
+    int recurrence;         /* 0: "standard" single pass; K>0: "...-recurrence-K" */
+    int precision;          /* CINDM_PREC_* */
+    int conv_engine;        /* CINDM_CONV_* */
+    int t_start, t_end;     /* inclusive start (e.g. 999) down to inclusive end (e.g. 0) */
+    uint64_t seed;          /* Philox key when noise_dev == NULL */
+    int64_t candidate_offset; /* global id of local candidate 0 (sharding-invariant noise) */
+    int use_graph;          /* capture one DDPM step in a CUDA graph and replay it */
+    cindm_objective objective;
+} cindm_sample_config;
+
+const char* cindm_last_error(void);
+int cindm_version(void);
+
+/* ---- engine life cycle; replaces TemporalUnet1D.__init__ / GaussianDiffusion1D.__init__ /
+ *      load_state_dict (model/diffusion_1d.py:519-608, :802-910; driver :163-180) ------------- */
+int cindm_create(const cindm_config* cfg, cindm_engine** out);
+int cindm_destroy(cindm_engine* e);
+/* one call per U-Net state-dict entry, names WITHOUT the "model." prefix, host fp32 data */
+int cindm_load_weight(cindm_engine* e, const char* name, const float* host, const int64_t* shape, int ndim);
+/* repack weights for the kernels, build the per-timestep time-embedding bias tables
+ * (time_mlp :537-542 and the 16 per-block Mish->Linear :493-497 are batch-invariant) */
+int cindm_finalize_weights(cindm_engine* e, void* stream);
+/* the 13 schedule buffers of GaussianDiffusion1D (:873-897), each [timesteps] fp32, host pointers
+ * in the order of cindm_schedule_tables */
+int cindm_set_schedule(cindm_engine* e, const float* tables13, int timesteps);
+/* allocate the activation workspace for up to max_slices slices per forward */
+int cindm_reserve(cindm_engine* e, int64_t max_slices, int precision);
+int64_t cindm_workspace_bytes(int64_t max_slices, int precision);
+
+/* ---- host-side helpers ------------------------------------------------------------------- */
+/* cosine_beta_schedule + derived buffers (model/diffusion_1d.py:470-480, :853-897): writes
+ * 13*timesteps floats: betas, alphas_cumprod, alphas_cumprod_prev, sqrt_alphas_cumprod,
+ * sqrt_one_minus_alphas_cumprod, log_one_minus_alphas_cumprod, sqrt_recip_alphas_cumprod,
+ * sqrt_recipm1_alphas_cumprod, posterior_variance, posterior_log_variance_clipped,
+ * posterior_mean_coef1, posterior_mean_coef2, loss_weight */
+int cindm_schedule_tables(int timesteps, float* out_host);
+/* integer maps of the composition operator (model/diffusion_1d.py:977-990); arrays are host:
+ * win_t0[W], pair_i[P], pair_j[P], cover[T_total] */
+int cindm_build_index_maps(int n_bodies, int n_composed, int compose_start_step, int horizon,
+                           int32_t* win_t0, int32_t* pair_i, int32_t* pair_j, int32_t* cover);
+
+/* ---- composition operator (model/diffusion_1d.py:959-1001) ---------------------------------- */
+/* x[B][T][4n] -> slices[W*P*B][24][8]   (gather at :985) */
+int cindm_compose_gather(const float* x_dev, float* slices_dev, int batch, int n_bodies, int n_composed,
+                         int compose_start_step, int horizon, void* stream);
+/* eps_pair[W*P*B][24][8] -> eps[B][T][4n]   (scatter :989-990, reduce :994-999) */
+int cindm_compose_scatter_mean(const float* eps_pair_dev, float* eps_dev, int batch, int n_bodies,
+                               int n_composed, int compose_start_step, int horizon, int compose_mode,
+                               void* stream);
+
+/* ---- epsilon model: TemporalUnet1D.forward (model/diffusion_1d.py:610-646) ------------------ */
+/* slices[S][24][8], one integer timestep for the whole batch -> eps_pair[S][24][8] */
+int cindm_unet_forward(cindm_engine* e, const float* slices_dev, int64_t n_slices, int t,
+                       float* eps_pair_dev, int precision, int conv_engine, void* stream);
+/* debug / parity: copy a named intermediate activation of the LAST forward to the host as
+ * channels-first fp32 [S][C][H]; names as in oracle/unet_ref.py taps */
+int cindm_unet_read_tap(cindm_engine* e, const char* name, float* host, int64_t capacity_elems,
+                        int64_t* s, int64_t* c, int64_t* h);
+int cindm_unet_enable_taps(cindm_engine* e, int enable);
+
+/* gather -> U-Net -> scatter-mean in one call: the compose branch of model_predictions (:959-1001) */
+int cindm_composed_eps(cindm_engine* e, const float* x_dev, float* eps_dev, int batch, int n_bodies,
+                       int n_composed, int compose_start_step, int compose_mode, int t, int precision,
+                       int conv_engine, void* stream);
+
+/* ---- guidance gradient: replaces torch.autograd.grad(design_fn(x), x) (:1316-1320) with the
+ *      closed form of get_design_fn (inference/inverse_design_diffusion_1d.py:211-229) --------- */
+int cindm_design_grad(const float* x_dev, float* grad_dev, int batch, int t_total, int n_bodies,
+                      const cindm_objective* obj, void* stream);
+
+/* ---- fused DDPM update: predict_start_from_noise + clamp + q_posterior + guidance + re-noise /
+ *      final noise (:914-918, :938-949, :1039, :1349, :1365-1370) ------------------------------
+ * pred = c1*clamp(A x - B eps) + c2 x - gscale*grad(x)
+ * renoise != 0: x_out = sqrt(r_t) pred + sqrt(1-r_t) noise       (recurrence iteration)
+ * renoise == 0: x_out = pred + exp(0.5 logvar_t) noise            (end of the step; noise may be NULL)
+ * pred_out / x0_out may be NULL.  Needs cindm_set_schedule. */
+int cindm_posterior_update(cindm_engine* e, const float* x_dev, const float* eps_dev, const float* noise_dev,
+                           float* x_out_dev, float* pred_out_dev, float* x0_out_dev, int batch, int t_total,
+                           int n_bodies, int t, int renoise, const cindm_objective* obj, void* stream);
+
+/* ---- the sampling loop: p_sample_loop / p_sample_compose_inside (:1655-1720, :1189-1376) ----
+ * x_dev[B][T][4n] holds the initial noise on entry and the designs on exit.  noise_dev == NULL
+ * draws N(0,1) from Philox4x32-10 keyed by (seed, global candidate, t, draw, element); otherwise
+ * noise_dev[step][draw][B][T][4n] with draw = 0..R-1 (re-noise) then R (final), as the reference
+ * consumes torch.randn_like.  x0_out_dev (optional) receives the last x_start. */
+int cindm_sample(cindm_engine* e, const cindm_sample_config* cfg, float* x_dev, const float* noise_dev,
+                 float* x0_out_dev, void* stream);
+/* fill x with the Philox N(0,1) stream used for the initial img (draw id 0xFFFF, t = timesteps) */
+int cindm_fill_initial_noise(float* x_dev, int batch, int t_total, int n_bodies, uint64_t seed,
+                             int64_t candidate_offset, int timesteps, void* stream);
+
+/* ---- scoring rollout: eval_simu / simulation (utils.py:1071-1148) on the GPU ----------------
+ * state0[B][n][4] in pixel units (positions 0..200, velocities px/s); runs n_steps of dt=1/60
+ * hard-disc dynamics (r=20, m=1, e=1, walls of radius 1 on the 200x200 box) and writes the state
+ * after steps stride-1, 2*stride-1, ... (traj[:, stride-1::stride]) into traj[B][n_steps/stride][n][4]. */
+int cindm_nbody_rollout(const double* state0_dev, double* traj_dev, int batch, int n_bodies, int n_steps,
+                        int stride, void* stream);
+/* fused metrics of the driver (inverse_design_diffusion_1d.py:316-337): pred[B][T][4n] fp32 (normalised
+ * units), runs the rollout from frame 0 and returns per-candidate MAE and last-frame objective */
+int cindm_score_designs(const float* pred_dev, float* mae_dev, float* objective_dev, int batch, int t_total,
+                        int n_bodies, double target_x, double target_y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CINDM_B200_H */

@@ -1,0 +1,95 @@
+"""CPU: the C-ABI library builds with nvcc for sm_100a, loads, and exports every symbol that
+include/cindm_b200.h declares.  No compute entry point is called here (there is no GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def library():
+    from cindm_b200 import build
+    return build.build()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "cindm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cindm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    from cindm_b200 import _lib
+    assert declared_symbols() == _lib.exported_symbols()
+
+
+def test_library_exports_every_declared_symbol(library):
+    handle = ctypes.CDLL(library)
+    for name in declared_symbols():
+        assert hasattr(handle, name), name
+    handle.cindm_version.restype = ctypes.c_int
+    assert handle.cindm_version() >= 100
+
+
+def test_host_only_entry_points(library):
+    """Schedule tables and index maps are pure host code: check them against the golden vectors."""
+    import numpy as np
+    import torch
+    from cindm_b200 import _lib
+    from cindm_b200.model.diffusion_1d import SCHEDULE_KEYS, schedule_buffers, cosine_beta_schedule
+    g = np.load(os.path.join(ROOT, "tests", "golden", "schedule.npz"))
+    out = torch.empty(13, 1000, dtype=torch.float32)
+    _lib.check(_lib.lib().cindm_schedule_tables(1000, ctypes.c_void_p(out.data_ptr())))
+    bufs = schedule_buffers(cosine_beta_schedule(1000))
+    for i, k in enumerate(SCHEDULE_KEYS):
+        ref = torch.from_numpy(g[k])
+        assert torch.equal(bufs[k], ref), k                       # host mirror: bit-exact
+        ulp = (out[i].view(torch.int32) - ref.view(torch.int32)).abs().max().item()
+        assert ulp <= 1, (k, ulp)                                  # C libm vs torch fp64: at most one fp32 ulp
+    gi = np.load(os.path.join(ROOT, "tests", "golden", "index_maps.npz"))
+    cover = (ctypes.c_int32 * 44)()
+    _lib.check(_lib.lib().cindm_build_index_maps(8, 2, 10, 24, None, None, None, cover))
+    assert list(cover) == gi["n8_nc2_s10:cover"].tolist()
+    assert list(cover) == [1] * 10 + [2] * 10 + [3] * 4 + [2] * 10 + [1] * 10
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from cindm_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.CindmError):
+        _lib.lib()
+
+
+def test_host_logic_parsers():
+    from cindm_b200 import _lib
+    from cindm_b200.model.diffusion_1d import parse_design_guidance, get_design_fn
+    assert parse_design_guidance("standard") == (_lib.GUIDE_STANDARD, 0)
+    assert parse_design_guidance("standard-recurrence-10") == (_lib.GUIDE_STANDARD, 10)
+    assert parse_design_guidance("standard-alpha-recurrence-3") == (_lib.GUIDE_STANDARD_ALPHA, 3)
+    with pytest.raises(ValueError):
+        parse_design_guidance("standard-recurrence-__import__('os')")
+    with pytest.raises(NotImplementedError):
+        parse_design_guidance("universal-forward-recurrence-5")
+    import torch
+    fn = get_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, coef=0.2, time_consistency_coef=0.2)
+    s = fn.as_struct(_lib.GUIDE_STANDARD)
+    assert (s.target_x, s.target_y, s.mode) == (0.5, 0.5, _lib.OBJ_L2)
+    assert abs(s.coef - 0.2) < 1e-7
+
+
+def test_state_dict_layout_matches_reference_keys():
+    from cindm_b200.model.diffusion_1d import GaussianDiffusion1D, TemporalUnet1D
+    model = TemporalUnet1D(horizon=24, transition_dim=8, cond_dim=False, dim=64, dim_mults=(1, 2, 4, 8), attention=True)
+    dif = GaussianDiffusion1D(model, image_size=24, conditioned_steps=0, timesteps=1000, sampling_timesteps=1000)
+    sd = dif.state_dict()
+    assert len(sd) == 247                                           # 234 U-Net entries + 13 buffers
+    assert tuple(sd["model.downs.0.0.blocks.0.block.0.weight"].shape) == (64, 8, 5)
+    assert tuple(sd["model.downs.0.2.fn.norm.g"].shape) == (1, 64, 1)
+    assert tuple(sd["model.ups.2.3.conv.weight"].shape) == (64, 64, 4)
+    dif.load_state_dict(sd)
+    with pytest.raises(RuntimeError):
+        dif.load_state_dict({k: v for k, v in sd.items() if k != "model.final_conv.1.bias"})

@@ -1,0 +1,282 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden vectors
+minted from the unmodified reference.  Tolerances are the ones BASELINE.json's north_star states:
+per-step composed eps <= 1e-5 rel-L2 in fp32, <= 1e-2 in 16-bit; index maps bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+META = json.load(open(os.path.join(HERE, "golden", "meta.json")))
+
+FP32_TOL = 1e-5
+HALF_TOL = 1e-2
+
+
+def rel_l2(a, b):
+    a = torch.as_tensor(a, dtype=torch.float64).cpu()
+    b = torch.as_tensor(b, dtype=torch.float64).cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def diffusion(test_weights):
+    from cindm_b200.model.diffusion_1d import GaussianDiffusion1D, TemporalUnet1D
+    model = TemporalUnet1D(horizon=24, transition_dim=8, cond_dim=False, dim=64, dim_mults=(1, 2, 4, 8), attention=True)
+    dif = GaussianDiffusion1D(model, image_size=24, conditioned_steps=0, timesteps=1000, sampling_timesteps=1000,
+                              loss_type="l1")
+    model.load_state_dict(test_weights)
+    dif.to("cuda:0")
+    return dif
+
+
+def set_precision(dif, precision, engine="simt"):
+    dif.precision = precision
+    dif.conv_engine = engine
+    dif.model.precision = precision
+    dif.model.conv_engine = engine
+
+
+def test_native_library_is_the_path(diffusion):
+    from cindm_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH)
+    assert _lib.lib().cindm_version() >= 100
+
+
+def test_schedule_tables_c_vs_golden(golden):
+    import ctypes
+    from cindm_b200 import _lib
+    from cindm_b200.model.diffusion_1d import SCHEDULE_KEYS
+    out = torch.empty(13, 1000, dtype=torch.float32)
+    _lib.check(_lib.lib().cindm_schedule_tables(1000, ctypes.c_void_p(out.data_ptr())))
+    g = golden("schedule.npz")
+    for i, k in enumerate(SCHEDULE_KEYS):
+        ref = torch.from_numpy(g[k])
+        ulp = (out[i].view(torch.int32) - ref.view(torch.int32)).abs().max().item()
+        assert ulp <= 1, (k, ulp)
+
+
+@pytest.mark.parametrize("t", [0, 37, 999])
+def test_unet_forward_fp32(diffusion, golden, t):
+    set_precision(diffusion, "fp32")
+    g = golden("unet_forward.npz")
+    x = torch.from_numpy(g["x"])
+    y = diffusion.model(x, torch.full((x.shape[0],), t, dtype=torch.long), None)
+    assert rel_l2(y, g[f"eps_t{t}"]) < FP32_TOL
+
+
+def test_unet_layer_taps_fp32(diffusion, golden):
+    set_precision(diffusion, "fp32")
+    g = golden("unet_forward.npz")
+    x = torch.from_numpy(g["x"])[:2]
+    diffusion.model.enable_taps(True)
+    try:
+        diffusion.model(x, torch.full((2,), 37, dtype=torch.long), None)
+        names = [k[4:] for k in g.files if k.startswith("tap:") and k != "tap:temb"]
+        taps = diffusion.model.read_taps(names)
+    finally:
+        diffusion.model.enable_taps(False)
+    worst = max((rel_l2(taps[n], g["tap:" + n]), n) for n in names)
+    assert worst[0] < FP32_TOL, worst
+
+
+def test_unet_forward_vs_oracle_random_inputs(diffusion, test_weights):
+    from oracle import unet_ref
+    set_precision(diffusion, "fp32")
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(37, 24, 8, generator=gen) * 1.7       # a slice count that is not a tile multiple
+    t = torch.full((37,), 613, dtype=torch.long)
+    y = diffusion.model(x, t, None)
+    assert rel_l2(y, unet_ref.unet_forward(test_weights, x, t)) < FP32_TOL
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16", HALF_TOL), ("bf16", 3e-2)])
+def test_unet_forward_16bit_simt(diffusion, golden, precision, tol):
+    # bf16 keeps 8 significand bits: ~1e-2 per-slice error on this 50-layer net (the product default is fp16)
+    set_precision(diffusion, precision)
+    g = golden("unet_forward.npz")
+    x = torch.from_numpy(g["x"])
+    y = diffusion.model(x, torch.full((x.shape[0],), 37, dtype=torch.long), None)
+    assert rel_l2(y, g["eps_t37"]) < tol
+
+
+@pytest.mark.parametrize("case", sorted(META["compose_cases"]))
+def test_composed_eps_fp32(diffusion, golden, case):
+    set_precision(diffusion, "fp32")
+    n, nc, start, mode, b, t = META["compose_cases"][case]
+    g = golden("composed_eps.npz")
+    eps = diffusion.composed_eps(torch.from_numpy(g[case + ":x"]), t, nc, start, n, mode)
+    assert rel_l2(eps, g[case + ":eps"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("case", sorted(META["compose_cases"]))
+def test_composed_eps_fp16(diffusion, golden, case):
+    set_precision(diffusion, "fp16")
+    n, nc, start, mode, b, t = META["compose_cases"][case]
+    g = golden("composed_eps.npz")
+    eps = diffusion.composed_eps(torch.from_numpy(g[case + ":x"]), t, nc, start, n, mode)
+    assert rel_l2(eps, g[case + ":eps"]) < HALF_TOL
+
+
+@pytest.mark.parametrize("n,nc,start", [tuple(c) for c in META["index_cases"]])
+def test_gather_scatter_index_maps_bit_exact(golden, n, nc, start):
+    """Coded inputs through the gather / scatter kernels reproduce the reference's integer maps exactly."""
+    import ctypes
+    from cindm_b200 import _lib
+    L = _lib.lib()
+    g = golden("index_maps.npz")
+    key = f"n{n}_nc{nc}_s{start}"
+    W, P, T, F = nc + 1, n * (n - 1) // 2, 24 + nc * start, 4 * n
+    B = 3
+    st = _lib.stream_ptr()
+    # gather: x holds its own flat index (exact in fp32 below 2^24)
+    x = (torch.arange(T * F, dtype=torch.float32).reshape(1, T, F) + torch.arange(B).reshape(B, 1, 1) * 100000.0).cuda()
+    slices = torch.empty(W * P * B, 24, 8, device="cuda")
+    _lib.check(L.cindm_compose_gather(_lib.ptr(x), _lib.ptr(slices), B, n, nc, start, 24, st))
+    got = slices.cpu().reshape(W * P, B, 24 * 8)
+    want = torch.from_numpy(g[key + ":gather"].astype(np.float32))
+    for b in range(B):
+        assert torch.equal(got[:, b] - 100000.0 * b, want)
+    # scatter: one-hot per model call
+    scatter = g[key + ":scatter"]
+    cover = g[key + ":cover"]
+    eps = torch.empty(B, T, F, device="cuda")
+    for call in range(W * P):
+        ep = torch.zeros(W * P, B, 24 * 8)
+        ep[call, 1] = torch.arange(1, 24 * 8 + 1, dtype=torch.float32)
+        ep = ep.reshape(W * P * B, 24, 8).cuda()
+        _lib.check(L.cindm_compose_scatter_mean(_lib.ptr(ep), _lib.ptr(eps), B, n, nc, start, 24, 0, st))
+        out = eps.cpu()
+        assert out[0].abs().sum() == 0 and out[2].abs().sum() == 0
+        flat = out[1].reshape(-1)
+        expect = torch.zeros(T * F, dtype=torch.float64)
+        for e in range(24 * 8):
+            tf = int(scatter[call, e])
+            expect[tf] = (e + 1) / (n - 1) / cover[tf // F]
+        assert torch.equal(flat != 0, expect != 0)
+        assert torch.allclose(flat.double(), expect, rtol=3e-7, atol=0)
+    # host map builder
+    win = (ctypes.c_int32 * W)()
+    pi = (ctypes.c_int32 * P)()
+    pj = (ctypes.c_int32 * P)()
+    cv = (ctypes.c_int32 * T)()
+    _lib.check(L.cindm_build_index_maps(n, nc, start, 24, win, pi, pj, cv))
+    assert list(cv) == cover.tolist()
+    assert list(win) == [k * start for k in range(W)]
+    assert [(a, b) for a, b in zip(pi, pj)] == [(i, j) for i in range(n) for j in range(i + 1, n)]
+
+
+def test_design_gradient_matches_autograd(diffusion, golden):
+    from cindm_b200.model.diffusion_1d import get_design_fn
+    g = golden("design_grad.npz")
+    cases = {"L2_n4": ("L2", 0.2, 0.2), "L2sq_n2": ("L2square", 0.4, 0.1), "L2_n8_nocons": ("L2", 0.6, 0.0)}
+    for name, (mode, coef, cc) in cases.items():
+        fn = get_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, coef=coef, time_consistency_coef=cc,
+                           design_fn_mode=mode)
+        x = torch.from_numpy(g[name + ":x"])
+        grad = diffusion.design_grad(x, fn).cpu()
+        ref = torch.from_numpy(g[name + ":grad"])
+        assert (grad - ref).abs().max().item() <= 1e-7, name
+        # the façade evaluates the same scalar the reference closure does
+        assert float(fn(x)) == pytest.approx(float(g[name + ":value"]), rel=1e-12)
+
+
+def golden_noise_for_step(noise, recurrence, t, shape):
+    """Golden noise is the reference's draw sequence (R x re-noise, then the final draw iff t > 0); the
+    C ABI wants R+1 (or 1) draws per step, so pad the missing t == 0 draw with zeros."""
+    draws = recurrence + 1 if recurrence > 0 else 1
+    take = draws if t > 0 else draws - 1
+    got = [noise.pop(0) for _ in range(take)]
+    if t == 0:
+        got.append(torch.zeros(shape))
+    return torch.stack(got)
+
+
+@pytest.mark.parametrize("case", sorted(META["traj_cases"]))
+def test_teacher_forced_steps_fp32(diffusion, golden, case):
+    from cindm_b200.model.diffusion_1d import get_design_fn, parse_design_guidance
+    set_precision(diffusion, "fp32")
+    n, nc, start, guidance, mode, coef, cc, b, steps = META["traj_cases"][case]
+    g = golden("trajectories.npz")
+    fn = get_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, coef=coef, time_consistency_coef=cc)
+    _, recurrence = parse_design_guidance(guidance)
+    noise = list(torch.from_numpy(g[case + ":noise"]))
+    img = torch.from_numpy(g[case + ":x_init"])
+    tabs = golden("schedule.npz")
+    for si, t in enumerate(steps):
+        nz = golden_noise_for_step(noise, recurrence, t, img.shape)
+        out, x0 = diffusion.p_sample_compose_inside(
+            img, None, t, design_fn=fn, design_guidance=guidance, compose_mode=mode, n_composed=nc,
+            compose_start_step=start, single_model_step=24, compose_n_bodies=n, noise=nz)
+        assert rel_l2(out, g[f"{case}:img_after_{si}"]) < FP32_TOL, (si, t)
+        # x0 = A_t x - B_t eps amplifies eps error by A_t (2e4 at t=999) before the clamp
+        amp = max(1.0, float(tabs["sqrt_recip_alphas_cumprod"][t]))
+        assert rel_l2(x0, g[f"{case}:x0_after_{si}"]) < FP32_TOL * amp, (si, t)
+        img = torch.from_numpy(g[f"{case}:img_after_{si}"])
+    assert not noise
+
+
+def test_cuda_graph_replay_equals_direct_launches(diffusion):
+    """Ten DDPM steps: graph replay (device-resident t) == step-by-step launches, bit for bit."""
+    import ctypes
+    from cindm_b200 import _lib
+    from cindm_b200.model.diffusion_1d import get_design_fn
+    set_precision(diffusion, "fp32")
+    fn = get_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, coef=0.2, time_consistency_coef=0.2)
+    eng = diffusion.model.engine()
+    outs = []
+    for use_graph, guidance in [(0, "standard-recurrence-2"), (1, "standard-recurrence-2"), (0, "standard"), (1, "standard")]:
+        cfg = diffusion._sample_config(3, 1, 10, 4, "mean-inside", fn, guidance, 999, 990, use_graph)
+        x = torch.empty(3, 34, 16, device="cuda")
+        _lib.check(_lib.lib().cindm_fill_initial_noise(_lib.ptr(x), 3, 34, 4, 7, 0, 1000, _lib.stream_ptr()))
+        _lib.check(_lib.lib().cindm_sample(eng.handle, ctypes.byref(cfg), _lib.ptr(x), None, None, _lib.stream_ptr()))
+        outs.append(x.cpu())
+    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[2], outs[3])
+    assert torch.isfinite(outs[0]).all()
+
+
+def test_philox_noise_is_sharding_invariant(diffusion):
+    """Candidates [0,4) sampled at once == [0,2) and [2,4) sampled separately with candidate_offset."""
+    from cindm_b200.model.diffusion_1d import get_design_fn
+    set_precision(diffusion, "fp32")
+    fn = get_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, coef=0.2, time_consistency_coef=0.2)
+    kw = dict(n_composed=1, compose_start_step=10, compose_n_bodies=2, compose_mode="mean-inside", design_fn=fn,
+              design_guidance="standard")
+    steps = diffusion.num_timesteps
+    try:
+        diffusion.num_timesteps = 5               # short chain: t = 4..0 of the 1000-step schedule
+        diffusion.seed, diffusion.candidate_offset = 123, 0
+        full = diffusion.p_sample_loop((4, 24, 8), None, **kw).cpu()
+        lo = diffusion.p_sample_loop((2, 24, 8), None, **kw).cpu()
+        diffusion.candidate_offset = 2
+        hi = diffusion.p_sample_loop((2, 24, 8), None, **kw).cpu()
+    finally:
+        diffusion.num_timesteps = steps
+        diffusion.candidate_offset = 0
+    assert torch.equal(full[:2], lo) and torch.equal(full[2:], hi)
+    # the noise is N(0,1): check moments of a large draw
+    import ctypes
+    from cindm_b200 import _lib
+    z = torch.empty(4096, 44, 32, device="cuda")
+    _lib.check(_lib.lib().cindm_fill_initial_noise(_lib.ptr(z), 4096, 44, 8, 1, 0, 1000, _lib.stream_ptr()))
+    assert abs(z.mean().item()) < 2e-3 and abs(z.std().item() - 1.0) < 2e-3
+    assert abs((z ** 4).mean().item() - 3.0) < 2e-2
+
+
+def test_unsupported_configurations_fail_loudly(diffusion):
+    from cindm_b200.model.diffusion_1d import GaussianDiffusion1D, parse_design_guidance
+    with pytest.raises(NotImplementedError):
+        diffusion.p_sample_loop((2, 24, 8), None, compose_mode="mean")
+    with pytest.raises(NotImplementedError):
+        parse_design_guidance("universal-backward")
+    with pytest.raises(NotImplementedError):
+        diffusion.p_sample_loop((2, 24, 8), None, compose_mode="mean-inside", design_fn=lambda x: x.sum())
+    with pytest.raises(NotImplementedError):
+        GaussianDiffusion1D(diffusion.model, image_size=24, conditioned_steps=4)
+    with pytest.raises(AssertionError):
+        diffusion.p_sample_loop((2, 24, 8), None, compose_mode="mean-inside", compose_start_step=24)
