@@ -72,6 +72,9 @@ int cindm_destroy(cindm_engine* e) {
     if (e->sb.pred) cudaFree(e->sb.pred);
     if (e->sb.eps) cudaFree(e->sb.eps);
     if (e->sb.t_dev) cudaFree(e->sb.t_dev);
+    if (e->sb.capture_stream) cudaStreamDestroy(e->sb.capture_stream);
+    if (e->sb.ev_in) cudaEventDestroy(e->sb.ev_in);
+    if (e->sb.ev_out) cudaEventDestroy(e->sb.ev_out);
     delete e;
     return 0;
     API_END

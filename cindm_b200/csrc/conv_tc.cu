@@ -1,4 +1,498 @@
+// Temporal convolution as an implicit GEMM on the 5th-generation tensor cores (sm_100a).
+//
+//   D[row][co] = sum_{tap, ci} A_tap[row][ci] * W[tap][co][ci]        row = (slice, position), fp32 accumulate
+//
+// * A operand: the channels-last activation tensor [S][H][C] is read through a 3-D TMA descriptor
+//   with box (64 channels, H positions, 128/H slices) whose H coordinate starts at tap - pad: the
+//   hardware zero-fills the out-of-range rows, which is exactly the conv's zero padding at slice
+//   boundaries, so a tile's M rows are whole slices and each tap is one more K block of the GEMM.
+// * B operand: repacked weights [tap][cout][cin] (K-major) through a 2-D descriptor.
+// * Both land in 128-byte-swizzled shared memory; one elected thread issues tcgen05.mma
+//   (cta_group::1, kind::f16, M=128, N=N_TILE, K=16) into a double-buffered TMEM accumulator.
+// * Epilogue warps read TMEM with tcgen05.ld and apply, fused: conv bias, GroupNorm(8) over
+//   (C/8 channels x H positions) of each slice (a tile owns whole slices, so the statistics are
+//   CTA-local), Mish, then the time-embedding bias or the residual, and store 16-bit activations.
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-5 epilogue.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "conv_tc.h"
+
 namespace cindm {
-int launch_conv_tc(const ConvTcLaunch&, cudaStream_t) { return fail(-99, "tcgen05 conv engine not built yet"); }
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kBlockK = 64;                  // 64 x 16-bit = one 128-byte swizzle row
+constexpr int kATileBytes = 128 * 128;       // 128 rows x 128 B
+constexpr int kThreads = 192;
+
+struct TcParams {
+    const float* bias;        // [cout] or null
+    const float* gamma;       // [cout]  (GN)
+    const float* beta;        // [cout]  (GN)
+    const float* add_vec;     // [cout] or [timesteps][cout] when t_dev != null
+    const int* t_dev;
+    const void* add_res;      // [S][H][cout] 16-bit or null
+    void* out;                // [S][H][cout] 16-bit
+    long long S;
+    int H, cout, c0, cin, taps, pad;
+    int slices_per_tile, rows_used, m_tiles, n_tiles, k_chunks_per_tap;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);      // start address
+    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+
+template <typename T16> struct Fmt;
+template <> struct Fmt<__half> { static constexpr uint32_t kind = 0; };
+template <> struct Fmt<__nv_bfloat16> { static constexpr uint32_t kind = 1; };
+
+template <typename T16>
+__device__ __forceinline__ uint32_t pack2(float a, float b);
+template <>
+__device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+template <>
+__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+template <typename T16>
+__device__ __forceinline__ float2 unpack2(uint32_t u);
+template <>
+__device__ __forceinline__ float2 unpack2<__half>(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
+template <>
+__device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t u) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+}
+
+// ------------------------------------------------------------------ the kernel
+template <typename T16, int N_TILE, int CPG, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+               const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+    constexpr int kBTileBytes = N_TILE * 128;
+    constexpr int kStageBytes = kATileBytes + kBTileBytes;
+    constexpr int NG = (EPI == EPI_GN_MISH) ? N_TILE / CPG : 1;       // GroupNorm groups inside one N tile
+    constexpr int PSTRIDE = 2 * NG + 1;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* tiles = smem;                                             // kStages x (A | B)
+    float* vec_bias = reinterpret_cast<float*>(smem + kStages * kStageBytes);
+    float* vec_gamma = vec_bias + 512;
+    float* vec_beta = vec_gamma + 512;
+    float* vec_add = vec_beta + 512;
+    float* part = vec_add + 512;                                       // [128][PSTRIDE]
+    float2* stats = reinterpret_cast<float2*>(part + 128 * 17);        // [42 slices][8 groups]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stats + 42 * 8);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full = empty_bar + kStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = p.m_tiles * p.n_tiles;
+    const int k_chunks = p.taps * p.k_chunks_per_tap;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        fence_barrier_init();
+        tma_prefetch_desc(&map_a0);
+        tma_prefetch_desc(&map_b);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    // per-layer channel vectors -> smem (epilogue broadcast reads)
+    {
+        const float* addv = p.add_vec;
+        if (addv && p.t_dev) addv += (long long)(*p.t_dev) * p.cout;
+        for (int c = threadIdx.x; c < p.cout; c += kThreads) {
+            vec_bias[c] = p.bias ? p.bias[c] : 0.f;
+            if (EPI == EPI_GN_MISH) { vec_gamma[c] = p.gamma[c]; vec_beta[c] = p.beta[c]; }
+            vec_add[c] = addv ? addv[c] : 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+                const int s0 = m_tile * p.slices_per_tile;
+                const uint32_t tx_bytes = (uint32_t)(p.rows_used * 128 + kBTileBytes);
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    for (int kc = 0; kc < p.k_chunks_per_tap; ++kc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* a_dst = tiles + stage * kStageBytes;
+                        uint8_t* b_dst = a_dst + kATileBytes;
+                        mbar_expect_tx(&full_bar[stage], tx_bytes);
+                        const int ci = kc * kBlockK;
+                        if (ci < p.c0) tma_load_3d(&map_a0, &full_bar[stage], a_dst, ci, tap - p.pad, s0);
+                        else           tma_load_3d(&map_a1, &full_bar[stage], a_dst, ci - p.c0, tap - p.pad, s0);
+                        tma_load_2d(&map_b, &full_bar[stage], b_dst, ci, tap * p.cout + n_tile * N_TILE);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (Fmt<T16>::kind << 7) | (Fmt<T16>::kind << 10) |
+                                       ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N_TILE);
+                for (int kc = 0; kc < k_chunks; ++kc) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(tiles + stage * kStageBytes);
+                    const uint32_t b_addr = a_addr + kATileBytes;
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        tc_mma_f16(d_tmem, umma_smem_desc(a_addr + k * 32), umma_smem_desc(b_addr + k * 32), idesc,
+                                   (kc > 0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit(&empty_bar[stage]);                 // frees the smem stage when the MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tmem_full[acc]);                       // accumulator ready for the epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // =============================== epilogue (4 warps) ===============================
+        const int q = warp & 3;                                   // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;                            // tile row == TMEM lane
+        const int et = (warp - 2) * 32 + lane;                    // 0..127 index among epilogue threads
+        T16* out = reinterpret_cast<T16*>(p.out);
+        const T16* res = reinterpret_cast<const T16*>(p.add_res);
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+            const long long s0 = (long long)m_tile * p.slices_per_tile;
+            const int n0 = n_tile * N_TILE;
+            const int sl = min(row / p.H, p.slices_per_tile - 1);  // slice within the tile
+            const bool valid = row < p.rows_used && (s0 + sl) < p.S;
+            const long long grow = s0 * p.H + row;                // global row (slices are contiguous rows)
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N_TILE);
+            float v[32];
+            if (EPI == EPI_GN_MISH) {
+                // ---- pass 1: per-row partial sums of every group ----
+                float s1[NG], s2[NG];
+#pragma unroll
+                for (int g = 0; g < NG; ++g) { s1[g] = 0.f; s2[g] = 0.f; }
+#pragma unroll
+                for (int c = 0; c < N_TILE; c += 32) {
+                    tmem_ld32(taddr + c, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float x = v[i] + vec_bias[n0 + c + i];
+                        const int g = (c + i) / CPG;
+                        s1[g] += x;
+                        s2[g] = fmaf(x, x, s2[g]);
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < NG; ++g) { part[row * PSTRIDE + 2 * g] = s1[g]; part[row * PSTRIDE + 2 * g + 1] = s2[g]; }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                // ---- reduce over the H rows of each slice ----
+                const float inv_cnt = 1.0f / (float)(p.H * CPG);
+                for (int idx = et; idx < p.slices_per_tile * NG; idx += 128) {
+                    const int s_l = idx / NG, g = idx - s_l * NG;
+                    float a = 0.f, b = 0.f;
+                    for (int h = 0; h < p.H; ++h) {
+                        a += part[(s_l * p.H + h) * PSTRIDE + 2 * g];
+                        b += part[(s_l * p.H + h) * PSTRIDE + 2 * g + 1];
+                    }
+                    const float mean = a * inv_cnt;
+                    const float var = fmaxf(b * inv_cnt - mean * mean, 0.f);
+                    stats[s_l * 8 + g] = make_float2(mean, rsqrtf(var + 1e-5f));
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            // ---- pass 2 (or the only pass): normalise / activate / add / store ----
+#pragma unroll 1
+            for (int c = 0; c < N_TILE; c += 32) {
+                tmem_ld32(taddr + c, v);
+                uint32_t packed[16];
+                uint4 rv[4];
+                if (res != nullptr && valid) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(res + grow * p.cout + n0 + c);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) rv[j] = rp[j];
+                }
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float y[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int ch = n0 + c + i + u;
+                        float x = v[i + u] + vec_bias[ch];
+                        if (EPI == EPI_GN_MISH) {
+                            const float2 st = stats[sl * 8 + (c + i + u) / CPG];
+                            x = (x - st.x) * st.y * vec_gamma[ch] + vec_beta[ch];
+                            x = mish_fast(x);
+                            x += vec_add[ch];
+                        }
+                        y[u] = x;
+                    }
+                    if (res != nullptr) {
+                        const uint32_t* rw = reinterpret_cast<const uint32_t*>(rv);
+                        float2 r2 = unpack2<T16>(rw[i >> 1]);
+                        y[0] += r2.x; y[1] += r2.y;
+                    }
+                    packed[i >> 1] = pack2<T16>(y[0], y[1]);
+                }
+                if (valid) {
+                    uint4* op = reinterpret_cast<uint4*>(out + grow * p.cout + n0 + c);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        op[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    }
+    return fn;
+}
+
+int encode_act_map(CUtensorMap* map, const void* base, int prec, long long S, int H, int C, int box_slices) {
+    auto enc = get_encode();
+    if (!enc) return fail(-100, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)S};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)H * C * 2};
+    cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)H, (cuuint32_t)box_slices};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, prec == PREC_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-100, "cuTensorMapEncodeTiled(activations) failed: " + std::to_string((int)r));
+    return 0;
+}
+
+int encode_weight_map(CUtensorMap* map, const void* base, int prec, int rows, int cin, int box_rows) {
+    auto enc = get_encode();
+    if (!enc) return fail(-100, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, prec == PREC_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-100, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r));
+    return 0;
+}
+
+template <int N_TILE>
+constexpr size_t smem_bytes_for() {
+    return 1024 + (size_t)kStages * (kATileBytes + N_TILE * 128) + 4 * 512 * 4 + 128 * 17 * 4 + 42 * 8 * 8 +
+           (2 * kStages + 4) * 8 + 16;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <typename T16, int N_TILE, int CPG, int EPI>
+int launch_instance(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, cudaStream_t st) {
+    auto kern = conv_tc_kernel<T16, N_TILE, CPG, EPI>;
+    constexpr size_t smem = smem_bytes_for<N_TILE>();
+    static bool configured = false;
+    if (!configured) {
+        CINDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int tiles = p.m_tiles * p.n_tiles;
+    int grid = tiles < num_sms() ? tiles : num_sms();
+    kern<<<grid, kThreads, smem, st>>>(a0, a1, b, p);
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
+template <typename T16>
+int dispatch(const ConvTcLaunch& a, const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& mb, const TcParams& p,
+             int n_tile, cudaStream_t st) {
+    if (a.epilogue == EPI_GN_MISH) {
+        switch (p.cout) {
+            case 64: return launch_instance<T16, 64, 8, EPI_GN_MISH>(m0, m1, mb, p, st);
+            case 128: return launch_instance<T16, 128, 16, EPI_GN_MISH>(m0, m1, mb, p, st);
+            case 256: return launch_instance<T16, 256, 32, EPI_GN_MISH>(m0, m1, mb, p, st);
+            case 512: return launch_instance<T16, 256, 64, EPI_GN_MISH>(m0, m1, mb, p, st);
+        }
+        return fail(-2, "conv_tc: unsupported channel count for the GroupNorm epilogue");
+    }
+    switch (n_tile) {
+        case 64: return launch_instance<T16, 64, 8, EPI_BIAS>(m0, m1, mb, p, st);
+        case 128: return launch_instance<T16, 128, 8, EPI_BIAS>(m0, m1, mb, p, st);
+        case 256: return launch_instance<T16, 256, 8, EPI_BIAS>(m0, m1, mb, p, st);
+    }
+    return fail(-2, "conv_tc: unsupported N tile");
+}
+
+}  // namespace
+
+int launch_conv_tc(const ConvTcLaunch& a, cudaStream_t st) {
+    const ConvW& w = *a.w;
+    if (a.prec != PREC_F16 && a.prec != PREC_BF16) return fail(-2, "conv_tc: 16-bit precisions only");
+    if (w.taps != 1 && w.taps != 5) return fail(-2, "conv_tc: taps must be 1 or 5");
+    if (w.cin % 64 || w.cout % 64) return fail(-2, "conv_tc: channel counts must be multiples of 64");
+    if (a.c0 + (a.in1 ? a.c1 : 0) != w.cin) return fail(-2, "conv_tc: input channels do not match the weight");
+    if (a.in1 && (a.c0 % 64)) return fail(-2, "conv_tc: concat split must be a multiple of 64 channels");
+    if (a.H < 1 || a.H > 128) return fail(-2, "conv_tc: bad H");
+    if (a.S == 0) return 0;
+    if (a.epilogue == EPI_GN_MISH && !a.gn) return fail(-2, "conv_tc: GroupNorm parameters missing");
+
+    TcParams p;
+    p.bias = w.bias;
+    p.gamma = a.gn ? a.gn->gamma : nullptr;
+    p.beta = a.gn ? a.gn->beta : nullptr;
+    p.add_vec = a.add_vec; p.t_dev = a.t_dev; p.add_res = a.add_res; p.out = a.out;
+    p.S = a.S; p.H = a.H; p.cout = w.cout; p.c0 = a.c0; p.cin = w.cin; p.taps = w.taps; p.pad = w.taps / 2;
+    p.slices_per_tile = 128 / a.H;
+    p.rows_used = p.slices_per_tile * a.H;
+    p.m_tiles = (int)((a.S + p.slices_per_tile - 1) / p.slices_per_tile);
+    int n_tile;
+    if (a.epilogue == EPI_GN_MISH) n_tile = w.cout < 256 ? w.cout : 256;
+    else n_tile = (w.cout % 256 == 0) ? 256 : ((w.cout % 128 == 0) ? 128 : 64);
+    p.n_tiles = w.cout / n_tile;
+    p.k_chunks_per_tap = w.cin / kBlockK;
+
+    CUtensorMap m0, m1, mb;
+    CINDM_TRY(encode_act_map(&m0, a.in0, a.prec, a.S, a.H, a.c0, p.slices_per_tile));
+    if (a.in1) CINDM_TRY(encode_act_map(&m1, a.in1, a.prec, a.S, a.H, a.c1, p.slices_per_tile));
+    else m1 = m0;
+    CINDM_TRY(encode_weight_map(&mb, w.w16[a.prec], a.prec, w.taps * w.cout, w.cin, n_tile));
+    if (a.prec == PREC_F16) return dispatch<__half>(a, m0, m1, mb, p, n_tile, st);
+    return dispatch<__nv_bfloat16>(a, m0, m1, mb, p, n_tile, st);
+}
+
+}  // namespace cindm

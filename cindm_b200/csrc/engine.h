@@ -60,6 +60,8 @@ struct Workspace {
 };
 
 struct SampleBuffers {           // sized by cindm_sample on first use
+    cudaStream_t capture_stream = nullptr;   // used when the caller's stream is the (uncapturable) legacy stream
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     size_t elems = 0;
     float* x_alt = nullptr;
     float* pred = nullptr;

@@ -284,8 +284,31 @@ static int issue_step(cindm_engine* e, const cindm_sample_config& c, float* bufs
     return 0;
 }
 
+static int sample_loop_on(cindm_engine* e, const cindm_sample_config& c, float* x, const float* noise, float* x0_out,
+                          cudaStream_t st);
+
 int sample_loop(cindm_engine* e, const cindm_sample_config& c, float* x, const float* noise, float* x0_out,
-                cudaStream_t st) {
+                cudaStream_t caller) {
+    // the legacy / per-thread default streams cannot be captured: run on an engine-owned stream that is
+    // ordered after the caller's stream, and make the caller's stream wait for it
+    const bool special = caller == nullptr || caller == cudaStreamLegacy || caller == cudaStreamPerThread;
+    if (!c.use_graph || !special) return sample_loop_on(e, c, x, noise, x0_out, caller);
+    SampleBuffers& sb = e->sb;
+    if (!sb.capture_stream) {
+        CINDM_CHECK_CUDA(cudaStreamCreateWithFlags(&sb.capture_stream, cudaStreamNonBlocking));
+        CINDM_CHECK_CUDA(cudaEventCreateWithFlags(&sb.ev_in, cudaEventDisableTiming));
+        CINDM_CHECK_CUDA(cudaEventCreateWithFlags(&sb.ev_out, cudaEventDisableTiming));
+    }
+    CINDM_CHECK_CUDA(cudaEventRecord(sb.ev_in, caller));
+    CINDM_CHECK_CUDA(cudaStreamWaitEvent(sb.capture_stream, sb.ev_in, 0));
+    int rc = sample_loop_on(e, c, x, noise, x0_out, sb.capture_stream);
+    CINDM_CHECK_CUDA(cudaEventRecord(sb.ev_out, sb.capture_stream));
+    CINDM_CHECK_CUDA(cudaStreamWaitEvent(caller, sb.ev_out, 0));
+    return rc;
+}
+
+static int sample_loop_on(cindm_engine* e, const cindm_sample_config& c, float* x, const float* noise, float* x0_out,
+                          cudaStream_t st) {
     if (!e->finalized) return fail(-4, "weights not finalized");
     if (!e->sched_dev) return fail(-4, "schedule tables not set (cindm_set_schedule)");
     if (c.t_start >= e->cfg.timesteps || c.t_end < 0 || c.t_end > c.t_start) return fail(-2, "bad timestep range");

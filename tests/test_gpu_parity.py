@@ -280,3 +280,60 @@ def test_unsupported_configurations_fail_loudly(diffusion):
         GaussianDiffusion1D(diffusion.model, image_size=24, conditioned_steps=4)
     with pytest.raises(AssertionError):
         diffusion.p_sample_loop((2, 24, 8), None, compose_mode="mean-inside", compose_start_step=24)
+
+
+# ----------------------------------------------------------------------------- tcgen05 conv engine
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_tcgen05_layer_taps_vs_simt(diffusion, golden, precision):
+    """Layer by layer: the tensor-core convs against the SIMT convs at the same storage precision."""
+    g = golden("unet_forward.npz")
+    x = torch.from_numpy(g["x"])
+    t = torch.full((x.shape[0],), 37, dtype=torch.long)
+    names = [k[4:] for k in g.files if k.startswith("tap:") and k != "tap:temb"]
+    taps = {}
+    diffusion.model.enable_taps(True)
+    try:
+        for engine in ("simt", "tcgen05"):
+            set_precision(diffusion, precision, engine)
+            diffusion.model(x, t, None)
+            taps[engine] = diffusion.model.read_taps(names)
+    finally:
+        diffusion.model.enable_taps(False)
+    tol = 5e-3 if precision == "fp16" else 4e-2
+    report = [(rel_l2(taps["tcgen05"][n], taps["simt"][n]), n) for n in names]
+    bad = [r for r in report if not (r[0] < tol)]
+    assert not bad, bad[:6]
+
+
+@pytest.mark.parametrize("t", [0, 37, 999])
+def test_unet_forward_tcgen05_fp16_vs_golden(diffusion, golden, t):
+    set_precision(diffusion, "fp16", "tcgen05")
+    g = golden("unet_forward.npz")
+    x = torch.from_numpy(g["x"])
+    y = diffusion.model(x, torch.full((x.shape[0],), t, dtype=torch.long), None)
+    assert rel_l2(y, g[f"eps_t{t}"]) < HALF_TOL
+
+
+@pytest.mark.parametrize("S", [1, 41, 1500])
+def test_unet_forward_tcgen05_many_tiles(diffusion, S):
+    """Partial tiles, and more tiles than SMs at H=24 (persistent tile loop), against the fp32 SIMT path."""
+    gen = torch.Generator().manual_seed(S)
+    x = torch.randn(S, 24, 8, generator=gen)
+    t = torch.full((S,), 420, dtype=torch.long)
+    set_precision(diffusion, "fp32", "simt")
+    ref = diffusion.model(x, t, None).cpu()
+    set_precision(diffusion, "fp16", "tcgen05")
+    y = diffusion.model(x, t, None).cpu()
+    assert torch.isfinite(y).all()
+    assert rel_l2(y, ref) < HALF_TOL
+    per_slice = ((y - ref).flatten(1).norm(dim=1) / ref.flatten(1).norm(dim=1)).max().item()
+    assert per_slice < 3 * HALF_TOL
+
+
+@pytest.mark.parametrize("case", sorted(META["compose_cases"]))
+def test_composed_eps_tcgen05_fp16(diffusion, golden, case):
+    set_precision(diffusion, "fp16", "tcgen05")
+    n, nc, start, mode, b, t = META["compose_cases"][case]
+    g = golden("composed_eps.npz")
+    eps = diffusion.composed_eps(torch.from_numpy(g[case + ":x"]), t, nc, start, n, mode)
+    assert rel_l2(eps, g[case + ":eps"]) < HALF_TOL
