@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the compositional-sampling hot path (BASELINE.json metric: composed-sampling
+designs/sec, 8-body, 28 pairs, 44 steps, 1000 DDPM steps).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A bench "step" is ONE DDPM denoising step t -> t-1 of the whole per-GPU candidate batch, i.e.
+R composed-epsilon evaluations (W*P*B U-Net slices each) with guidance + re-noise, and the final
+posterior noise.  Per-step cost does not depend on t, so
+    designs/sec = candidates / (1000 * seconds_per_step).
+Workload at every N: C4 of SURVEY.md section 8 — 512 candidates per GPU (4096 over 8 GPUs, weak
+scaling), compose_n_bodies=8, n_composed=2 (3 windows), compose_start_step=10, guidance
+standard-recurrence-10, design_coef 0.2, consistency_coef 0.2 (scripts_paper/1D/cindm.sh:22),
+random-init weights, Philox noise generated in-kernel, fp16 operands / fp32 accumulation.
+
+Rank 0 prints one JSON line (see the keys below).  `--impl reference` times the CPU oracle port
+(oracle/sampler_ref.py: the reference's own loop structure in PyTorch, all host threads) on a
+bounded sample of the same workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DDPM_STEPS = 1000
+N_BODIES, N_COMPOSED, START = 8, 2, 10
+CAND_PER_GPU = 512
+RECURRENCE = 10
+COEF, CONS_COEF = 0.2, 0.2
+HORIZON = 24
+T_TOTAL = HORIZON + N_COMPOSED * START
+PAIRS = N_BODIES * (N_BODIES - 1) // 2
+WINDOWS = N_COMPOSED + 1
+# algorithmic FLOP per slice-forward (nonzero-tap conv MACs + attention MACs, x2)
+FLOP_PER_SLICE = 116_533_248
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--candidates", type=int, default=CAND_PER_GPU, help="candidates per GPU")
+    ap.add_argument("--recurrence", type=int, default=RECURRENCE)
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "simt"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="also print the per-kernel-class event timings")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- CPU oracle arm
+def cpu_oracle_step_time(batch, recurrence, steps, warmup):
+    """Seconds per DDPM step of the oracle port on `batch` candidates of the C4 shape, all host threads."""
+    import torch
+    from cindm_b200.model.params import init_unet_params
+    from oracle import sampler_ref
+    torch.set_num_threads(os.cpu_count())
+    sd = init_unet_params(seed=0)
+    tabs = sampler_ref.cosine_schedule_tables()
+    fn = sampler_ref.make_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, COEF, CONS_COEF, "L2")
+    gen = torch.Generator().manual_seed(0)
+    img = torch.randn(batch, T_TOTAL, 4 * N_BODIES, generator=gen)
+    noise_fn = lambda shape: torch.randn(shape, generator=gen)
+    guidance = f"standard-recurrence-{recurrence}" if recurrence > 0 else "standard"
+    t = DDPM_STEPS - 1
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            img, _ = sampler_ref.p_sample_step(sd, tabs, img, t, noise_fn, n_composed=N_COMPOSED, compose_start_step=START,
+                                               compose_n_bodies=N_BODIES, compose_mode="mean-inside", design_fn=fn,
+                                               design_guidance=guidance)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+            t -= 1
+    return sum(times) / len(times)
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": "C4: 8-body, 28 pairs x 3 windows, 44 steps, composed from the 2-body 24-step temporal-unet1d (dim 64)",
+        "candidates_per_gpu": args.candidates, "candidates_total": args.candidates * n_gpus,
+        "slices_per_evaluation_per_gpu": WINDOWS * PAIRS * args.candidates,
+        "design_guidance": f"standard-recurrence-{args.recurrence}" if args.recurrence > 0 else "standard",
+        "compose_mode": "mean-inside", "design_coef": COEF, "consistency_coef": CONS_COEF,
+        "ddpm_steps_per_design": DDPM_STEPS,
+        "step": "one DDPM step (R composed evaluations + updates) of the whole per-GPU batch; designs/sec = candidates/(1000*s_per_step)",
+        "l2": "inputs larger than L2: each conv layer streams >=132 MB of activations per evaluation",
+        "parallelism": f"dp{n_gpus} (independent candidates, no per-step communication)",
+    }
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    batch = 2
+    sec = cpu_oracle_step_time(batch, args.recurrence, args.steps, min(args.warmup, 1))
+    value = batch / (DDPM_STEPS * sec)
+    cfg = workload_config(args, 1)
+    cfg["candidates_per_gpu"] = cfg["candidates_total"] = batch
+    cfg["slices_per_evaluation_per_gpu"] = WINDOWS * PAIRS * batch
+    line = {
+        "impl": "reference", "metric": "composed-sampling designs/sec (8-body, 1000 DDPM steps)", "value": value,
+        "unit": "designs/s", "n_gpus": 0, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": "designs/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{batch} candidates x {args.steps} DDPM steps of the C4 shape (R={args.recurrence}), "
+                                   "oracle/sampler_ref.py in the reference's one-forward-per-(window,pair) loop form"},
+        "e2e": {"value": value, "unit": "designs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args, rank, local_rank, world):
+    import torch
+    from cindm_b200 import _lib
+    from cindm_b200.model.diffusion_1d import GaussianDiffusion1D, TemporalUnet1D, get_design_fn
+    from cindm_b200.model.params import init_unet_params
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    L = _lib.lib()
+    model = TemporalUnet1D(horizon=HORIZON, transition_dim=8, cond_dim=False, dim=64, dim_mults=(1, 2, 4, 8), attention=True)
+    dif = GaussianDiffusion1D(model, image_size=HORIZON, conditioned_steps=0, timesteps=DDPM_STEPS, sampling_timesteps=DDPM_STEPS)
+    model.load_state_dict(init_unet_params(seed=0))
+    dif.to(dev)
+    dif.precision = model.precision = args.precision
+    dif.conv_engine = model.conv_engine = args.engine
+    dif.seed = 0
+    dif.candidate_offset = rank * args.candidates
+    fn = get_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, coef=COEF, time_consistency_coef=CONS_COEF)
+    guidance = f"standard-recurrence-{args.recurrence}" if args.recurrence > 0 else "standard"
+    B = args.candidates
+    eng = model.engine()
+    stream = torch.cuda.Stream(device=dev)
+    st = ctypes.c_void_p(stream.cuda_stream)
+
+    x = torch.empty(B, T_TOTAL, 4 * N_BODIES, device=dev)
+    x0 = torch.empty_like(x)
+
+    def run_steps(t_start, n):
+        cfg = dif._sample_config(B, N_COMPOSED, START, N_BODIES, "mean-inside", fn, guidance, t_start, t_start - n + 1, True)
+        _lib.check(L.cindm_sample(eng.handle, ctypes.byref(cfg), _lib.ptr(x), None, _lib.ptr(x0), st))
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.cuda.stream(stream):
+        _lib.check(L.cindm_fill_initial_noise(_lib.ptr(x), B, T_TOTAL, N_BODIES, 0, rank * B, DDPM_STEPS, st))
+        # ---- device-resident timing: W warm-up steps (graph capture happens here), then exactly K steps
+        per_call = 2 if (max(args.recurrence, 1) % 2) else 1          # the cached graph holds 1 or 2 DDPM steps
+        warm = max(args.warmup, 3)
+        warm += warm % per_call
+        steps = args.steps + (args.steps % per_call)
+        run_steps(DDPM_STEPS - 1, warm)
+        barrier()
+        launches0 = L.cindm_launch_count()
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run_steps(DDPM_STEPS - 1 - warm, steps)
+        e1.record(stream)
+        barrier()
+        launches = L.cindm_launch_count() - launches0
+        ms = e0.elapsed_time(e1)
+        clk = clocks.stop() if rank == 0 else None
+
+        # ---- end-to-end through the public per-step API with HOST buffers (pinned), H2D + D2H inside the timed region
+        host_in = torch.empty(B, T_TOTAL, 4 * N_BODIES, pin_memory=True)
+        host_out = torch.empty_like(host_in, pin_memory=True)
+        host_in.copy_(x.cpu())
+        e2e_steps = max(2, min(steps, 4))
+        e2e_steps += e2e_steps % per_call
+
+        def e2e_once(t_start):
+            x.copy_(host_in, non_blocking=True)
+            run_steps(t_start, per_call)
+            host_out.copy_(x, non_blocking=True)
+            stream.synchronize()
+            host_in.copy_(host_out)
+
+        e2e_once(DDPM_STEPS - 1)                         # warm-up (graph already cached)
+        barrier()
+        t0 = time.perf_counter()
+        t = DDPM_STEPS - 1 - per_call
+        for _ in range(e2e_steps // per_call):
+            e2e_once(t)
+            t -= per_call
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+
+    # ---- max over ranks
+    ms_t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = ms_t.tolist()
+    sec_per_step = ms_max / 1e3 / steps
+    total_cand = B * world
+    value = total_cand / (DDPM_STEPS * sec_per_step)
+    e2e_value = total_cand / (DDPM_STEPS * e2e_ms_max / 1e3)
+
+    # ---- final score all-gather (the path's only collective): one NCCL all-gather of per-candidate objectives
+    if dist is not None:
+        score = ((x[:, -1].reshape(B, N_BODIES, 4)[..., :2] - 0.5).norm(dim=-1)).mean(-1).contiguous()
+        gathered = torch.empty(world * B, device=dev)
+        dist.all_gather_into_tensor(gathered, score)
+        _ = torch.topk(gathered, k=min(8, world * B), largest=False)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel-class timing of one composed evaluation (un-graphed, CUDA events on the launching stream)
+    roofline, classes = None, {}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    with torch.cuda.stream(stream):
+        eps = torch.empty_like(x)
+        for rep in range(3):
+            if rep == 2:
+                _lib.check(L.cindm_profile_enable(1))
+            _lib.check(L.cindm_composed_eps(eng.handle, _lib.ptr(x), _lib.ptr(eps), B, N_BODIES, N_COMPOSED, START, 0, 500,
+                                            _lib.PRECISIONS[args.precision],
+                                            _lib.CONV_TCGEN05 if args.engine == "tcgen05" else _lib.CONV_SIMT, st))
+        stream.synchronize()
+        buf = ctypes.create_string_buffer(1 << 16)
+        L.cindm_profile_report(buf, len(buf))
+        _lib.check(L.cindm_profile_enable(0))
+    for row in buf.value.decode().strip().splitlines():
+        tag, groups, total_ms, work = row.split(",")
+        classes[tag] = {"launches": int(groups), "ms": float(total_ms), "work": float(work)}
+    eval_ms = sum(c["ms"] for c in classes.values())
+    S = WINDOWS * PAIRS * B
+    if "conv_tc" in classes and classes["conv_tc"]["ms"] > 0:
+        c = classes["conv_tc"]
+        achieved = c["work"] / (c["ms"] * 1e-3) / 1e12
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv + GN/Mish epilogue), all layers of one evaluation",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
+                    "algorithmic_flop_per_launch_group": c["work"] / c["launches"], "avg_launch_ms": c["ms"] / c["launches"],
+                    "share_of_evaluation": c["ms"] / eval_ms, "traffic": None}
+    elif "conv_simt" in classes:
+        c = classes["conv_simt"]
+        achieved = c["work"] / (c["ms"] * 1e-3) / 1e12
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        roofline = {"bound": "tensor", "kernel": "conv1d_simt_kernel (fp32 FMA path)", "achieved": achieved, "peak": peak,
+                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None}
+
+    line = {
+        "metric": "composed-sampling designs/sec (8-body, 1000 DDPM steps)", "value": value, "unit": "designs/s",
+        "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": workload_config(args, world),
+        "e2e": {"value": e2e_value, "unit": "designs/s", "h2d_bytes_per_step": host_in.numel() * 4,
+                "d2h_bytes_per_step": host_out.numel() * 4,
+                "note": "per DDPM step: pinned host x -> device, cindm_sample (one cached-graph replay), device -> pinned host"},
+        "gpu_launches": int(launches), "clocks": clk,
+        "roofline": roofline,
+        "model_tflops_per_gpu": FLOP_PER_SLICE * S * max(args.recurrence, 1) / sec_per_step / 1e12,
+        "kernel_classes_one_evaluation": classes,
+    }
+    if not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        cb, cr = 2, args.recurrence
+        sec = cpu_oracle_step_time(cb, cr, 1, 0)
+        line["cpu_baseline"] = {
+            "value": cb / (DDPM_STEPS * sec), "unit": "designs/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{cb} candidates x 1 DDPM step of the C4 shape (R={cr}; {WINDOWS * PAIRS * cr} U-Net forwards of batch {cb}) "
+                      f"with oracle/sampler_ref.py in the reference's loop form, {time.perf_counter() - t0:.0f} s of CPU work"}
+    print(json.dumps(line))
+    if args.profile:
+        for k, v in sorted(classes.items(), key=lambda kv: -kv[1]["ms"]):
+            print(f"# {k:18s} {v['launches']:4d} launches {v['ms']:9.3f} ms", file=sys.stderr)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -39,6 +39,9 @@ class CindmError(RuntimeError):
 _SIGNATURES = {
     "cindm_last_error": (c_char_p, []),
     "cindm_version": (c_int, []),
+    "cindm_launch_count": (ctypes.c_longlong, []),
+    "cindm_profile_enable": (c_int, [c_int]),
+    "cindm_profile_report": (c_int, [c_char_p, c_int]),
     "cindm_create": (c_int, [POINTER(Config), POINTER(c_void_p)]),
     "cindm_destroy": (c_int, [c_void_p]),
     "cindm_load_weight": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int]),

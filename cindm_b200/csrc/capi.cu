@@ -1,6 +1,8 @@
 // extern "C" boundary of libcindm_b200.so (declared in include/cindm_b200.h).
 #include <cmath>
+#include <cstdio>
 #include <cstring>
+#include <tuple>
 
 #include "engine.h"
 
@@ -11,6 +13,29 @@ void set_error(const std::string& msg) { g_last_error = msg; }
 int fail(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
+}
+
+// ---- tracing state
+static long long g_launches = 0;
+static bool g_profiling = false;
+struct ProfEntry { std::string tag; cudaEvent_t e0, e1; double work; };
+static std::vector<ProfEntry> g_prof;
+static std::vector<size_t> g_prof_open;
+void count_launch() { ++g_launches; }
+void add_launches(long long n) { g_launches += n; }
+long long launch_count() { return g_launches; }
+bool profiling_enabled() { return g_profiling; }
+void profile_record(const char* tag, cudaStream_t st, bool begin, double work) {
+    if (begin) {
+        ProfEntry pe; pe.tag = tag; pe.work = work;
+        cudaEventCreate(&pe.e0); cudaEventCreate(&pe.e1);
+        cudaEventRecord(pe.e0, st);
+        g_prof.push_back(pe);
+        g_prof_open.push_back(g_prof.size() - 1);
+    } else if (!g_prof_open.empty()) {
+        cudaEventRecord(g_prof[g_prof_open.back()].e1, st);
+        g_prof_open.pop_back();
+    }
 }
 
 int nbody_rollout(const double* state0, double* traj, int B, int n, int n_steps, int stride, cudaStream_t st);
@@ -46,6 +71,47 @@ extern "C" {
 const char* cindm_last_error(void) { return g_last_error.c_str(); }
 int cindm_version(void) { return 100; }
 
+long long cindm_launch_count(void) { return launch_count(); }
+
+int cindm_profile_enable(int enable) {
+    API_BEGIN
+    cudaDeviceSynchronize();
+    for (auto& pe : g_prof) { cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1); }
+    g_prof.clear(); g_prof_open.clear();
+    g_profiling = enable != 0;
+    return 0;
+    API_END
+}
+
+// Writes "tag,launch_groups,total_ms,work" lines (one per kernel class) into buf; returns bytes needed.
+int cindm_profile_report(char* buf, int capacity) {
+    API_BEGIN
+    cudaDeviceSynchronize();
+    std::map<std::string, std::tuple<int, double, double>> acc;
+    std::vector<std::string> order;
+    for (auto& pe : g_prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pe.e0, pe.e1) != cudaSuccess) continue;
+        if (!acc.count(pe.tag)) order.push_back(pe.tag);
+        auto& a = acc[pe.tag];
+        std::get<0>(a) += 1; std::get<1>(a) += ms; std::get<2>(a) += pe.work;
+    }
+    std::string out;
+    for (auto& tag : order) {
+        auto& a = acc[tag];
+        char line[256];
+        snprintf(line, sizeof line, "%s,%d,%.6f,%.6e\n", tag.c_str(), std::get<0>(a), std::get<1>(a), std::get<2>(a));
+        out += line;
+    }
+    if (buf && capacity > 0) {
+        int n = (int)out.size() < capacity - 1 ? (int)out.size() : capacity - 1;
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return (int)out.size() + 1;
+    API_END
+}
+
 int cindm_create(const cindm_config* cfg, cindm_engine** out) {
     API_BEGIN
     if (!cfg || !out) return fail(-2, "null argument");
@@ -72,6 +138,7 @@ int cindm_destroy(cindm_engine* e) {
     if (e->sb.pred) cudaFree(e->sb.pred);
     if (e->sb.eps) cudaFree(e->sb.eps);
     if (e->sb.t_dev) cudaFree(e->sb.t_dev);
+    graph_cache_clear(e);
     if (e->sb.capture_stream) cudaStreamDestroy(e->sb.capture_stream);
     if (e->sb.ev_in) cudaEventDestroy(e->sb.ev_in);
     if (e->sb.ev_out) cudaEventDestroy(e->sb.ev_out);

@@ -23,11 +23,28 @@ int fail(int code, const std::string& msg);      // records msg, returns code
 
 #define CINDM_CHECK_LAUNCH()                                                                      \
     do {                                                                                          \
+        ::cindm::count_launch();                                                                  \
         cudaError_t _e = cudaGetLastError();                                                      \
         if (_e != cudaSuccess)                                                                    \
             return ::cindm::fail(-101, std::string("kernel launch (") + __FILE__ + ":" +          \
                                            std::to_string(__LINE__) + "): " + cudaGetErrorString(_e)); \
     } while (0)
+
+// ---- built-in tracing: launches counted always; per-kernel-class CUDA-event timing when enabled
+void count_launch();
+void add_launches(long long n);
+long long launch_count();
+bool profiling_enabled();
+void profile_record(const char* tag, cudaStream_t st, bool begin, double work);
+
+// RAII: brackets the kernel launches of one launcher with two events on the launching stream.
+struct KernelTimer {
+    const char* tag; cudaStream_t st; bool on;
+    KernelTimer(const char* t, cudaStream_t s, double work = 0.0) : tag(t), st(s), on(profiling_enabled()) {
+        if (on) profile_record(tag, st, true, work);
+    }
+    ~KernelTimer() { if (on) profile_record(tag, st, false, 0.0); }
+};
 
 #define CINDM_TRY(expr)            \
     do {                           \

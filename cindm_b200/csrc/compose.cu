@@ -80,6 +80,7 @@ int launch_compose_gather(const float* x, float* slices, int B, int n, int nc, i
     const int W = nc + 1, T = H + nc * start, P = n * (n - 1) / 2;
     long long total = (long long)W * P * B * H * 2;
     if (total == 0) return 0;
+    KernelTimer kt("compose_gather", st, (double)total * 16.0 + (double)B * T * n * 16.0);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     compose_gather_kernel<<<blocks, 256, 0, st>>>((const float4*)x, (float4*)slices, B, n, W, start, H, T);
@@ -92,6 +93,7 @@ int launch_compose_scatter(const float* eps_pair, float* eps, int B, int n, int 
     const int W = nc + 1, T = H + nc * start;
     long long total = (long long)B * T * n;
     if (total == 0) return 0;
+    KernelTimer kt("compose_scatter", st, (double)total * 16.0 + (double)W * (n * (n - 1) / 2) * B * H * 32.0);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     compose_scatter_kernel<<<blocks, 256, 0, st>>>((const float4*)eps_pair, (float4*)eps, B, n, W, start, H, T, mode);

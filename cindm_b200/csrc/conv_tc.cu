@@ -486,6 +486,9 @@ int launch_conv_tc(const ConvTcLaunch& a, cudaStream_t st) {
     p.n_tiles = w.cout / n_tile;
     p.k_chunks_per_tap = w.cin / kBlockK;
 
+    // algorithmic work: 2 x nonzero-tap MACs (a k=5, pad=2 conv over H positions has 5H-6 in-range taps)
+    const double nz_taps = w.taps == 1 ? (double)a.H : (double)(5 * a.H - 6);
+    KernelTimer kt("conv_tc", st, 2.0 * (double)a.S * nz_taps * w.cin * w.cout);
     CUtensorMap m0, m1, mb;
     CINDM_TRY(encode_act_map(&m0, a.in0, a.prec, a.S, a.H, a.c0, p.slices_per_tile));
     if (a.in1) CINDM_TRY(encode_act_map(&m1, a.in1, a.prec, a.S, a.H, a.c1, p.slices_per_tile));

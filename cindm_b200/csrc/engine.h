@@ -63,6 +63,10 @@ struct SampleBuffers {           // sized by cindm_sample on first use
     cudaStream_t capture_stream = nullptr;   // used when the caller's stream is the (uncapturable) legacy stream
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     size_t elems = 0;
+    // cached CUDA graph of one (or two) DDPM steps
+    std::string graph_key;
+    cudaGraphExec_t graph_exec = nullptr;
+    long long graph_nodes = 0;
     float* x_alt = nullptr;
     float* pred = nullptr;
     float* eps = nullptr;
@@ -161,6 +165,7 @@ int launch_fill_noise(float* x, int B, int T, int n, uint64_t seed, int64_t cand
                       cudaStream_t st);
 int launch_step_counter(int* t_dev, int delta, cudaStream_t st);
 
+void graph_cache_clear(cindm_engine* e);
 int finalize_weights(cindm_engine* e, cudaStream_t st);
 int reserve_workspace(cindm_engine* e, int64_t S, int prec);
 int64_t workspace_bytes(int64_t S, int prec, int horizon);

@@ -146,6 +146,7 @@ int launch_conv_simt(const ConvLaunch& a, cudaStream_t st) {
     if (p.c0 + p.c1 != p.cin) return fail(-2, "conv: input channels do not match the weight");
     if (p.in1 && (p.c0 % 16) != 0) return fail(-2, "conv: concat split must be a multiple of 16 channels");
     if (p.rows == 0) return 0;
+    KernelTimer kt("conv_simt", st, 2.0 * (double)p.rows * p.taps * p.cin * p.cout);
     switch (a.in_prec) {
         case PREC_F32: return conv_dispatch1<float>(p, a.out_prec, st);
         case PREC_F16: return conv_dispatch1<__half>(p, a.out_prec, st);
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(256) gn_mish_kernel(const float* __restrict__ 
 int launch_gn_mish(const float* in, const NormW& gn, const float* add_vec, const int* t_dev, const void* add_res,
                    void* out, int64_t S, int H, int C, int out_prec, cudaStream_t st) {
     if (S == 0) return 0;
+    KernelTimer kt("gn_mish", st, (double)S * H * C * (4.0 + elem_size(out_prec) * (add_res ? 2 : 1)));
     int blocks = ceil_div(S * 8, 8);
     switch (out_prec) {
         case PREC_F32:
@@ -249,6 +251,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ in
 
 int launch_layernorm(const void* in, const float* g, void* out, int64_t rows, int C, int prec, cudaStream_t st) {
     if (rows == 0) return 0;
+    KernelTimer kt("layernorm", st, (double)rows * C * 2.0 * elem_size(prec));
     int blocks = ceil_div(rows, 8);
     switch (prec) {
         case PREC_F32: layernorm_kernel<float><<<blocks, 256, 0, st>>>((const float*)in, g, (float*)out, rows, C); break;
@@ -317,6 +320,7 @@ __global__ void __launch_bounds__(128) attn_core_kernel(const T* __restrict__ qk
 int launch_attn_core(const void* qkv, void* out, int64_t S, int n, int prec, cudaStream_t st) {
     if (S == 0) return 0;
     if (n > 24) return fail(-2, "attention core supports at most 24 positions");
+    KernelTimer kt("attn_core", st, (double)S * n * 512.0 * elem_size(prec));
     const size_t smem = (3 * 128 * 25 + 4 * 32 * 33) * sizeof(float);
     static bool configured = false;
     if (!configured) {

@@ -219,6 +219,7 @@ int launch_update(const UpdateLaunch& u, cudaStream_t st) {
     p.obj = u.obj;
     long long total = (long long)u.B * u.T * u.n;
     if (total == 0) return 0;
+    KernelTimer kt("ddpm_update", st, (double)total * 16.0 * (u.noise ? 4.0 : 3.0));
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     ddpm_update_kernel<<<blocks, 256, 0, st>>>(p);
@@ -240,11 +241,22 @@ int composed_eps(cindm_engine* e, const float* x, float* eps, int B, int n, int 
     return launch_compose_scatter(e->ws.eps_pair, eps, B, n, nc, start, H, mode, st);
 }
 
+void graph_cache_clear(cindm_engine* e) {
+    if (e->sb.graph_exec) {
+        cudaDeviceSynchronize();
+        cudaGraphExecDestroy(e->sb.graph_exec);
+        e->sb.graph_exec = nullptr;
+    }
+    e->sb.graph_key.clear();
+    e->sb.graph_nodes = 0;
+}
+
 static int ensure_sample_buffers(cindm_engine* e, size_t elems) {
     SampleBuffers& sb = e->sb;
     if (!sb.t_dev) CINDM_CHECK_CUDA(cudaMalloc(&sb.t_dev, sizeof(int)));
     if (sb.elems >= elems) return 0;
     CINDM_CHECK_CUDA(cudaDeviceSynchronize());
+    graph_cache_clear(e);
     if (sb.x_alt) cudaFree(sb.x_alt);
     if (sb.pred) cudaFree(sb.pred);
     if (sb.eps) cudaFree(sb.eps);
@@ -332,27 +344,40 @@ static int sample_loop_on(cindm_engine* e, const cindm_sample_config& c, float* 
         const int iters = c.recurrence > 0 ? c.recurrence : 1;
         const int steps_per_graph = (iters % 2) ? 2 : 1;
         CINDM_CHECK_CUDA(cudaMemcpyAsync(e->sb.t_dev, &c.t_start, sizeof(int), cudaMemcpyHostToDevice, st));
-        cudaGraph_t graph = nullptr;
-        cudaGraphExec_t exec = nullptr;
-        CINDM_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        int rc = 0, gcur = 0;
-        for (int k = 0; k < steps_per_graph && rc == 0; ++k) {
-            rc = issue_step(e, c, bufs, gcur, noise, x0_out, 0, e->sb.t_dev, st);
-            if (rc == 0) rc = launch_step_counter(e->sb.t_dev, -1, st);
+        // the captured step depends on everything but the timestep range (t lives in device memory), unless an
+        // explicit noise tensor is indexed relative to t_start
+        cindm_sample_config kc = c;
+        if (!noise) { kc.t_start = 0; kc.t_end = 0; }
+        std::string key(reinterpret_cast<const char*>(&kc), sizeof(kc));
+        const void* ptrs[4] = {x, noise, x0_out, (const void*)st};
+        key.append(reinterpret_cast<const char*>(ptrs), sizeof(ptrs));
+        SampleBuffers& sb = e->sb;
+        if (!sb.graph_exec || sb.graph_key != key) {
+            graph_cache_clear(e);
+            cudaGraph_t graph = nullptr;
+            CINDM_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const long long before = launch_count();
+            int rc = 0, gcur = 0;
+            for (int k = 0; k < steps_per_graph && rc == 0; ++k) {
+                rc = issue_step(e, c, bufs, gcur, noise, x0_out, 0, e->sb.t_dev, st);
+                if (rc == 0) rc = launch_step_counter(e->sb.t_dev, -1, st);
+            }
+            const long long nodes = launch_count() - before;
+            add_launches(-nodes);                                  // captured, not executed
+            cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) return fail(-100, std::string("graph capture: ") + cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&sb.graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) { sb.graph_exec = nullptr; return fail(-100, std::string("graph instantiate: ") + cudaGetErrorString(ce)); }
+            sb.graph_key = key;
+            sb.graph_nodes = nodes;
         }
-        cudaError_t ce = cudaStreamEndCapture(st, &graph);
-        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-        if (ce != cudaSuccess) return fail(-100, std::string("graph capture: ") + cudaGetErrorString(ce));
-        CINDM_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
         int done = 0;
         for (; done + steps_per_graph <= n_steps; done += steps_per_graph) {
-            ce = cudaGraphLaunch(exec, st);
-            if (ce != cudaSuccess) break;
+            CINDM_CHECK_CUDA(cudaGraphLaunch(sb.graph_exec, st));
+            add_launches(sb.graph_nodes);
         }
-        cudaStreamSynchronize(st);
-        cudaGraphExecDestroy(exec);
-        cudaGraphDestroy(graph);
-        if (ce != cudaSuccess) return fail(-100, std::string("graph launch: ") + cudaGetErrorString(ce));
         for (int t = c.t_start - done; t >= c.t_end; --t)       // odd remainder, issued directly
             CINDM_TRY(issue_step(e, c, bufs, cur, noise, x0_out, t, nullptr, st));
     }

@@ -187,6 +187,7 @@ int reserve_workspace(cindm_engine* e, int64_t S, int prec) {
     if (w.base && w.max_slices >= S && w.precision == prec) return 0;
     if (w.base) {
         CINDM_CHECK_CUDA(cudaDeviceSynchronize());
+        graph_cache_clear(e);
         CINDM_CHECK_CUDA(cudaFree(w.base));
         w = Workspace();
     }

@@ -73,6 +73,15 @@ typedef struct {
 const char* cindm_last_error(void);
 int cindm_version(void);
 
+/* ---- tracing (the reference has none) -----------------------------------
+ * cindm_launch_count: kernels this library has launched in this process (graph replays count
+ * their kernel nodes).  cindm_profile_enable(1) makes every launcher bracket its kernels with CUDA
+ * events on the launching stream (do not use while capturing a graph); cindm_profile_report
+ * writes "class,launch_groups,total_ms,algorithmic_work" lines and returns the bytes needed. */
+long long cindm_launch_count(void);
+int cindm_profile_enable(int enable);
+int cindm_profile_report(char* buf, int capacity);
+
 /* ---- engine life cycle; replaces TemporalUnet1D.__init__ / GaussianDiffusion1D.__init__ /
  *      load_state_dict (model/diffusion_1d.py:519-608, :802-910; driver :163-180) ------------- */
 int cindm_create(const cindm_config* cfg, cindm_engine** out);
