@@ -36,7 +36,11 @@ struct TcParams {
     const void* add_res;      // [S][H][cout] 16-bit or null
     void* out;                // [S][H][cout] 16-bit
     long long S;
-    int H, cout, c0, cin, taps, pad;
+    int H;                    // rows per slice inside an M tile (output positions of this GEMM)
+    int cout, c0, cin, taps;
+    int tap_hoff[5];          // H coordinate where the A box of each tap starts (out-of-range rows read as zero)
+    int tap_wrow[5];          // first row of each tap's block in the [taps*cout][cin] weight matrix
+    int out_mul, out_add;     // output row = tile row * out_mul + out_add (2, parity for the transposed conv)
     int slices_per_tile, rows_used, m_tiles, n_tiles, k_chunks_per_tap;
 };
 
@@ -219,9 +223,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                         uint8_t* b_dst = a_dst + kATileBytes;
                         mbar_expect_tx(&full_bar[stage], tx_bytes);
                         const int ci = kc * kBlockK;
-                        if (ci < p.c0) tma_load_3d(&map_a0, &full_bar[stage], a_dst, ci, tap - p.pad, s0);
-                        else           tma_load_3d(&map_a1, &full_bar[stage], a_dst, ci - p.c0, tap - p.pad, s0);
-                        tma_load_2d(&map_b, &full_bar[stage], b_dst, ci, tap * p.cout + n_tile * N_TILE);
+                        if (ci < p.c0) tma_load_3d(&map_a0, &full_bar[stage], a_dst, ci, p.tap_hoff[tap], s0);
+                        else           tma_load_3d(&map_a1, &full_bar[stage], a_dst, ci - p.c0, p.tap_hoff[tap], s0);
+                        tma_load_2d(&map_b, &full_bar[stage], b_dst, ci, p.tap_wrow[tap] + n_tile * N_TILE);
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -344,7 +348,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                     packed[i >> 1] = pack2<T16>(y[0], y[1]);
                 }
                 if (valid) {
-                    uint4* op = reinterpret_cast<uint4*>(out + grow * p.cout + n0 + c);
+                    uint4* op = reinterpret_cast<uint4*>(out + (grow * p.out_mul + p.out_add) * p.cout + n0 + c);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         op[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
@@ -377,13 +381,15 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     return fn;
 }
 
-int encode_act_map(CUtensorMap* map, const void* base, int prec, long long S, int H, int C, int box_slices) {
+// box_rows positions per slice are loaded, every h_stride-th position starting at the tap's H coordinate
+int encode_act_map(CUtensorMap* map, const void* base, int prec, long long S, int H, int C, int box_slices,
+                   int box_rows, int h_stride) {
     auto enc = get_encode();
     if (!enc) return fail(-100, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)S};
     cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)H * C * 2};
-    cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)H, (cuuint32_t)box_slices};
-    cuuint32_t estr[3] = {1, 1, 1};
+    cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)(box_rows * h_stride), (cuuint32_t)box_slices};
+    cuuint32_t estr[3] = {1, (cuuint32_t)h_stride, 1};
     CUresult r = enc(map, prec == PREC_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                      const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -460,25 +466,33 @@ int dispatch(const ConvTcLaunch& a, const CUtensorMap& m0, const CUtensorMap& m1
 
 }  // namespace
 
-int launch_conv_tc(const ConvTcLaunch& a, cudaStream_t st) {
+static int launch_conv_tc_one(const ConvTcLaunch& a, int parity, cudaStream_t st) {
     const ConvW& w = *a.w;
-    if (a.prec != PREC_F16 && a.prec != PREC_BF16) return fail(-2, "conv_tc: 16-bit precisions only");
-    if (w.taps != 1 && w.taps != 5) return fail(-2, "conv_tc: taps must be 1 or 5");
-    if (w.cin % 64 || w.cout % 64) return fail(-2, "conv_tc: channel counts must be multiples of 64");
-    if (a.c0 + (a.in1 ? a.c1 : 0) != w.cin) return fail(-2, "conv_tc: input channels do not match the weight");
-    if (a.in1 && (a.c0 % 64)) return fail(-2, "conv_tc: concat split must be a multiple of 64 channels");
-    if (a.H < 1 || a.H > 128) return fail(-2, "conv_tc: bad H");
-    if (a.S == 0) return 0;
-    if (a.epilogue == EPI_GN_MISH && !a.gn) return fail(-2, "conv_tc: GroupNorm parameters missing");
-
     TcParams p;
     p.bias = w.bias;
     p.gamma = a.gn ? a.gn->gamma : nullptr;
     p.beta = a.gn ? a.gn->beta : nullptr;
     p.add_vec = a.add_vec; p.t_dev = a.t_dev; p.add_res = a.add_res; p.out = a.out;
-    p.S = a.S; p.H = a.H; p.cout = w.cout; p.c0 = a.c0; p.cin = w.cin; p.taps = w.taps; p.pad = w.taps / 2;
-    p.slices_per_tile = 128 / a.H;
-    p.rows_used = p.slices_per_tile * a.H;
+    p.S = a.S; p.cout = w.cout; p.c0 = a.c0; p.cin = w.cin;
+    p.out_mul = 1; p.out_add = 0;
+    int h_stride = 1;
+    double nz_taps;                         // in-range taps summed over one slice's output positions
+    if (a.mode == TC_SAME) {
+        p.H = a.H; p.taps = w.taps;
+        for (int k = 0; k < w.taps; ++k) { p.tap_hoff[k] = k - w.taps / 2; p.tap_wrow[k] = k * w.cout; }
+        nz_taps = w.taps == 1 ? (double)a.H : (double)(5 * a.H - 6);
+    } else if (a.mode == TC_DOWN) {         // out[p] = sum_k in[2p + k - 1] W[k]
+        p.H = a.H / 2; p.taps = 3; h_stride = 2;
+        for (int k = 0; k < 3; ++k) { p.tap_hoff[k] = k - 1; p.tap_wrow[k] = k * w.cout; }
+        nz_taps = 3.0 * p.H - 1.0;
+    } else {                                // out[2m] = in[m] W[1] + in[m-1] W[3];  out[2m+1] = in[m] W[2] + in[m+1] W[0]
+        p.H = a.H; p.taps = 2; p.out_mul = 2; p.out_add = parity;
+        p.tap_hoff[0] = 0; p.tap_wrow[0] = (parity ? 2 : 1) * w.cout;
+        p.tap_hoff[1] = parity ? 1 : -1; p.tap_wrow[1] = (parity ? 0 : 3) * w.cout;
+        nz_taps = 2.0 * a.H - 1.0;
+    }
+    p.slices_per_tile = 128 / p.H;
+    p.rows_used = p.slices_per_tile * p.H;
     p.m_tiles = (int)((a.S + p.slices_per_tile - 1) / p.slices_per_tile);
     int n_tile;
     if (a.epilogue == EPI_GN_MISH) n_tile = w.cout < 256 ? w.cout : 256;
@@ -486,16 +500,35 @@ int launch_conv_tc(const ConvTcLaunch& a, cudaStream_t st) {
     p.n_tiles = w.cout / n_tile;
     p.k_chunks_per_tap = w.cin / kBlockK;
 
-    // algorithmic work: 2 x nonzero-tap MACs (a k=5, pad=2 conv over H positions has 5H-6 in-range taps)
-    const double nz_taps = w.taps == 1 ? (double)a.H : (double)(5 * a.H - 6);
+    // algorithmic work: 2 x nonzero-tap MACs
     KernelTimer kt("conv_tc", st, 2.0 * (double)a.S * nz_taps * w.cin * w.cout);
     CUtensorMap m0, m1, mb;
-    CINDM_TRY(encode_act_map(&m0, a.in0, a.prec, a.S, a.H, a.c0, p.slices_per_tile));
-    if (a.in1) CINDM_TRY(encode_act_map(&m1, a.in1, a.prec, a.S, a.H, a.c1, p.slices_per_tile));
+    CINDM_TRY(encode_act_map(&m0, a.in0, a.prec, a.S, a.H, a.c0, p.slices_per_tile, p.H, h_stride));
+    if (a.in1) CINDM_TRY(encode_act_map(&m1, a.in1, a.prec, a.S, a.H, a.c1, p.slices_per_tile, p.H, h_stride));
     else m1 = m0;
     CINDM_TRY(encode_weight_map(&mb, w.w16[a.prec], a.prec, w.taps * w.cout, w.cin, n_tile));
     if (a.prec == PREC_F16) return dispatch<__half>(a, m0, m1, mb, p, n_tile, st);
     return dispatch<__nv_bfloat16>(a, m0, m1, mb, p, n_tile, st);
+}
+
+int launch_conv_tc(const ConvTcLaunch& a, cudaStream_t st) {
+    const ConvW& w = *a.w;
+    if (a.prec != PREC_F16 && a.prec != PREC_BF16) return fail(-2, "conv_tc: 16-bit precisions only");
+    const int want_taps = a.mode == TC_SAME ? w.taps : (a.mode == TC_DOWN ? 3 : 4);
+    if (w.taps != want_taps || (a.mode == TC_SAME && w.taps != 1 && w.taps != 5))
+        return fail(-2, "conv_tc: tap count does not match the conv mode");
+    if (w.cin % 64 || w.cout % 64) return fail(-2, "conv_tc: channel counts must be multiples of 64");
+    if (a.c0 + (a.in1 ? a.c1 : 0) != w.cin) return fail(-2, "conv_tc: input channels do not match the weight");
+    if (a.in1 && (a.c0 % 64)) return fail(-2, "conv_tc: concat split must be a multiple of 64 channels");
+    if (a.H < 1 || a.H > 128 || (a.mode == TC_DOWN && (a.H % 2))) return fail(-2, "conv_tc: bad H");
+    if (a.mode != TC_SAME && (a.epilogue != EPI_BIAS || a.add_res)) return fail(-2, "conv_tc: resampling convs take the plain epilogue");
+    if (a.S == 0) return 0;
+    if (a.epilogue == EPI_GN_MISH && !a.gn) return fail(-2, "conv_tc: GroupNorm parameters missing");
+    if (a.mode == TC_UP) {
+        CINDM_TRY(launch_conv_tc_one(a, 0, st));
+        return launch_conv_tc_one(a, 1, st);
+    }
+    return launch_conv_tc_one(a, 0, st);
 }
 
 }  // namespace cindm

@@ -5,6 +5,9 @@
 namespace cindm {
 
 enum { EPI_BIAS = 0, EPI_GN_MISH = 1 };
+// TC_SAME: k in {1,5}, stride 1, pad k/2 (H -> H).  TC_DOWN: Downsample1d k=3 s=2 p=1 (H -> H/2).
+// TC_UP: Upsample1d ConvTranspose k=4 s=2 p=1 (H -> 2H), run as two 2-tap GEMMs (even / odd outputs).
+enum { TC_SAME = 0, TC_DOWN = 1, TC_UP = 2 };
 
 struct ConvTcLaunch {
     const void* in0 = nullptr; int c0 = 0;      // [S][H][c0] 16-bit
@@ -16,7 +19,8 @@ struct ConvTcLaunch {
     const void* add_res = nullptr;              // residual tensor [S][H][cout] added last
     void* out = nullptr;                        // [S][H][cout] 16-bit
     int64_t S = 0;
-    int H = 0;
+    int H = 0;                                  // input positions per slice
+    int mode = TC_SAME;
     int prec = PREC_F16;
     int epilogue = EPI_BIAS;
 };

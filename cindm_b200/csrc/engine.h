@@ -137,11 +137,25 @@ int launch_gn_mish(const float* in, const NormW& gn, const float* add_vec, const
                    void* out, int64_t S, int H, int C, int out_prec, cudaStream_t st);
 int launch_layernorm(const void* in, const float* g, void* out, int64_t rows, int C, int prec, cudaStream_t st);
 int launch_attn_core(const void* qkv, void* out, int64_t S, int n, int prec, cudaStream_t st);
-int launch_time_tables(cindm_engine* e, cudaStream_t st);
+
+// fused first block (16-bit paths): see kernels_fused.cu
+struct StemLaunch {
+    const float* x = nullptr;                     // slices [S][24][8], or the design tensor when gather != 0
+    int gather = 0, B = 0, n = 0, start = 0, T = 0;
+    const ConvW* conv0 = nullptr; const NormW* gn = nullptr; const ConvW* res = nullptr;
+    const float* tbias = nullptr; const int* t_dev = nullptr;
+    void* out_b0 = nullptr; void* out_res = nullptr;
+    int64_t S = 0; int prec = PREC_F16;
+};
+int launch_stem(const StemLaunch& a, cudaStream_t st);
+int launch_head(const void* in, const ConvW& w, float* out, int64_t rows, int prec, cudaStream_t st);
+
+// when non-null, the U-Net reads its slices straight out of the design tensor x[B][T][4n]
+struct GatherSpec { const float* x; int B, n, nc, start; };
 
 // t_dev == nullptr: use the host value t; else the device integer *t_dev (CUDA-graph replay)
 int unet_forward(cindm_engine* e, const float* slices, int64_t S, int t, const int* t_dev, float* eps_pair,
-                 int precision, int conv_engine, cudaStream_t st);
+                 int precision, int conv_engine, cudaStream_t st, const GatherSpec* gather = nullptr);
 
 int launch_compose_gather(const float* x, float* slices, int B, int n, int nc, int start, int H, cudaStream_t st);
 int launch_compose_scatter(const float* eps_pair, float* eps, int B, int n, int nc, int start, int H, int mode,

@@ -1,0 +1,337 @@
+// Per-slice fused kernels of the throughput path (16-bit activations, fp32 math):
+//   stem  : [composition gather] + conv(8->64,k5) + GroupNorm + Mish + time bias, and the 1x1 residual conv
+//   head  : final 1x1 conv 64 -> 8 to fp32 eps_pair
+//   attn  : linear-attention core (softmax_n(k), k v^T, ctx^T q) with register-tiled 4x4 outer products
+// They replace generic SIMT GEMM launches whose K or N extent (8 channels) is too small to tile well.
+#include "engine.h"
+
+namespace cindm {
+
+// ------------------------------------------------------------------------------------------
+// Linear attention core, one CTA (256 threads = 4 heads x 64) per slice.
+//   qkv: [S][n][384] (q | k | v, each 4 heads x 32), out: [S][n][128]
+//   reference LinearAttentionTemporal.forward, model/diffusion_1d.py:281-291
+// Shared memory rows are padded to 132 floats so that both the float4 channel reads (stage 3)
+// and the per-position scalar reads (stage 4) are bank-conflict free.
+// ------------------------------------------------------------------------------------------
+constexpr int kAttnRow = 132;
+constexpr int kCtxRow = 36;
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<__half>(const __half* p, float (&v)[8]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+    float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+template <typename T>
+__device__ __forceinline__ void store4(T* p, float a, float b, float c, float d);
+template <>
+__device__ __forceinline__ void store4<__half>(__half* p, float a, float b, float c, float d) {
+    __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+    uint2 u = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    *reinterpret_cast<uint2*>(p) = u;
+}
+template <>
+__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float a, float b, float c, float d) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    uint2 u = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    *reinterpret_cast<uint2*>(p) = u;
+}
+template <>
+__device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) attn_core_tiled_kernel(const T* __restrict__ qkv, T* __restrict__ out, int n) {
+    extern __shared__ __align__(16) float sm[];
+    float* sq = sm;                          // [n][132]  q * 32^-0.5
+    float* sk = sq + n * kAttnRow;           // [n][132]
+    float* sv = sk + n * kAttnRow;           // [n][132]
+    float* ctx = sv + n * kAttnRow;          // [4][32][36]
+    const long long s = blockIdx.x;
+    const int tid = threadIdx.x;
+    const T* src = qkv + s * (long long)n * 384;
+    // ---- 1. load (8 channels per thread per iteration)
+    for (int i = tid; i < n * 48; i += 256) {
+        const int pos = i / 48, c8 = (i - pos * 48) * 8;
+        float v[8];
+        load8<T>(src + pos * 384 + c8, v);
+        float* dst;
+        float scale = 1.0f;
+        if (c8 < 128) { dst = sq + pos * kAttnRow + c8; scale = 0.17677669529663687f; }
+        else if (c8 < 256) dst = sk + pos * kAttnRow + (c8 - 128);
+        else dst = sv + pos * kAttnRow + (c8 - 256);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dst[k] = v[k] * scale;
+    }
+    __syncthreads();
+    // ---- 2. softmax over positions for every k channel
+    if (tid < 128) {
+        float m = -INFINITY;
+        for (int j = 0; j < n; ++j) m = fmaxf(m, sk[j * kAttnRow + tid]);
+        float sum = 0.f;
+        for (int j = 0; j < n; ++j) {
+            float e = __expf(sk[j * kAttnRow + tid] - m);
+            sk[j * kAttnRow + tid] = e;
+            sum += e;
+        }
+        const float inv = 1.0f / sum;
+        for (int j = 0; j < n; ++j) sk[j * kAttnRow + tid] *= inv;
+    }
+    __syncthreads();
+    const int h = tid >> 6, l = tid & 63;
+    // ---- 3. ctx[d][e] = sum_j k[d][j] v[e][j], 4x4 register tile per thread
+    {
+        const int bi = l >> 3, bj = l & 7;
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+        for (int j = 0; j < n; ++j) {
+            const float4 kd = *reinterpret_cast<const float4*>(sk + j * kAttnRow + h * 32 + 4 * bi);
+            const float4 ve = *reinterpret_cast<const float4*>(sv + j * kAttnRow + h * 32 + 4 * bj);
+            const float ka[4] = {kd.x, kd.y, kd.z, kd.w}, va[4] = {ve.x, ve.y, ve.z, ve.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(ka[a], va[b], acc[a][b]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+            *reinterpret_cast<float4*>(ctx + (h * 32 + 4 * bi + a) * kCtxRow + 4 * bj) =
+                make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+    }
+    __syncthreads();
+    // ---- 4. out[e][j] = sum_d ctx[d][e] q[d][j]; thread = 4 channels x positions {ng, ng+8, ng+16}
+    {
+        const int be = l & 7, ng = l >> 3;
+        float acc[3][4];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[k][b] = 0.f;
+        const bool on[3] = {ng < n, ng + 8 < n, ng + 16 < n};
+        for (int d = 0; d < 32; ++d) {
+            const float4 c4 = *reinterpret_cast<const float4*>(ctx + (h * 32 + d) * kCtxRow + 4 * be);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (!on[k]) continue;
+                const float qv = sq[(ng + 8 * k) * kAttnRow + h * 32 + d];
+                acc[k][0] = fmaf(c4.x, qv, acc[k][0]);
+                acc[k][1] = fmaf(c4.y, qv, acc[k][1]);
+                acc[k][2] = fmaf(c4.z, qv, acc[k][2]);
+                acc[k][3] = fmaf(c4.w, qv, acc[k][3]);
+            }
+        }
+        T* dst = out + s * (long long)n * 128;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (on[k]) store4<T>(dst + (ng + 8 * k) * 128 + h * 32 + 4 * be, acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+    }
+}
+
+int launch_attn_core(const void* qkv, void* out, int64_t S, int n, int prec, cudaStream_t st) {
+    if (S == 0) return 0;
+    if (n > 24) return fail(-2, "attention core supports at most 24 positions");
+    KernelTimer kt("attn_core", st, (double)S * n * 512.0 * elem_size(prec));
+    const size_t smem = ((size_t)3 * n * kAttnRow + 4 * 32 * kCtxRow) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        const int mx = (3 * 24 * kAttnRow + 4 * 32 * kCtxRow) * (int)sizeof(float);
+        CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_tiled_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_tiled_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_tiled_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        configured = true;
+    }
+    switch (prec) {
+        case PREC_F32: attn_core_tiled_kernel<float><<<(unsigned)S, 256, smem, st>>>((const float*)qkv, (float*)out, n); break;
+        case PREC_F16: attn_core_tiled_kernel<__half><<<(unsigned)S, 256, smem, st>>>((const __half*)qkv, (__half*)out, n); break;
+        case PREC_BF16:
+            attn_core_tiled_kernel<__nv_bfloat16><<<(unsigned)S, 256, smem, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, n);
+            break;
+        default: return fail(-2, "attn: bad precision");
+    }
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Stem: the first ResidualTemporalBlock's first Conv1dBlock (8 -> 64, k=5) + GroupNorm(8) + Mish + time
+// bias, and its 1x1 residual conv (8 -> 64), straight from the fp32 design tensor.  With
+// gather != 0 the composition gather (reference :985) is fused into the loader: slice s =
+// (kk*P + pair)*B + b reads x[b][kk*start + h][4*body + f].
+// One warp-pair (64 threads = 64 output channels) per slice; weights live in registers.
+// ------------------------------------------------------------------------------------------
+struct StemParams {
+    const float* x;            // gather: [B][T][4n];  else slices [S][24][8]
+    const float* w0;           // [5][8][64]
+    const float* b0;           // [64]
+    const float* gamma; const float* beta;
+    const float* tbias;        // [64] or [timesteps][64] with t_dev
+    const int* t_dev;
+    const float* wr;           // [1][8][64]
+    const float* br;           // [64]
+    void* out_b0;              // [S][24][64]
+    void* out_res;             // [S][24][64]
+    long long S;
+    int gather, B, n, P, start, T;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) stem_kernel(StemParams p) {
+    __shared__ float xs[4][24 + 4][8];                      // per-slice input with 2 zero rows of padding each side
+    const int sub = threadIdx.x >> 6, co = threadIdx.x & 63;
+    const long long s = (long long)blockIdx.x * 4 + sub;
+    const bool active = s < p.S;
+    // ---- load the slice (24 x 8 floats = 48 float4; 64 threads)
+    if (co < 4) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { xs[sub][co < 2 ? co : 24 + co][c] = 0.f; }
+    }
+    if (active && co < 48) {
+        const int h = co >> 1, half = co & 1;
+        float4 v;
+        if (p.gather) {
+            const int b = (int)(s % p.B);
+            const int wp = (int)(s / p.B);
+            const int pr = wp % p.P, kk = wp / p.P;
+            int ii = 0, rem = pr;
+            while (rem >= p.n - 1 - ii) { rem -= p.n - 1 - ii; ++ii; }
+            const int jj = ii + 1 + rem;
+            const int body = half ? jj : ii;
+            v = reinterpret_cast<const float4*>(p.x)[((long long)b * p.T + kk * p.start + h) * p.n + body];
+        } else {
+            v = reinterpret_cast<const float4*>(p.x)[(s * 24 + h) * 2 + half];
+        }
+        *reinterpret_cast<float4*>(&xs[sub][h + 2][half * 4]) = v;
+    }
+    // ---- weights of this output channel
+    float w[5][8], wr[8];
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) w[k][c] = p.w0[(k * 8 + c) * 64 + co];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) wr[c] = p.wr[c * 64 + co];
+    const float bias0 = p.b0[co], biasr = p.br[co];
+    const float ga = p.gamma[co], be = p.beta[co];
+    const float tb = p.t_dev ? p.tbias[(long long)(*p.t_dev) * 64 + co] : p.tbias[co];
+    __syncthreads();
+    if (!active) return;
+    float y[24];
+    float sum = 0.f;
+#pragma unroll
+    for (int h = 0; h < 24; ++h) {
+        float a = bias0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) a = fmaf(w[k][c], xs[sub][h + k][c], a);
+        y[h] = a;
+        sum += a;
+    }
+    // GroupNorm group = 8 consecutive channels (lanes) x 24 positions
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+    const float mean = sum * (1.0f / 192.0f);
+    float sq = 0.f;
+#pragma unroll
+    for (int h = 0; h < 24; ++h) { float d = y[h] - mean; sq = fmaf(d, d, sq); }
+    sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+    sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+    sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+    const float rstd = rsqrtf(sq * (1.0f / 192.0f) + 1e-5f);
+    T* ob = reinterpret_cast<T*>(p.out_b0) + s * 24 * 64 + co;
+    T* orr = reinterpret_cast<T*>(p.out_res) + s * 24 * 64 + co;
+#pragma unroll
+    for (int h = 0; h < 24; ++h) {
+        float v = (y[h] - mean) * rstd * ga + be;
+        v = mish_fast(v) + tb;
+        ob[h * 64] = from_f32<T>(v);
+        float r = biasr;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) r = fmaf(wr[c], xs[sub][h + 2][c], r);
+        orr[h * 64] = from_f32<T>(r);
+    }
+}
+
+int launch_stem(const StemLaunch& a, cudaStream_t st) {
+    if (a.S == 0) return 0;
+    KernelTimer kt("stem", st, (double)a.S * 24 * (32.0 + 2.0 * 64 * elem_size(a.prec)));
+    StemParams p;
+    p.x = a.x; p.w0 = a.conv0->w; p.b0 = a.conv0->bias; p.gamma = a.gn->gamma; p.beta = a.gn->beta;
+    p.tbias = a.tbias; p.t_dev = a.t_dev; p.wr = a.res->w; p.br = a.res->bias;
+    p.out_b0 = a.out_b0; p.out_res = a.out_res; p.S = a.S;
+    p.gather = a.gather; p.B = a.B; p.n = a.n; p.P = a.n * (a.n - 1) / 2; p.start = a.start; p.T = a.T;
+    const unsigned blocks = (unsigned)((a.S + 3) / 4);
+    if (a.prec == PREC_F16) stem_kernel<__half><<<blocks, 256, 0, st>>>(p);
+    else if (a.prec == PREC_BF16) stem_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p);
+    else return fail(-2, "stem kernel is built for the 16-bit precisions");
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Head: final 1x1 conv 64 -> 8 (+bias) from 16-bit activations to fp32 eps_pair [S][24][8]
+// (reference final_conv[1], model/diffusion_1d.py:607).  One thread per (slice, position) row.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ in, const float* __restrict__ w,
+                                                   const float* __restrict__ bias, float* __restrict__ out,
+                                                   long long rows) {
+    __shared__ float sw[64][8];
+    __shared__ float sb[8];
+    for (int i = threadIdx.x; i < 512; i += 256) sw[i >> 3][i & 7] = w[i];        // w: [1][64][8]
+    if (threadIdx.x < 8) sb[threadIdx.x] = bias[threadIdx.x];
+    __syncthreads();
+    const long long r = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (r >= rows) return;
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = sb[o];
+    const T* src = in + r * 64;
+#pragma unroll
+    for (int c8 = 0; c8 < 64; c8 += 8) {
+        float v[8];
+        load8<T>(src + c8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int o = 0; o < 8; ++o) acc[o] = fmaf(v[k], sw[c8 + k][o], acc[o]);
+    }
+    float4* dst = reinterpret_cast<float4*>(out + r * 8);
+    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
+int launch_head(const void* in, const ConvW& w, float* out, int64_t rows, int prec, cudaStream_t st) {
+    if (rows == 0) return 0;
+    KernelTimer kt("head", st, (double)rows * (64.0 * elem_size(prec) + 32.0));
+    const unsigned blocks = (unsigned)((rows + 255) / 256);
+    if (prec == PREC_F16) head_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)in, w.w, w.bias, out, rows);
+    else if (prec == PREC_BF16) head_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in, w.w, w.bias, out, rows);
+    else return fail(-2, "head kernel is built for the 16-bit precisions");
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace cindm

@@ -266,82 +266,6 @@ int launch_layernorm(const void* in, const float* g, void* out, int64_t rows, in
 }
 
 // ------------------------------------------------------------------------------------------
-// Linear attention core (4 heads x 32), reference LinearAttentionTemporal.forward :281-291:
-//   q *= 32^-0.5;  k = softmax_n(k);  ctx[d][e] = sum_n k[d][n] v[e][n];  out[e][n] = sum_d ctx[d][e] q[d][n]
-// qkv: [S][n][384] (q | k | v, each head-major 4 x 32);  out: [S][n][128].  One CTA per slice.
-// ------------------------------------------------------------------------------------------
-template <typename T, int NMAX>
-__global__ void __launch_bounds__(128) attn_core_kernel(const T* __restrict__ qkv, T* __restrict__ out, int n) {
-    extern __shared__ float attn_smem[];
-    float (*sq)[NMAX + 1] = reinterpret_cast<float (*)[NMAX + 1]>(attn_smem);
-    float (*sk)[NMAX + 1] = sq + 128;
-    float (*sv)[NMAX + 1] = sk + 128;
-    float (*ctx)[32][33] = reinterpret_cast<float (*)[32][33]>(attn_smem + 3 * 128 * (NMAX + 1));
-    const long long s = blockIdx.x;
-    const int tid = threadIdx.x;
-    const T* src = qkv + s * (long long)n * 384;
-    for (int i = tid; i < n * 384; i += 128) {
-        int pos = i / 384, c = i - pos * 384;
-        float v = to_f32<T>(src[i]);
-        if (c < 128) sq[c][pos] = v * 0.17677669529663687f;      // 32^-0.5
-        else if (c < 256) sk[c - 128][pos] = v;
-        else sv[c - 256][pos] = v;
-    }
-    __syncthreads();
-    {   // softmax over positions for k row `tid`
-        float m = -INFINITY;
-        for (int j = 0; j < n; ++j) m = fmaxf(m, sk[tid][j]);
-        float sum = 0.f;
-        for (int j = 0; j < n; ++j) {
-            float e = expf(sk[tid][j] - m);
-            sk[tid][j] = e;
-            sum += e;
-        }
-        float inv = 1.0f / sum;
-        for (int j = 0; j < n; ++j) sk[tid][j] *= inv;
-    }
-    __syncthreads();
-    const int h = tid >> 5, d = tid & 31;
-    for (int e = 0; e < 32; ++e) {
-        float a = 0.f;
-        for (int j = 0; j < n; ++j) a = fmaf(sk[tid][j], sv[h * 32 + e][j], a);
-        ctx[h][d][e] = a;
-    }
-    __syncthreads();
-    T* dst = out + s * (long long)n * 128;
-    for (int j = 0; j < n; ++j) {
-        float a = 0.f;
-#pragma unroll 8
-        for (int dd = 0; dd < 32; ++dd) a = fmaf(ctx[h][dd][d], sq[h * 32 + dd][j], a);
-        dst[j * 128 + tid] = from_f32<T>(a);
-    }
-}
-
-int launch_attn_core(const void* qkv, void* out, int64_t S, int n, int prec, cudaStream_t st) {
-    if (S == 0) return 0;
-    if (n > 24) return fail(-2, "attention core supports at most 24 positions");
-    KernelTimer kt("attn_core", st, (double)S * n * 512.0 * elem_size(prec));
-    const size_t smem = (3 * 128 * 25 + 4 * 32 * 33) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_kernel<float, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_kernel<__half, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_kernel<__nv_bfloat16, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    switch (prec) {
-        case PREC_F32: attn_core_kernel<float, 24><<<(unsigned)S, 128, smem, st>>>((const float*)qkv, (float*)out, n); break;
-        case PREC_F16: attn_core_kernel<__half, 24><<<(unsigned)S, 128, smem, st>>>((const __half*)qkv, (__half*)out, n); break;
-        case PREC_BF16:
-            attn_core_kernel<__nv_bfloat16, 24><<<(unsigned)S, 128, smem, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, n);
-            break;
-        default: return fail(-2, "attn: bad precision");
-    }
-    CINDM_CHECK_LAUNCH();
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------------
 // Time embedding tables.  `time` is identical for every slice of a forward (reference
 // p_sample_compose_inside :1287 builds torch.full((b,), t)), so time_mlp (:537-542) and every
 // block's Mish->Linear (:493-497) depend on t only: evaluate them once for t = 0..T-1.

@@ -236,8 +236,13 @@ int composed_eps(cindm_engine* e, const float* x, float* eps, int B, int n, int 
     const int64_t S = (int64_t)(nc + 1) * (n * (n - 1) / 2) * B;
     if (S > e->ws.max_slices || e->ws.precision != prec)
         return fail(-6, "workspace not reserved for this slice count / precision (call cindm_reserve)");
-    CINDM_TRY(launch_compose_gather(x, e->ws.slices, B, n, nc, start, H, st));
-    CINDM_TRY(unet_forward(e, e->ws.slices, S, t, t_dev, e->ws.eps_pair, prec, conv_engine, st));
+    if (prec == PREC_F32) {
+        CINDM_TRY(launch_compose_gather(x, e->ws.slices, B, n, nc, start, H, st));
+        CINDM_TRY(unet_forward(e, e->ws.slices, S, t, t_dev, e->ws.eps_pair, prec, conv_engine, st));
+    } else {
+        GatherSpec gs{x, B, n, nc, start};          // the stem kernel gathers straight from x
+        CINDM_TRY(unet_forward(e, nullptr, S, t, t_dev, e->ws.eps_pair, prec, conv_engine, st, &gs));
+    }
     return launch_compose_scatter(e->ws.eps_pair, eps, B, n, nc, start, H, mode, st);
 }
 

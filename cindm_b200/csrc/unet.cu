@@ -257,12 +257,13 @@ struct Fwd {
     // plain conv (1x1, strided, transposed) with bias and optional residual
     int conv_plain(const ConvW& w, const void* in0, int c0, const void* in1, int c1, int in_prec, int Hin, int Hout,
                    int stride, int pad, int transposed, const void* res, void* out, int out_prec) {
-        if (engine == CINDM_CONV_TCGEN05 && in_prec != PREC_F32 && out_prec != PREC_F32 && w.taps == 1 &&
+        if (engine == CINDM_CONV_TCGEN05 && in_prec != PREC_F32 && out_prec != PREC_F32 &&
             (w.cin % 64) == 0 && (w.cout % 64) == 0) {
             ConvTcLaunch a;
             a.in0 = in0; a.c0 = c0; a.in1 = in1; a.c1 = c1; a.w = &w; a.gn = nullptr;
             a.add_vec = nullptr; a.add_res = res; a.out = out; a.S = S; a.H = Hin; a.prec = prec;
             a.epilogue = EPI_BIAS;
+            a.mode = transposed ? TC_UP : (stride == 2 ? TC_DOWN : TC_SAME);
             return launch_conv_tc(a, st);
         }
         ConvLaunch a;
@@ -300,7 +301,8 @@ struct Fwd {
 }  // namespace
 
 int unet_forward(cindm_engine* e, const float* slices, int64_t S, int t, const int* t_dev, float* eps_pair,
-                 int precision, int conv_engine, cudaStream_t st) {
+                 int precision, int conv_engine, cudaStream_t st, const GatherSpec* gather) {
+    if (gather && precision == PREC_F32) return fail(-5, "fused gather is part of the 16-bit stem kernel");
     if (!e->finalized) return fail(-4, "weights not finalized");
     if (!t_dev && (t < 0 || t >= e->cfg.timesteps)) return fail(-2, "timestep out of range");
     if (S > e->ws.max_slices || e->ws.precision != precision)
@@ -331,7 +333,22 @@ int unet_forward(cindm_engine* e, const float* slices, int64_t S, int t, const i
     int x_prec = PREC_F32;
     for (int i = 0; i < 4; ++i) {
         int tmp_i = next_buf(cur_i, -1), out_i = next_buf(cur_i, tmp_i);
-        CINDM_TRY(f.resblock(e->downs_rb[i][0], x_in, ch[i], nullptr, 0, x_prec, H, w.act[tmp_i], w.act[out_i]));
+        if (i == 0 && precision != PREC_F32) {
+            // fused stem: [gather +] conv0 + GN + Mish + time bias, and the 1x1 residual conv, in one kernel
+            const ResBlockW& r = e->downs_rb[0][0];
+            StemLaunch sl;
+            sl.x = gather ? gather->x : slices;
+            if (gather) { sl.gather = 1; sl.B = gather->B; sl.n = gather->n; sl.start = gather->start;
+                          sl.T = e->cfg.horizon + gather->nc * gather->start; }
+            sl.conv0 = &r.conv0; sl.gn = &r.gn0; sl.res = &r.res;
+            sl.tbias = t_dev ? r.time_bias : r.time_bias + (size_t)t * r.conv0.cout; sl.t_dev = t_dev;
+            sl.out_b0 = w.act[tmp_i]; sl.out_res = w.res; sl.S = S; sl.prec = precision;
+            CINDM_TRY(launch_stem(sl, st));
+            CINDM_TRY(f.conv_block(r.conv1, r.gn1, w.act[tmp_i], r.conv0.cout, nullptr, 0, precision, H, nullptr, w.res,
+                                   w.act[out_i]));
+        } else {
+            CINDM_TRY(f.resblock(e->downs_rb[i][0], x_in, ch[i], nullptr, 0, x_prec, H, w.act[tmp_i], w.act[out_i]));
+        }
         cur = w.act[out_i]; cur_i = out_i; x_in = cur; x_prec = precision;
         CINDM_TRY(f.record_tap("downs." + std::to_string(i) + ".0", cur, ch[i + 1], H));
         tmp_i = next_buf(cur_i, -1); out_i = next_buf(cur_i, tmp_i);
@@ -402,7 +419,8 @@ int unet_forward(cindm_engine* e, const float* slices, int64_t S, int t, const i
                                w.act[out_i]));
         cur = w.act[out_i]; cur_i = out_i;
         CINDM_TRY(f.record_tap("final_conv.0", cur, dim, H));
-        CINDM_TRY(f.conv_plain(e->final_out, cur, dim, nullptr, 0, precision, H, H, 1, 0, 0, nullptr, eps_pair, PREC_F32));
+        if (precision != PREC_F32) CINDM_TRY(launch_head(cur, e->final_out, eps_pair, S * H, precision, st));
+        else CINDM_TRY(f.conv_plain(e->final_out, cur, dim, nullptr, 0, precision, H, H, 1, 0, 0, nullptr, eps_pair, PREC_F32));
     }
     return 0;
 }
