@@ -301,12 +301,15 @@ def run_b200(args, rank, local_rank, world):
                                             _lib.PRECISIONS[args.precision],
                                             _lib.CONV_TCGEN05 if args.engine == "tcgen05" else _lib.CONV_SIMT, st))
         stream.synchronize()
-        buf = ctypes.create_string_buffer(1 << 16)
+        buf = ctypes.create_string_buffer(1 << 18)
         L.cindm_profile_report(buf, len(buf))
         _lib.check(L.cindm_profile_enable(0))
+    detail = {}
     for row in buf.value.decode().strip().splitlines():
         tag, groups, total_ms, work = row.split(",")
-        classes[tag] = {"launches": int(groups), "ms": float(total_ms), "work": float(work)}
+        detail[tag] = {"launches": int(groups), "ms": float(total_ms), "work": float(work)}
+        c = classes.setdefault(tag.split(" ")[0], {"launches": 0, "ms": 0.0, "work": 0.0})
+        c["launches"] += int(groups); c["ms"] += float(total_ms); c["work"] += float(work)
     eval_ms = sum(c["ms"] for c in classes.values())
     S = WINDOWS * PAIRS * B
     if "conv_tc" in classes and classes["conv_tc"]["ms"] > 0:
@@ -350,6 +353,9 @@ def run_b200(args, rank, local_rank, world):
     if args.profile:
         for k, v in sorted(classes.items(), key=lambda kv: -kv[1]["ms"]):
             print(f"# {k:18s} {v['launches']:4d} launches {v['ms']:9.3f} ms", file=sys.stderr)
+        for k, v in sorted(detail.items(), key=lambda kv: -kv[1]["ms"]):
+            rate = v["work"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0
+            print(f"#   {k:44s} {v['launches']:3d} x {v['ms'] / v['launches']:8.4f} ms  {rate:9.2f} T(FLOP|B)/s", file=sys.stderr)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -39,7 +39,7 @@ void profile_record(const char* tag, cudaStream_t st, bool begin, double work) {
 }
 
 int nbody_rollout(const double* state0, double* traj, int B, int n, int n_steps, int stride, cudaStream_t st);
-int score_designs(const float* pred, float* mae, float* objective, int B, int T, int n, double tx, double ty,
+int score_designs(const float* pred, double* mae, double* objective, int B, int T, int n, double tx, double ty,
                   cudaStream_t st);
 
 }  // namespace cindm
@@ -369,7 +369,7 @@ int cindm_nbody_rollout(const double* state0, double* traj, int B, int n, int n_
     API_END
 }
 
-int cindm_score_designs(const float* pred, float* mae, float* objective, int B, int T, int n, double tx, double ty,
+int cindm_score_designs(const float* pred, double* mae, double* objective, int B, int T, int n, double tx, double ty,
                         void* stream) {
     API_BEGIN
     return score_designs(pred, mae, objective, B, T, n, tx, ty, (cudaStream_t)stream);

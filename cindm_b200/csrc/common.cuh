@@ -39,11 +39,11 @@ void profile_record(const char* tag, cudaStream_t st, bool begin, double work);
 
 // RAII: brackets the kernel launches of one launcher with two events on the launching stream.
 struct KernelTimer {
-    const char* tag; cudaStream_t st; bool on;
-    KernelTimer(const char* t, cudaStream_t s, double work = 0.0) : tag(t), st(s), on(profiling_enabled()) {
-        if (on) profile_record(tag, st, true, work);
+    cudaStream_t st; bool on;
+    KernelTimer(const char* t, cudaStream_t s, double work = 0.0) : st(s), on(profiling_enabled()) {
+        if (on) profile_record(t, st, true, work);
     }
-    ~KernelTimer() { if (on) profile_record(tag, st, false, 0.0); }
+    ~KernelTimer() { if (on) profile_record("", st, false, 0.0); }
 };
 
 #define CINDM_TRY(expr)            \

@@ -13,6 +13,7 @@
 //   (C/8 channels x H positions) of each slice (a tile owns whole slices, so the statistics are
 //   CTA-local), Mish, then the time-embedding bias or the residual, and store 16-bit activations.
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-5 epilogue.
+#include <cstdio>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -501,7 +502,10 @@ static int launch_conv_tc_one(const ConvTcLaunch& a, int parity, cudaStream_t st
     p.k_chunks_per_tap = w.cin / kBlockK;
 
     // algorithmic work: 2 x nonzero-tap MACs
-    KernelTimer kt("conv_tc", st, 2.0 * (double)a.S * nz_taps * w.cin * w.cout);
+    char tag[96];
+    snprintf(tag, sizeof tag, "conv_tc %s H%d %d->%d k%d %s", a.mode == TC_SAME ? "same" : (a.mode == TC_DOWN ? "down" : "up"),
+             a.H, w.cin, w.cout, w.taps, a.epilogue == EPI_GN_MISH ? "gn" : "bias");
+    KernelTimer kt(tag, st, 2.0 * (double)a.S * nz_taps * w.cin * w.cout);
     CUtensorMap m0, m1, mb;
     CINDM_TRY(encode_act_map(&m0, a.in0, a.prec, a.S, a.H, a.c0, p.slices_per_tile, p.H, h_stride));
     if (a.in1) CINDM_TRY(encode_act_map(&m1, a.in1, a.prec, a.S, a.H, a.c1, p.slices_per_tile, p.H, h_stride));

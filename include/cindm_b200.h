@@ -167,8 +167,9 @@ int cindm_fill_initial_noise(float* x_dev, int batch, int t_total, int n_bodies,
 int cindm_nbody_rollout(const double* state0_dev, double* traj_dev, int batch, int n_bodies, int n_steps,
                         int stride, void* stream);
 /* fused metrics of the driver (inverse_design_diffusion_1d.py:316-337): pred[B][T][4n] fp32 (normalised
- * units), runs the rollout from frame 0 and returns per-candidate MAE and last-frame objective */
-int cindm_score_designs(const float* pred_dev, float* mae_dev, float* objective_dev, int batch, int t_total,
+ * units), runs the rollout from frame 0 and returns, per candidate, mean |cat(frame0, simulated) - pred| over
+ * all T*4n entries and the mean over bodies of the last simulated frame's distance to the target (fp64) */
+int cindm_score_designs(const float* pred_dev, double* mae_dev, double* objective_dev, int batch, int t_total,
                         int n_bodies, double target_x, double target_y, void* stream);
 
 #ifdef __cplusplus
