@@ -12,7 +12,8 @@
 // * Epilogue warps read TMEM with tcgen05.ld and apply, fused: conv bias, GroupNorm(8) over
 //   (C/8 channels x H positions) of each slice (a tile owns whole slices, so the statistics are
 //   CTA-local), Mish, then the time-embedding bias or the residual, and store 16-bit activations.
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-5 epilogue.
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-9 epilogue
+// (two warps per TMEM lane quarter, each owning half of the tile's columns).
 #include <cstdio>
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -26,7 +27,7 @@ namespace {
 constexpr int kStages = 4;
 constexpr int kBlockK = 64;                  // 64 x 16-bit = one 128-byte swizzle row
 constexpr int kATileBytes = 128 * 128;       // 128 rows x 128 B
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;             // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 
 struct TcParams {
     const float* bias;        // [cout] or null
@@ -188,7 +189,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
         fence_barrier_init();
         tma_prefetch_desc(&map_a0);
         tma_prefetch_desc(&map_b);
@@ -263,12 +264,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
         __syncwarp();
     } else {
-        // =============================== epilogue (4 warps) ===============================
+        // =============================== epilogue (8 warps) ===============================
+        // Two warps share each TMEM lane quarter (hardware: warp w may read lanes 32*(w%4)..+31); each takes
+        // half of the tile's columns.
         const int q = warp & 3;                                   // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;                         // which half of the N tile
         const int row = q * 32 + lane;                            // tile row == TMEM lane
-        const int et = (warp - 2) * 32 + lane;                    // 0..127 index among epilogue threads
+        const int et = (warp - 2) * 32 + lane;                    // 0..255 index among epilogue threads
+        constexpr int HALF_N = N_TILE / 2;
+        constexpr int HG = (EPI == EPI_GN_MISH) ? HALF_N / CPG : 1;   // groups owned by one thread
         T16* out = reinterpret_cast<T16*>(p.out);
         const T16* res = reinterpret_cast<const T16*>(p.add_res);
+        const float4* bias4 = reinterpret_cast<const float4*>(vec_bias);
+        const float4* gamma4 = reinterpret_cast<const float4*>(vec_gamma);
+        const float4* beta4 = reinterpret_cast<const float4*>(vec_beta);
+        const float4* add4 = reinterpret_cast<const float4*>(vec_add);
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
@@ -279,30 +289,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             const long long grow = s0 * p.H + row;                // global row (slices are contiguous rows)
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N_TILE);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N_TILE + half * HALF_N);
+            const int cbase = n0 + half * HALF_N;                 // first channel this thread handles
             float v[32];
+            float g_mean[HG], g_rstd[HG];
             if (EPI == EPI_GN_MISH) {
-                // ---- pass 1: per-row partial sums of every group ----
-                float s1[NG], s2[NG];
+                // ---- pass 1: per-row partial sums of every group in this thread's column half ----
+                float s1[HG], s2[HG];
 #pragma unroll
-                for (int g = 0; g < NG; ++g) { s1[g] = 0.f; s2[g] = 0.f; }
+                for (int g = 0; g < HG; ++g) { s1[g] = 0.f; s2[g] = 0.f; }
 #pragma unroll
-                for (int c = 0; c < N_TILE; c += 32) {
+                for (int c = 0; c < HALF_N; c += 32) {
                     tmem_ld32(taddr + c, v);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float x = v[i] + vec_bias[n0 + c + i];
-                        const int g = (c + i) / CPG;
-                        s1[g] += x;
-                        s2[g] = fmaf(x, x, s2[g]);
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 b4 = bias4[(cbase + c + i) >> 2];
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float x = v[i + u] + bb[u];
+                            const int g = (c + i + u) / CPG;
+                            s1[g] += x;
+                            s2[g] = fmaf(x, x, s2[g]);
+                        }
                     }
                 }
 #pragma unroll
-                for (int g = 0; g < NG; ++g) { part[row * PSTRIDE + 2 * g] = s1[g]; part[row * PSTRIDE + 2 * g + 1] = s2[g]; }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int g = 0; g < HG; ++g) {
+                    part[row * PSTRIDE + 2 * (half * HG + g)] = s1[g];
+                    part[row * PSTRIDE + 2 * (half * HG + g) + 1] = s2[g];
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 // ---- reduce over the H rows of each slice ----
                 const float inv_cnt = 1.0f / (float)(p.H * CPG);
-                for (int idx = et; idx < p.slices_per_tile * NG; idx += 128) {
+                for (int idx = et; idx < p.slices_per_tile * NG; idx += 256) {
                     const int s_l = idx / NG, g = idx - s_l * NG;
                     float a = 0.f, b = 0.f;
                     for (int h = 0; h < p.H; ++h) {
@@ -313,43 +333,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                     const float var = fmaxf(b * inv_cnt - mean * mean, 0.f);
                     stats[s_l * 8 + g] = make_float2(mean, rsqrtf(var + 1e-5f));
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+                for (int g = 0; g < HG; ++g) {
+                    const float2 st = stats[sl * 8 + half * HG + g];
+                    g_mean[g] = st.x; g_rstd[g] = st.y;
+                }
             }
             // ---- pass 2 (or the only pass): normalise / activate / add / store ----
-#pragma unroll 1
-            for (int c = 0; c < N_TILE; c += 32) {
+#pragma unroll
+            for (int c = 0; c < HALF_N; c += 32) {
                 tmem_ld32(taddr + c, v);
                 uint32_t packed[16];
                 uint4 rv[4];
                 if (res != nullptr && valid) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(res + grow * p.cout + n0 + c);
+                    const uint4* rp = reinterpret_cast<const uint4*>(res + grow * p.cout + cbase + c);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) rv[j] = rp[j];
                 }
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float y[2];
+                for (int i = 0; i < 32; i += 4) {
+                    const int ch4 = (cbase + c + i) >> 2;
+                    const float4 b4 = bias4[ch4];
+                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                    float y[4];
+                    if (EPI == EPI_GN_MISH) {
+                        const float4 ga4 = gamma4[ch4], be4 = beta4[ch4], ad4 = add4[ch4];
+                        const float ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w}, be[4] = {be4.x, be4.y, be4.z, be4.w};
+                        const float ad[4] = {ad4.x, ad4.y, ad4.z, ad4.w};
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int ch = n0 + c + i + u;
-                        float x = v[i + u] + vec_bias[ch];
-                        if (EPI == EPI_GN_MISH) {
-                            const float2 st = stats[sl * 8 + (c + i + u) / CPG];
-                            x = (x - st.x) * st.y * vec_gamma[ch] + vec_beta[ch];
-                            x = mish_fast(x);
-                            x += vec_add[ch];
+                        for (int u = 0; u < 4; ++u) {
+                            const int g = (c + i + u) / CPG;
+                            const float sc = g_rstd[g] * ga[u];
+                            const float x = fmaf(v[i + u] + bb[u] - g_mean[g], sc, be[u]);
+                            y[u] = mish_fast(x) + ad[u];
                         }
-                        y[u] = x;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) y[u] = v[i + u] + bb[u];
                     }
                     if (res != nullptr) {
                         const uint32_t* rw = reinterpret_cast<const uint32_t*>(rv);
-                        float2 r2 = unpack2<T16>(rw[i >> 1]);
-                        y[0] += r2.x; y[1] += r2.y;
+                        const float2 r0 = unpack2<T16>(rw[i >> 1]), r1 = unpack2<T16>(rw[(i >> 1) + 1]);
+                        y[0] += r0.x; y[1] += r0.y; y[2] += r1.x; y[3] += r1.y;
                     }
                     packed[i >> 1] = pack2<T16>(y[0], y[1]);
+                    packed[(i >> 1) + 1] = pack2<T16>(y[2], y[3]);
                 }
                 if (valid) {
-                    uint4* op = reinterpret_cast<uint4*>(out + (grow * p.out_mul + p.out_add) * p.cout + n0 + c);
+                    uint4* op = reinterpret_cast<uint4*>(out + (grow * p.out_mul + p.out_add) * p.cout + cbase + c);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         op[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);

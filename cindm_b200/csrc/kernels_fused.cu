@@ -40,6 +40,27 @@ __device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
 }
 
 template <typename T>
+__device__ __forceinline__ void unpack8(const uint4& raw, const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void unpack8<__half>(const uint4& raw, const __half*, float (&v)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <>
+__device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& raw, const __nv_bfloat16*, float (&v)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <>
+__device__ __forceinline__ void unpack8<float>(const uint4& raw, const float* p, float (&v)[8]) {
+    const float4 b = reinterpret_cast<const float4*>(p)[1];
+    v[0] = __uint_as_float(raw.x); v[1] = __uint_as_float(raw.y); v[2] = __uint_as_float(raw.z); v[3] = __uint_as_float(raw.w);
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+template <typename T>
 __device__ __forceinline__ void store4(T* p, float a, float b, float c, float d);
 template <>
 __device__ __forceinline__ void store4<__half>(__half* p, float a, float b, float c, float d) {
@@ -64,22 +85,35 @@ __global__ void __launch_bounds__(256) attn_core_tiled_kernel(const T* __restric
     float* sq = sm;                          // [n][132]  q * 32^-0.5
     float* sk = sq + n * kAttnRow;           // [n][132]
     float* sv = sk + n * kAttnRow;           // [n][132]
-    float* ctx = sv + n * kAttnRow;          // [4][32][36]
+    float* ctx = sk;                         // [4][32][36], written over k/v once they are consumed
     const long long s = blockIdx.x;
     const int tid = threadIdx.x;
     const T* src = qkv + s * (long long)n * 384;
-    // ---- 1. load (8 channels per thread per iteration)
-    for (int i = tid; i < n * 48; i += 256) {
-        const int pos = i / 48, c8 = (i - pos * 48) * 8;
-        float v[8];
-        load8<T>(src + pos * 384 + c8, v);
-        float* dst;
-        float scale = 1.0f;
-        if (c8 < 128) { dst = sq + pos * kAttnRow + c8; scale = 0.17677669529663687f; }
-        else if (c8 < 256) dst = sk + pos * kAttnRow + (c8 - 128);
-        else dst = sv + pos * kAttnRow + (c8 - 256);
+    // ---- 1. load: all global reads are issued before the first use (n*48 <= 1152 16-byte vectors, <= 5 per thread)
+    {
+        constexpr int kMaxVec = 5;
+        uint4 raw[kMaxVec];
+        const int nvec = n * 48;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) dst[k] = v[k] * scale;
+        for (int r = 0; r < kMaxVec; ++r) {
+            const int i = tid + r * 256;
+            if (i < nvec) raw[r] = reinterpret_cast<const uint4*>(src)[i * (int)(sizeof(T) * 8 / 16)];
+        }
+#pragma unroll
+        for (int r = 0; r < kMaxVec; ++r) {
+            const int i = tid + r * 256;
+            if (i >= nvec) continue;
+            const int pos = i / 48, c8 = (i - pos * 48) * 8;
+            float v[8];
+            unpack8<T>(raw[r], src + (long long)i * 8, v);
+            float* dst;
+            float scale = 1.0f;
+            if (c8 < 128) { dst = sq + pos * kAttnRow + c8; scale = 0.17677669529663687f; }
+            else if (c8 < 256) dst = sk + pos * kAttnRow + (c8 - 128);
+            else dst = sv + pos * kAttnRow + (c8 - 256);
+            *reinterpret_cast<float4*>(dst) = make_float4(v[0] * scale, v[1] * scale, v[2] * scale, v[3] * scale);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4] * scale, v[5] * scale, v[6] * scale, v[7] * scale);
+        }
     }
     __syncthreads();
     // ---- 2. softmax over positions for every k channel
@@ -114,6 +148,7 @@ __global__ void __launch_bounds__(256) attn_core_tiled_kernel(const T* __restric
 #pragma unroll
                 for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(ka[a], va[b], acc[a][b]);
         }
+        __syncthreads();                     // everyone is done reading k / v: reuse their storage for ctx
 #pragma unroll
         for (int a = 0; a < 4; ++a)
             *reinterpret_cast<float4*>(ctx + (h * 32 + 4 * bi + a) * kCtxRow + 4 * bj) =
@@ -129,6 +164,7 @@ __global__ void __launch_bounds__(256) attn_core_tiled_kernel(const T* __restric
 #pragma unroll
             for (int b = 0; b < 4; ++b) acc[k][b] = 0.f;
         const bool on[3] = {ng < n, ng + 8 < n, ng + 16 < n};
+#pragma unroll 4
         for (int d = 0; d < 32; ++d) {
             const float4 c4 = *reinterpret_cast<const float4*>(ctx + (h * 32 + d) * kCtxRow + 4 * be);
 #pragma unroll
@@ -148,14 +184,19 @@ __global__ void __launch_bounds__(256) attn_core_tiled_kernel(const T* __restric
     }
 }
 
+static size_t attn_smem_bytes(int n) {
+    size_t kv = (size_t)2 * n * kAttnRow, cx = (size_t)4 * 32 * kCtxRow;
+    return ((size_t)n * kAttnRow + (kv > cx ? kv : cx)) * sizeof(float);
+}
+
 int launch_attn_core(const void* qkv, void* out, int64_t S, int n, int prec, cudaStream_t st) {
     if (S == 0) return 0;
     if (n > 24) return fail(-2, "attention core supports at most 24 positions");
     KernelTimer kt("attn_core", st, (double)S * n * 512.0 * elem_size(prec));
-    const size_t smem = ((size_t)3 * n * kAttnRow + 4 * 32 * kCtxRow) * sizeof(float);
+    const size_t smem = attn_smem_bytes(n);
     static bool configured = false;
     if (!configured) {
-        const int mx = (3 * 24 * kAttnRow + 4 * 32 * kCtxRow) * (int)sizeof(float);
+        const int mx = (int)attn_smem_bytes(24);
         CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_tiled_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_tiled_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_tiled_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));

@@ -48,7 +48,8 @@ def eval_simu(cond_design, design_fn, n_bodies, rollout_steps, time_interval=4):
     cond_simu = cond_simu.reshape(cond_simu.shape[0], n_bodies, -1)
     pred_simu = simulation(cond_simu, rollout_steps * time_interval, stride=time_interval)
     pred_simu = pred_simu.reshape(pred_simu.shape[0], pred_simu.shape[1], -1)
-    pred_simu = pred_simu.to(cond_design.device) / 200.0
+    # true fp64 division (torch's CUDA scalar-divisor fast path multiplies by the reciprocal instead)
+    pred_simu = torch.div(pred_simu.to(cond_design.device), torch.full((), 200.0, dtype=torch.float64, device=pred_simu.device))
     return pred_simu, design_fn(pred_simu)
 
 
