@@ -39,7 +39,8 @@ struct TcParams {
     void* out;                // [S][H][cout] 16-bit
     long long S;
     int H;                    // rows per slice inside an M tile (output positions of this GEMM)
-    int cout, c0, cin, taps;
+    int cout, c0, c1, cin, taps;
+    int kpp;                  // Toeplitz: 64-channel K chunks per input position (= cin / 64)
     int tap_hoff[5];          // H coordinate where the A box of each tap starts (out-of-range rows read as zero)
     int tap_wrow[5];          // first row of each tap's block in the [taps*cout][cin] weight matrix
     int out_mul, out_add;     // output row = tile row * out_mul + out_add (2, parity for the transposed conv)
@@ -167,6 +168,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     constexpr int kStageBytes = kATileBytes + kBTileBytes;
     constexpr int NG = (EPI == EPI_GN_MISH) ? N_TILE / CPG : 1;       // GroupNorm groups inside one N tile
     constexpr int PSTRIDE = 2 * NG + 1;
+    constexpr int ACC_STRIDE = (N_TILE == 192) ? 256 : N_TILE;        // TMEM columns between the two accumulators
+    constexpr bool HAS_GN = (EPI != EPI_BIAS);
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -201,7 +204,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if (addv && p.t_dev) addv += (long long)(*p.t_dev) * p.cout;
         for (int c = threadIdx.x; c < p.cout; c += kThreads) {
             vec_bias[c] = p.bias ? p.bias[c] : 0.f;
-            if (EPI == EPI_GN_MISH) { vec_gamma[c] = p.gamma[c]; vec_beta[c] = p.beta[c]; }
+            if (HAS_GN) { vec_gamma[c] = p.gamma[c]; vec_beta[c] = p.beta[c]; }
             vec_add[c] = addv ? addv[c] : 0.f;
         }
     }
@@ -224,10 +227,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                         uint8_t* a_dst = tiles + stage * kStageBytes;
                         uint8_t* b_dst = a_dst + kATileBytes;
                         mbar_expect_tx(&full_bar[stage], tx_bytes);
-                        const int ci = kc * kBlockK;
-                        if (ci < p.c0) tma_load_3d(&map_a0, &full_bar[stage], a_dst, ci, p.tap_hoff[tap], s0);
-                        else           tma_load_3d(&map_a1, &full_bar[stage], a_dst, ci - p.c0, p.tap_hoff[tap], s0);
-                        tma_load_2d(&map_b, &full_bar[stage], b_dst, ci, p.tap_wrow[tap] + n_tile * N_TILE);
+                        if (EPI == EPI_GN_MISH_T3) {
+                            // K index = (input position q, channel ci); the A matrix is the [S][3*C] view of the tensor
+                            const int qpos = kc / p.kpp, ci = (kc - qpos * p.kpp) * kBlockK;
+                            if (ci < p.c0) tma_load_3d(&map_a0, &full_bar[stage], a_dst, qpos * p.c0 + ci, 0, s0);
+                            else           tma_load_3d(&map_a1, &full_bar[stage], a_dst, qpos * p.c1 + ci - p.c0, 0, s0);
+                            tma_load_2d(&map_b, &full_bar[stage], b_dst, kc * kBlockK, n_tile * N_TILE);
+                        } else {
+                            const int ci = kc * kBlockK;
+                            if (ci < p.c0) tma_load_3d(&map_a0, &full_bar[stage], a_dst, ci, p.tap_hoff[tap], s0);
+                            else           tma_load_3d(&map_a1, &full_bar[stage], a_dst, ci - p.c0, p.tap_hoff[tap], s0);
+                            tma_load_2d(&map_b, &full_bar[stage], b_dst, ci, p.tap_wrow[tap] + n_tile * N_TILE);
+                        }
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -244,7 +255,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N_TILE);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
                 for (int kc = 0; kc < k_chunks; ++kc) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -289,7 +300,87 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             const long long grow = s0 * p.H + row;                // global row (slices are contiguous rows)
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N_TILE + half * HALF_N);
+            if constexpr (EPI == EPI_GN_MISH_T3) {
+                // ---------- block-Toeplitz tile: row = slice, 192 columns = (group, position, channel) ----------
+                constexpr int GCOLS = 3 * CPG;                     // accumulator columns of one GroupNorm group
+                const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_STRIDE + half * 96);
+                const long long slice = s0 + row;
+                const bool ok = slice < p.S;
+                const int g0 = n_tile * (192 / GCOLS);
+                float v[32];
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) {
+                    const int j0 = half * 96 + cc * 32;
+                    const int gl = j0 / GCOLS, rem = j0 - gl * GCOLS, pp = rem / CPG;
+                    const int chb = (g0 + gl) * CPG + (rem - pp * CPG);
+                    tmem_ld32(tbase + cc * 32, v);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 b4 = bias4[(chb + i) >> 2];
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { const float x = v[i + u] + bb[u]; s1 += x; s2 = fmaf(x, x, s2); }
+                    }
+                }
+                if (CPG == 64) {
+                    // the group spans both column halves: exchange partial sums with the partner warp (double-buffered
+                    // by accumulator parity so a fast warp cannot overwrite what its partner still has to read)
+                    float* ex = part + acc * 512;
+                    ex[(half * 128 + row) * 2] = s1; ex[(half * 128 + row) * 2 + 1] = s2;
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    s1 += ex[((half ^ 1) * 128 + row) * 2]; s2 += ex[((half ^ 1) * 128 + row) * 2 + 1];
+                }
+                const float mean = s1 * (1.0f / (float)GCOLS);
+                const float rstd = rsqrtf(fmaxf(s2 * (1.0f / (float)GCOLS) - mean * mean, 0.f) + 1e-5f);
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) {
+                    const int j0 = half * 96 + cc * 32;
+                    const int gl = j0 / GCOLS, rem = j0 - gl * GCOLS, pp = rem / CPG;
+                    const int chb = (g0 + gl) * CPG + (rem - pp * CPG);
+                    const long long off = (slice * 3 + pp) * p.cout + chb;
+                    tmem_ld32(tbase + cc * 32, v);
+                    uint32_t packed[16];
+                    uint4 rv[4];
+                    if (res != nullptr && ok) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(res + off);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) rv[j] = rp[j];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const int ch4 = (chb + i) >> 2;
+                        const float4 b4 = bias4[ch4], ga4 = gamma4[ch4], be4 = beta4[ch4], ad4 = add4[ch4];
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w};
+                        const float be[4] = {be4.x, be4.y, be4.z, be4.w}, ad[4] = {ad4.x, ad4.y, ad4.z, ad4.w};
+                        float y[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float x = fmaf(v[i + u] + bb[u] - mean, rstd * ga[u], be[u]);
+                            y[u] = mish_fast(x) + ad[u];
+                        }
+                        if (res != nullptr) {
+                            const uint32_t* rw = reinterpret_cast<const uint32_t*>(rv);
+                            const float2 r0 = unpack2<T16>(rw[i >> 1]), r1 = unpack2<T16>(rw[(i >> 1) + 1]);
+                            y[0] += r0.x; y[1] += r0.y; y[2] += r1.x; y[3] += r1.y;
+                        }
+                        packed[i >> 1] = pack2<T16>(y[0], y[1]);
+                        packed[(i >> 1) + 1] = pack2<T16>(y[2], y[3]);
+                    }
+                    if (ok) {
+                        uint4* op = reinterpret_cast<uint4*>(out + off);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            op[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_STRIDE + half * HALF_N);
             const int cbase = n0 + half * HALF_N;                 // first channel this thread handles
             float v[32];
             float g_mean[HG], g_rstd[HG];
@@ -480,6 +571,13 @@ int launch_instance(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensor
 template <typename T16>
 int dispatch(const ConvTcLaunch& a, const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& mb, const TcParams& p,
              int n_tile, cudaStream_t st) {
+    if (a.epilogue == EPI_GN_MISH_T3) {
+        switch (p.cout) {
+            case 256: return launch_instance<T16, 192, 32, EPI_GN_MISH_T3>(m0, m1, mb, p, st);
+            case 512: return launch_instance<T16, 192, 64, EPI_GN_MISH_T3>(m0, m1, mb, p, st);
+        }
+        return fail(-2, "conv_tc: the block-Toeplitz path is built for 256 / 512 output channels");
+    }
     if (a.epilogue == EPI_GN_MISH) {
         switch (p.cout) {
             case 64: return launch_instance<T16, 64, 8, EPI_GN_MISH>(m0, m1, mb, p, st);
@@ -506,8 +604,26 @@ static int launch_conv_tc_one(const ConvTcLaunch& a, int parity, cudaStream_t st
     p.gamma = a.gn ? a.gn->gamma : nullptr;
     p.beta = a.gn ? a.gn->beta : nullptr;
     p.add_vec = a.add_vec; p.t_dev = a.t_dev; p.add_res = a.add_res; p.out = a.out;
-    p.S = a.S; p.cout = w.cout; p.c0 = a.c0; p.cin = w.cin;
+    p.S = a.S; p.cout = w.cout; p.c0 = a.c0; p.c1 = a.in1 ? a.c1 : 0; p.cin = w.cin; p.kpp = w.cin / kBlockK;
     p.out_mul = 1; p.out_add = 0;
+    if (a.epilogue == EPI_GN_MISH_T3) {
+        // one dense GEMM: rows = slices, K = 3*cin, N = 3*cout in (group, position, channel) order
+        p.H = 1; p.taps = 1; p.tap_hoff[0] = 0; p.tap_wrow[0] = 0;
+        p.slices_per_tile = 128; p.rows_used = 128;
+        p.m_tiles = (int)((a.S + 127) / 128);
+        p.n_tiles = 3 * w.cout / 192;
+        p.k_chunks_per_tap = 3 * w.cin / kBlockK;
+        char tag[96];
+        snprintf(tag, sizeof tag, "conv_tc toep H3 %d->%d k5 gn", w.cin, w.cout);
+        KernelTimer kt(tag, st, 2.0 * (double)a.S * 9.0 * w.cin * w.cout);
+        CUtensorMap m0, m1, mb;
+        CINDM_TRY(encode_act_map(&m0, a.in0, a.prec, a.S, 1, 3 * a.c0, 128, 1, 1));
+        if (a.in1) CINDM_TRY(encode_act_map(&m1, a.in1, a.prec, a.S, 1, 3 * a.c1, 128, 1, 1));
+        else m1 = m0;
+        CINDM_TRY(encode_weight_map(&mb, w.w16t[a.prec], a.prec, 3 * w.cout, 3 * w.cin, 192));
+        if (a.prec == PREC_F16) return dispatch<__half>(a, m0, m1, mb, p, 192, st);
+        return dispatch<__nv_bfloat16>(a, m0, m1, mb, p, 192, st);
+    }
     int h_stride = 1;
     double nz_taps;                         // in-range taps summed over one slice's output positions
     if (a.mode == TC_SAME) {
@@ -559,7 +675,9 @@ int launch_conv_tc(const ConvTcLaunch& a, cudaStream_t st) {
     if (a.H < 1 || a.H > 128 || (a.mode == TC_DOWN && (a.H % 2))) return fail(-2, "conv_tc: bad H");
     if (a.mode != TC_SAME && (a.epilogue != EPI_BIAS || a.add_res)) return fail(-2, "conv_tc: resampling convs take the plain epilogue");
     if (a.S == 0) return 0;
-    if (a.epilogue == EPI_GN_MISH && !a.gn) return fail(-2, "conv_tc: GroupNorm parameters missing");
+    if (a.epilogue != EPI_BIAS && !a.gn) return fail(-2, "conv_tc: GroupNorm parameters missing");
+    if (a.epilogue == EPI_GN_MISH_T3 && (a.H != 3 || w.taps != 5 || a.mode != TC_SAME || !w.w16t[a.prec]))
+        return fail(-2, "conv_tc: the block-Toeplitz path needs H == 3, k == 5 and the repacked operand");
     if (a.mode == TC_UP) {
         CINDM_TRY(launch_conv_tc_one(a, 0, st));
         return launch_conv_tc_one(a, 1, st);

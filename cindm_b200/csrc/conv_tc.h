@@ -4,7 +4,10 @@
 
 namespace cindm {
 
-enum { EPI_BIAS = 0, EPI_GN_MISH = 1 };
+// EPI_GN_MISH_T3: k=5 conv at H=3 as ONE dense GEMM [S, 3*Cin] x [3*Cin, 3*Cout] (block-Toeplitz weights, no
+// zero taps: 9 instead of 15 tap-blocks), rows = slices, columns ordered (group, position, channel) so that a
+// GroupNorm group is 192 / 96 consecutive accumulator columns of one row.
+enum { EPI_BIAS = 0, EPI_GN_MISH = 1, EPI_GN_MISH_T3 = 2 };
 // TC_SAME: k in {1,5}, stride 1, pad k/2 (H -> H).  TC_DOWN: Downsample1d k=3 s=2 p=1 (H -> H/2).
 // TC_UP: Upsample1d ConvTranspose k=4 s=2 p=1 (H -> 2H), run as two 2-tap GEMMs (even / odd outputs).
 enum { TC_SAME = 0, TC_DOWN = 1, TC_UP = 2 };

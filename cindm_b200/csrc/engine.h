@@ -22,6 +22,7 @@ struct ConvW {
     float* w = nullptr;
     float* bias = nullptr;        // [cout] or null
     void* w16[3] = {nullptr, nullptr, nullptr};
+    void* w16t[3] = {nullptr, nullptr, nullptr};   // H=3 block-Toeplitz operand [(g,p,c)][(q,ci)], see conv_tc.h
 };
 
 struct NormW {
@@ -104,6 +105,7 @@ struct cindm_engine {
     cindm::Workspace ws;
     cindm::SampleBuffers sb;
 
+    bool use_toeplitz = true;              // H=3 convs as one dense block-Toeplitz GEMM (tcgen05 engine)
     bool taps_enabled = false;
     std::map<std::string, cindm::Tap> taps;
     std::vector<void*> tap_allocs;

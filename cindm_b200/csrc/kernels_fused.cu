@@ -80,25 +80,33 @@ __device__ __forceinline__ void store4<float>(float* p, float a, float b, float 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) attn_core_tiled_kernel(const T* __restrict__ qkv, T* __restrict__ out, int n) {
+__global__ void __launch_bounds__(256) attn_core_tiled_kernel(const T* __restrict__ qkv, T* __restrict__ out, int n,
+                                                              long long S) {
     extern __shared__ __align__(16) float sm[];
     float* sq = sm;                          // [n][132]  q * 32^-0.5
     float* sk = sq + n * kAttnRow;           // [n][132]
     float* sv = sk + n * kAttnRow;           // [n][132]
     float* ctx = sk;                         // [4][32][36], written over k/v once they are consumed
-    const long long s = blockIdx.x;
     const int tid = threadIdx.x;
-    const T* src = qkv + s * (long long)n * 384;
-    // ---- 1. load: all global reads are issued before the first use (n*48 <= 1152 16-byte vectors, <= 5 per thread)
-    {
-        constexpr int kMaxVec = 5;
-        uint4 raw[kMaxVec];
-        const int nvec = n * 48;
+    const int h = tid >> 6, l = tid & 63;
+    constexpr int kMaxVec = 5;               // n*48 <= 1152 16-byte vectors per slice, <= 5 per thread
+    constexpr int kVecStride = (int)(sizeof(T) * 8 / 16);
+    const int nvec = n * 48;
+    uint4 raw[kMaxVec];
+    // persistent CTA: slices blockIdx.x, +gridDim.x, ...; the next slice's global reads are in flight while
+    // the current one is computed
+    long long s = blockIdx.x;
+    if (s < S) {
+        const T* src = qkv + s * (long long)n * 384;
 #pragma unroll
         for (int r = 0; r < kMaxVec; ++r) {
             const int i = tid + r * 256;
-            if (i < nvec) raw[r] = reinterpret_cast<const uint4*>(src)[i * (int)(sizeof(T) * 8 / 16)];
+            if (i < nvec) raw[r] = reinterpret_cast<const uint4*>(src)[i * kVecStride];
         }
+    }
+    for (; s < S; s += gridDim.x) {
+        const T* src = qkv + s * (long long)n * 384;
+        // ---- 1. registers -> shared (fp32)
 #pragma unroll
         for (int r = 0; r < kMaxVec; ++r) {
             const int i = tid + r * 256;
@@ -114,73 +122,84 @@ __global__ void __launch_bounds__(256) attn_core_tiled_kernel(const T* __restric
             *reinterpret_cast<float4*>(dst) = make_float4(v[0] * scale, v[1] * scale, v[2] * scale, v[3] * scale);
             *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4] * scale, v[5] * scale, v[6] * scale, v[7] * scale);
         }
-    }
-    __syncthreads();
-    // ---- 2. softmax over positions for every k channel
-    if (tid < 128) {
-        float m = -INFINITY;
-        for (int j = 0; j < n; ++j) m = fmaxf(m, sk[j * kAttnRow + tid]);
-        float sum = 0.f;
-        for (int j = 0; j < n; ++j) {
-            float e = __expf(sk[j * kAttnRow + tid] - m);
-            sk[j * kAttnRow + tid] = e;
-            sum += e;
+        {
+            const long long sn = s + gridDim.x;
+            if (sn < S) {
+                const T* nsrc = qkv + sn * (long long)n * 384;
+#pragma unroll
+                for (int r = 0; r < kMaxVec; ++r) {
+                    const int i = tid + r * 256;
+                    if (i < nvec) raw[r] = reinterpret_cast<const uint4*>(nsrc)[i * kVecStride];
+                }
+            }
         }
-        const float inv = 1.0f / sum;
-        for (int j = 0; j < n; ++j) sk[j * kAttnRow + tid] *= inv;
-    }
-    __syncthreads();
-    const int h = tid >> 6, l = tid & 63;
-    // ---- 3. ctx[d][e] = sum_j k[d][j] v[e][j], 4x4 register tile per thread
-    {
-        const int bi = l >> 3, bj = l & 7;
-        float acc[4][4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-        for (int j = 0; j < n; ++j) {
-            const float4 kd = *reinterpret_cast<const float4*>(sk + j * kAttnRow + h * 32 + 4 * bi);
-            const float4 ve = *reinterpret_cast<const float4*>(sv + j * kAttnRow + h * 32 + 4 * bj);
-            const float ka[4] = {kd.x, kd.y, kd.z, kd.w}, va[4] = {ve.x, ve.y, ve.z, ve.w};
+        __syncthreads();
+        // ---- 2. softmax over positions for every k channel
+        if (tid < 128) {
+            float m = -INFINITY;
+            for (int j = 0; j < n; ++j) m = fmaxf(m, sk[j * kAttnRow + tid]);
+            float sum = 0.f;
+            for (int j = 0; j < n; ++j) {
+                float e = __expf(sk[j * kAttnRow + tid] - m);
+                sk[j * kAttnRow + tid] = e;
+                sum += e;
+            }
+            const float inv = 1.0f / sum;
+            for (int j = 0; j < n; ++j) sk[j * kAttnRow + tid] *= inv;
+        }
+        __syncthreads();
+        // ---- 3. ctx[d][e] = sum_j k[d][j] v[e][j], 4x4 register tile per thread
+        {
+            const int bi = l >> 3, bj = l & 7;
+            float acc[4][4];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(ka[a], va[b], acc[a][b]);
-        }
-        __syncthreads();                     // everyone is done reading k / v: reuse their storage for ctx
+                for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+            for (int j = 0; j < n; ++j) {
+                const float4 kd = *reinterpret_cast<const float4*>(sk + j * kAttnRow + h * 32 + 4 * bi);
+                const float4 ve = *reinterpret_cast<const float4*>(sv + j * kAttnRow + h * 32 + 4 * bj);
+                const float ka[4] = {kd.x, kd.y, kd.z, kd.w}, va[4] = {ve.x, ve.y, ve.z, ve.w};
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-            *reinterpret_cast<float4*>(ctx + (h * 32 + 4 * bi + a) * kCtxRow + 4 * bj) =
-                make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
-    }
-    __syncthreads();
-    // ---- 4. out[e][j] = sum_d ctx[d][e] q[d][j]; thread = 4 channels x positions {ng, ng+8, ng+16}
-    {
-        const int be = l & 7, ng = l >> 3;
-        float acc[3][4];
+                for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) acc[k][b] = 0.f;
-        const bool on[3] = {ng < n, ng + 8 < n, ng + 16 < n};
-#pragma unroll 4
-        for (int d = 0; d < 32; ++d) {
-            const float4 c4 = *reinterpret_cast<const float4*>(ctx + (h * 32 + d) * kCtxRow + 4 * be);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (!on[k]) continue;
-                const float qv = sq[(ng + 8 * k) * kAttnRow + h * 32 + d];
-                acc[k][0] = fmaf(c4.x, qv, acc[k][0]);
-                acc[k][1] = fmaf(c4.y, qv, acc[k][1]);
-                acc[k][2] = fmaf(c4.z, qv, acc[k][2]);
-                acc[k][3] = fmaf(c4.w, qv, acc[k][3]);
+                    for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(ka[a], va[b], acc[a][b]);
             }
-        }
-        T* dst = out + s * (long long)n * 128;
+            __syncthreads();                 // everyone is done reading k / v: reuse their storage for ctx
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-            if (on[k]) store4<T>(dst + (ng + 8 * k) * 128 + h * 32 + 4 * be, acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+            for (int a = 0; a < 4; ++a)
+                *reinterpret_cast<float4*>(ctx + (h * 32 + 4 * bi + a) * kCtxRow + 4 * bj) =
+                    make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+        }
+        __syncthreads();
+        // ---- 4. out[e][j] = sum_d ctx[d][e] q[d][j]; thread = 4 channels x positions {ng, ng+8, ng+16}
+        {
+            const int be = l & 7, ng = l >> 3;
+            float acc[3][4];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[k][b] = 0.f;
+            const bool on[3] = {ng < n, ng + 8 < n, ng + 16 < n};
+#pragma unroll 4
+            for (int d = 0; d < 32; ++d) {
+                const float4 c4 = *reinterpret_cast<const float4*>(ctx + (h * 32 + d) * kCtxRow + 4 * be);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (!on[k]) continue;
+                    const float qv = sq[(ng + 8 * k) * kAttnRow + h * 32 + d];
+                    acc[k][0] = fmaf(c4.x, qv, acc[k][0]);
+                    acc[k][1] = fmaf(c4.y, qv, acc[k][1]);
+                    acc[k][2] = fmaf(c4.z, qv, acc[k][2]);
+                    acc[k][3] = fmaf(c4.w, qv, acc[k][3]);
+                }
+            }
+            T* dst = out + s * (long long)n * 128;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (on[k]) store4<T>(dst + (ng + 8 * k) * 128 + h * 32 + 4 * be, acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+        }
+        __syncthreads();                     // shared memory is rewritten by the next slice
     }
 }
 
@@ -202,11 +221,20 @@ int launch_attn_core(const void* qkv, void* out, int64_t S, int n, int prec, cud
         CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_tiled_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         configured = true;
     }
+    // persistent grid: as many CTAs as fit on the machine at this shared-memory footprint
+    int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long want = (long long)sms * per_sm;
+    const unsigned grid = (unsigned)(S < want ? S : want);
     switch (prec) {
-        case PREC_F32: attn_core_tiled_kernel<float><<<(unsigned)S, 256, smem, st>>>((const float*)qkv, (float*)out, n); break;
-        case PREC_F16: attn_core_tiled_kernel<__half><<<(unsigned)S, 256, smem, st>>>((const __half*)qkv, (__half*)out, n); break;
+        case PREC_F32: attn_core_tiled_kernel<float><<<grid, 256, smem, st>>>((const float*)qkv, (float*)out, n, S); break;
+        case PREC_F16: attn_core_tiled_kernel<__half><<<grid, 256, smem, st>>>((const __half*)qkv, (__half*)out, n, S); break;
         case PREC_BF16:
-            attn_core_tiled_kernel<__nv_bfloat16><<<(unsigned)S, 256, smem, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, n);
+            attn_core_tiled_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, n, S);
             break;
         default: return fail(-2, "attn: bad precision");
     }

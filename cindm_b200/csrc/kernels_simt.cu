@@ -1,6 +1,8 @@
 // SIMT (fp32 FMA) kernels of the temporal U-Net: the parity-grade path, plus the small
 // per-slice operators (GroupNorm+Mish, channel LayerNorm, linear attention core) that both
 // precisions share.  Activations are channels-last: [S][H][C].
+#include <type_traits>
+
 #include "engine.h"
 
 namespace cindm {
@@ -249,10 +251,89 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ in
     for (int c = lane; c < C; c += 32) out[r * C + c] = from_f32<T>((to_f32<T>(x[c]) - mean) * rstd * g[c]);
 }
 
+// 16-bit version: each lane owns 8 consecutive channels per 256-channel segment (one 16-byte load), a row is
+// covered by min(32, C/8) lanes, so C = 64 packs four rows into one warp.  Values stay in registers between
+// the mean, variance and normalise passes.
+template <typename T, int C>
+__global__ void __launch_bounds__(256) layernorm16_kernel(const T* __restrict__ in, const float* __restrict__ g,
+                                                          T* __restrict__ out, long long rows) {
+    constexpr int LPR = (C / 8) < 32 ? (C / 8) : 32;       // lanes per row
+    constexpr int RPW = 32 / LPR;                          // rows per warp
+    constexpr int VPL = C / (8 * LPR);                     // 16-byte vectors per lane
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long r = warp * RPW + lane / LPR;
+    const int l = lane % LPR;
+    const bool ok = r < rows;
+    float v[VPL][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (ok) u = *reinterpret_cast<const uint4*>(in + r * C + (k * LPR + l) * 8);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 f;
+            if (sizeof(T) == 2 && std::is_same<T, __half>::value) f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+            else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+            v[k][2 * j] = f.x; v[k][2 * j + 1] = f.y;
+            sum += f.x + f.y;
+        }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.0f / C);
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[k][j] - mean; sq = fmaf(d, d, sq); }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * (1.0f / C) + 1e-5f);
+    if (!ok) return;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        const int c0 = (k * LPR + l) * 8;
+        const float4 g0 = *reinterpret_cast<const float4*>(g + c0), g1 = *reinterpret_cast<const float4*>(g + c0 + 4);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float a = (v[k][2 * j] - mean) * rstd * gg[2 * j], b = (v[k][2 * j + 1] - mean) * rstd * gg[2 * j + 1];
+            if (std::is_same<T, __half>::value) { __half2 h = __floats2half2_rn(a, b); w[j] = *reinterpret_cast<uint32_t*>(&h); }
+            else { __nv_bfloat162 h = __floats2bfloat162_rn(a, b); w[j] = *reinterpret_cast<uint32_t*>(&h); }
+        }
+        *reinterpret_cast<uint4*>(out + r * C + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+template <typename T>
+static int launch_layernorm16(const T* in, const float* g, T* out, long long rows, int C, cudaStream_t st) {
+    auto blocks = [&](int rpw) { return (unsigned)((rows + rpw * 8 - 1) / (rpw * 8)); };
+    switch (C) {
+        case 64: layernorm16_kernel<T, 64><<<blocks(4), 256, 0, st>>>(in, g, out, rows); break;
+        case 128: layernorm16_kernel<T, 128><<<blocks(2), 256, 0, st>>>(in, g, out, rows); break;
+        case 256: layernorm16_kernel<T, 256><<<blocks(1), 256, 0, st>>>(in, g, out, rows); break;
+        case 512: layernorm16_kernel<T, 512><<<blocks(1), 256, 0, st>>>(in, g, out, rows); break;
+        default: return -1;
+    }
+    return 0;
+}
+
 int launch_layernorm(const void* in, const float* g, void* out, int64_t rows, int C, int prec, cudaStream_t st) {
     if (rows == 0) return 0;
     KernelTimer kt("layernorm", st, (double)rows * C * 2.0 * elem_size(prec));
     int blocks = ceil_div(rows, 8);
+    if (prec == PREC_F16 && launch_layernorm16<__half>((const __half*)in, g, (__half*)out, rows, C, st) == 0) {
+        CINDM_CHECK_LAUNCH();
+        return 0;
+    }
+    if (prec == PREC_BF16 && launch_layernorm16<__nv_bfloat16>((const __nv_bfloat16*)in, g, (__nv_bfloat16*)out, rows, C, st) == 0) {
+        CINDM_CHECK_LAUNCH();
+        return 0;
+    }
     switch (prec) {
         case PREC_F32: layernorm_kernel<float><<<blocks, 256, 0, st>>>((const float*)in, g, (float*)out, rows, C); break;
         case PREC_F16: layernorm_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)in, g, (__half*)out, rows, C); break;

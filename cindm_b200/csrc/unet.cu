@@ -82,12 +82,41 @@ struct Uploader {
         c.bias = bias ? vec(prefix + ".bias", cout) : nullptr;
     }
 
-    void resblock(ResBlockW& r, const std::string& prefix, int cin, int cout) {
+    // Block-Toeplitz operand of a k=5, pad=2 conv over 3 positions: rows n = (group, out position p, channel in
+    // group), columns k = (in position q, ci); entry = W[co][ci][q - p + 2] (every tap index is in range at H=3).
+    void toeplitz3(ConvW& c, const std::string& prefix) {
+        const HostTensor* t = find(prefix + ".weight");
+        if (!t || rc) return;
+        const int cin = c.cin, cout = c.cout, cpg = cout / 8;
+        std::vector<__half> wh((size_t)9 * cin * cout);
+        std::vector<__nv_bfloat16> wb(wh.size());
+        for (int g = 0; g < 8; ++g)
+            for (int p = 0; p < 3; ++p)
+                for (int cc = 0; cc < cpg; ++cc) {
+                    const int co = g * cpg + cc;
+                    const size_t n = ((size_t)g * 3 + p) * cpg + cc;
+                    for (int q = 0; q < 3; ++q)
+                        for (int ci = 0; ci < cin; ++ci) {
+                            float v = t->data[((size_t)co * cin + ci) * 5 + (q - p + 2)];
+                            size_t idx = n * (3 * (size_t)cin) + (size_t)q * cin + ci;
+                            wh[idx] = __float2half_rn(v);
+                            wb[idx] = __float2bfloat16_rn(v);
+                        }
+                }
+        c.w16t[PREC_F16] = upload(wh.data(), wh.size() * sizeof(__half));
+        c.w16t[PREC_BF16] = upload(wb.data(), wb.size() * sizeof(__nv_bfloat16));
+    }
+
+    void resblock(ResBlockW& r, const std::string& prefix, int cin, int cout, bool bottom = false) {
         r.name = prefix;
         conv(r.conv0, prefix + ".blocks.0.block.0", cin, cout, 5, true);
+        if (bottom && e->cfg.horizon == 24) {
+            toeplitz3(r.conv0, prefix + ".blocks.0.block.0");
+        }
         r.gn0.gamma = vec(prefix + ".blocks.0.block.2.weight", cout);
         r.gn0.beta = vec(prefix + ".blocks.0.block.2.bias", cout);
         conv(r.conv1, prefix + ".blocks.1.block.0", cout, cout, 5, true);
+        if (bottom && e->cfg.horizon == 24) toeplitz3(r.conv1, prefix + ".blocks.1.block.0");
         r.gn1.gamma = vec(prefix + ".blocks.1.block.2.weight", cout);
         r.gn1.beta = vec(prefix + ".blocks.1.block.2.bias", cout);
         r.has_res = cin != cout;
@@ -136,19 +165,19 @@ int finalize_weights(cindm_engine* e, cudaStream_t st) {
     const int ch[5] = {F, dim, dim * 2, dim * 4, dim * 8};
     for (int i = 0; i < 4; ++i) {
         std::string p = "downs." + std::to_string(i);
-        up.resblock(e->downs_rb[i][0], p + ".0", ch[i], ch[i + 1]);
-        up.resblock(e->downs_rb[i][1], p + ".1", ch[i + 1], ch[i + 1]);
+        up.resblock(e->downs_rb[i][0], p + ".0", ch[i], ch[i + 1], i == 3);
+        up.resblock(e->downs_rb[i][1], p + ".1", ch[i + 1], ch[i + 1], i == 3);
         up.attn(e->downs_at[i], p + ".2", ch[i + 1]);
         if (i < 3) up.conv(e->down_conv[i], p + ".3.conv", ch[i + 1], ch[i + 1], 3, true);
     }
-    up.resblock(e->mid_rb[0], "mid_block1", ch[4], ch[4]);
+    up.resblock(e->mid_rb[0], "mid_block1", ch[4], ch[4], true);
     up.attn(e->mid_at, "mid_attn", ch[4]);
-    up.resblock(e->mid_rb[1], "mid_block2", ch[4], ch[4]);
+    up.resblock(e->mid_rb[1], "mid_block2", ch[4], ch[4], true);
     for (int i = 0; i < 3; ++i) {
         std::string p = "ups." + std::to_string(i);
         int co = ch[4 - i], ci = ch[3 - i];      // (dim_in, dim_out) of reversed(in_out[1:]): ci -> co going down
-        up.resblock(e->ups_rb[i][0], p + ".0", co * 2, co);
-        up.resblock(e->ups_rb[i][1], p + ".1", co, ci);
+        up.resblock(e->ups_rb[i][0], p + ".0", co * 2, co, i == 0);
+        up.resblock(e->ups_rb[i][1], p + ".1", co, ci, i == 0);
         up.attn(e->ups_at[i], p + ".2", ci);
         up.conv(e->up_conv[i], p + ".3.conv", ci, ci, 4, true, /*transposed=*/true);
     }
@@ -244,7 +273,7 @@ struct Fwd {
             a.in0 = in0; a.c0 = c0; a.in1 = in1; a.c1 = c1; a.w = &w; a.gn = &gn;
             a.add_vec = add_vec; a.t_dev = add_vec ? t_dev : nullptr; a.add_res = add_res; a.out = out; a.S = S;
             a.H = H; a.prec = prec;
-            a.epilogue = EPI_GN_MISH;
+            a.epilogue = (H == 3 && w.w16t[prec] != nullptr && e->use_toeplitz) ? EPI_GN_MISH_T3 : EPI_GN_MISH;
             return launch_conv_tc(a, st);
         }
         ConvLaunch a;
