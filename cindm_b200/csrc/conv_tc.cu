@@ -298,6 +298,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             const int sl = min(row / p.H, p.slices_per_tile - 1);  // slice within the tile
             const bool valid = row < p.rows_used && (s0 + sl) < p.S;
             const long long grow = s0 * p.H + row;                // global row (slices are contiguous rows)
+            // the residual rows of this tile do not depend on the accumulator: start fetching them before the wait
+            uint4 rv[4];
+            if (res != nullptr) {
+                long long roff;
+                if (EPI == EPI_GN_MISH_T3) {
+                    constexpr int GC = 3 * CPG;
+                    const int j0 = half * 96, gl = j0 / GC, rem = j0 - gl * GC, pp = rem / CPG;
+                    roff = ((s0 + row) * 3 + pp) * p.cout + (n_tile * (192 / GC) + gl) * CPG + (rem - pp * CPG);
+                    if (s0 + row >= p.S) roff = -1;
+                } else {
+                    roff = valid ? grow * p.cout + n0 + half * (N_TILE / 2) : -1;
+                }
+                if (roff >= 0) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(res + roff);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) rv[j] = rp[j];
+                }
+            }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             if constexpr (EPI == EPI_GN_MISH_T3) {
@@ -341,11 +359,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                     const long long off = (slice * 3 + pp) * p.cout + chb;
                     tmem_ld32(tbase + cc * 32, v);
                     uint32_t packed[16];
-                    uint4 rv[4];
-                    if (res != nullptr && ok) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(res + off);
+                    uint4 rn[4];
+                    if (res != nullptr && ok && cc < 2) {          // next chunk's residual, in flight during this chunk's math
+                        const int j1 = half * 96 + (cc + 1) * 32;
+                        const int gl1 = j1 / GCOLS, rem1 = j1 - gl1 * GCOLS, pp1 = rem1 / CPG;
+                        const uint4* rp = reinterpret_cast<const uint4*>(
+                            res + (slice * 3 + pp1) * p.cout + (g0 + gl1) * CPG + (rem1 - pp1 * CPG));
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) rv[j] = rp[j];
+                        for (int j = 0; j < 4; ++j) rn[j] = rp[j];
                     }
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
@@ -372,6 +393,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             op[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                    }
+                    if (res != nullptr && cc < 2) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) rv[j] = rn[j];
                     }
                 }
                 tc_fence_before();
@@ -436,11 +461,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             for (int c = 0; c < HALF_N; c += 32) {
                 tmem_ld32(taddr + c, v);
                 uint32_t packed[16];
-                uint4 rv[4];
-                if (res != nullptr && valid) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(res + grow * p.cout + cbase + c);
+                uint4 rn[4];
+                if (res != nullptr && valid && c + 32 < HALF_N) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(res + grow * p.cout + cbase + c + 32);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) rv[j] = rp[j];
+                    for (int j = 0; j < 4; ++j) rn[j] = rp[j];
                 }
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
@@ -476,6 +501,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         op[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                }
+                if (res != nullptr && c + 32 < HALF_N) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) rv[j] = rn[j];
                 }
             }
             tc_fence_before();

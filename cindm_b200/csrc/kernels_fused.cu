@@ -208,10 +208,178 @@ static size_t attn_smem_bytes(int n) {
     return ((size_t)n * kAttnRow + (kv > cx ? kv : cx)) * sizeof(float);
 }
 
+// ------------------------------------------------------------------------------------------
+// Tensor-core version for the 16-bit precisions: one warp per (slice, head), no block-level barriers.
+//   ctx^T[e][d] = sum_j V[j][e] * softmax_j(K)[j][d]       mma.m16n8k16, A = V^T (ldmatrix.trans), B = K_s (ldmatrix.trans)
+//   out[j][e]   = 32^-0.5 * sum_d Q[j][d] * ctx[d][e]       A = Q (ldmatrix), B = ctx^T accumulators re-used in registers:
+// the C-fragment of ctx^T (row e = lane/4, cols d = 2*(lane%4)..+1) is exactly the B-fragment (k = d, n = e) that
+// the second product needs, so ctx never leaves the register file.  Positions are padded to 16 or 32 with zeros.
+// ------------------------------------------------------------------------------------------
+constexpr int kMmaRow = 40;                  // halves per shared-memory row (80 B: ldmatrix conflict-free)
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+template <typename T>
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
+template <>
+__device__ __forceinline__ void mma16816<__half>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <>
+__device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <typename T> __device__ __forceinline__ uint32_t pack_pair(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack_pair<__half>(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack_pair<__nv_bfloat16>(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <typename T, int KS>      // KS = number of 16-position steps (1: n <= 16, 2: n <= 32)
+__global__ void __launch_bounds__(256) attn_core_mma_kernel(const T* __restrict__ qkv, T* __restrict__ out, int n,
+                                                            long long tasks) {
+    extern __shared__ __align__(16) unsigned char attn_mma_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T* sK = reinterpret_cast<T*>(attn_mma_smem) + warp * (3 * 32 * kMmaRow);
+    T* sV = sK + 32 * kMmaRow;
+    T* sQ = sV + 32 * kMmaRow;
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int ROWS = 16 * KS;
+    const T zero = from_f32<T>(0.f);
+    for (long long task = (long long)blockIdx.x * 8 + warp; task < tasks; task += (long long)gridDim.x * 8) {
+        const long long s = task >> 2;
+        const int h = (int)(task & 3);
+        const T* base = qkv + s * (long long)n * 384 + h * 32;
+        // ---- K: softmax over positions, one channel per lane
+        {
+            float kv[ROWS];
+            float m = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) {
+                kv[j] = j < n ? to_f32<T>(base[j * 384 + 128 + lane]) : -INFINITY;
+                m = fmaxf(m, kv[j]);
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) { kv[j] = __expf(kv[j] - m); sum += kv[j]; }      // exp(-inf) = 0 pads the rows >= n
+            const float inv = 1.0f / sum;
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) sK[j * kMmaRow + lane] = from_f32<T>(kv[j] * inv);
+        }
+        // ---- V and Q rows: 64 bytes each, 4 lanes per row
+#pragma unroll
+        for (int r0 = 0; r0 < ROWS; r0 += 8) {
+            const int j = r0 + (lane >> 2), part = lane & 3;
+            uint4 vv = make_uint4(0, 0, 0, 0), qq = make_uint4(0, 0, 0, 0);
+            if (j < n) {
+                vv = *reinterpret_cast<const uint4*>(base + j * 384 + 256 + part * 8);
+                qq = *reinterpret_cast<const uint4*>(base + j * 384 + part * 8);
+            }
+            *reinterpret_cast<uint4*>(sV + j * kMmaRow + part * 8) = vv;
+            *reinterpret_cast<uint4*>(sQ + j * kMmaRow + part * 8) = qq;
+        }
+        __syncwarp();
+        // ---- ctx^T = V^T K_s : M = e (2 tiles of 16), N = d (4 tiles of 8), K = positions
+        float ct[2][4][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) ct[mt][nt][c] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            // B fragments of K_s for all four d tiles: stored [j][d]; matrices (j0, d0) (j0+8, d0) (j0, d0+8) (j0+8, d0+8)
+            uint32_t bk[2][4];
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {
+                const int row = 16 * ks + (lane & 7) + ((lane >> 3) & 1) * 8, col = 16 * np + (lane >> 4) * 8;
+                ldsm_x4_trans((uint32_t)__cvta_generic_to_shared(sK + row * kMmaRow + col), bk[np]);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                // A fragments of V^T: stored [j][e]; matrices (j0, e0) (j0, e0+8) (j0+8, e0) (j0+8, e0+8)
+                uint32_t av[4];
+                const int row = 16 * ks + (lane & 7) + (lane >> 4) * 8, col = 16 * mt + ((lane >> 3) & 1) * 8;
+                ldsm_x4_trans((uint32_t)__cvta_generic_to_shared(sV + row * kMmaRow + col), av);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) mma16816<T>(ct[mt][nt], av, bk[nt >> 1][(nt & 1) * 2], bk[nt >> 1][(nt & 1) * 2 + 1]);
+            }
+        }
+        // ---- out = Q ctx : M = positions (KS tiles of 16), N = e (4 tiles of 8), K = d (2 steps of 16)
+        T* dst = out + s * (long long)n * 128 + h * 32;
+#pragma unroll
+        for (int mt = 0; mt < KS; ++mt) {
+            float oc[4][4];
+#pragma unroll
+            for (int ne = 0; ne < 4; ++ne)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) oc[ne][c] = 0.f;
+#pragma unroll
+            for (int kd = 0; kd < 2; ++kd) {
+                uint32_t aq[4];
+                const int row = 16 * mt + (lane & 7) + ((lane >> 3) & 1) * 8, col = 16 * kd + (lane >> 4) * 8;
+                ldsm_x4((uint32_t)__cvta_generic_to_shared(sQ + row * kMmaRow + col), aq);
+#pragma unroll
+                for (int ne = 0; ne < 4; ++ne) {
+                    // B[k = d][n = e] = ctx^T[e][d]: rows e of tile ne live in ct[ne/2] (upper half: c0,c1; lower: c2,c3)
+                    const int m2 = ne >> 1, hi = (ne & 1) * 2;
+                    const uint32_t b0 = pack_pair<T>(ct[m2][2 * kd][hi], ct[m2][2 * kd][hi + 1]);
+                    const uint32_t b1 = pack_pair<T>(ct[m2][2 * kd + 1][hi], ct[m2][2 * kd + 1][hi + 1]);
+                    mma16816<T>(oc[ne], aq, b0, b1);
+                }
+            }
+            const float scale = 0.17677669529663687f;                 // 32^-0.5 (q * scale in the reference, :284)
+            const int j0 = 16 * mt + g, j1 = j0 + 8;
+#pragma unroll
+            for (int ne = 0; ne < 4; ++ne) {
+                const int e = 8 * ne + 2 * t;
+                if (j0 < n) *reinterpret_cast<uint32_t*>(dst + j0 * 128 + e) = pack_pair<T>(oc[ne][0] * scale, oc[ne][1] * scale);
+                if (j1 < n) *reinterpret_cast<uint32_t*>(dst + j1 * 128 + e) = pack_pair<T>(oc[ne][2] * scale, oc[ne][3] * scale);
+            }
+        }
+        __syncwarp();            // this warp's shared memory is rewritten by its next task
+    }
+}
+
+template <typename T>
+static int launch_attn_mma(const T* qkv, T* out, int64_t S, int n, cudaStream_t st) {
+    const size_t smem = (size_t)8 * 3 * 32 * kMmaRow * sizeof(T);
+    static bool configured = false;
+    if (!configured) {
+        CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_mma_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_mma_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tasks = S * 4;
+    long long want = (long long)sms * 3;
+    const long long need = (tasks + 7) / 8;
+    const unsigned grid = (unsigned)(need < want ? need : want);
+    if (n <= 16) attn_core_mma_kernel<T, 1><<<grid, 256, smem, st>>>(qkv, out, n, tasks);
+    else attn_core_mma_kernel<T, 2><<<grid, 256, smem, st>>>(qkv, out, n, tasks);
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
 int launch_attn_core(const void* qkv, void* out, int64_t S, int n, int prec, cudaStream_t st) {
     if (S == 0) return 0;
     if (n > 24) return fail(-2, "attention core supports at most 24 positions");
     KernelTimer kt("attn_core", st, (double)S * n * 512.0 * elem_size(prec));
+    if (prec == PREC_F16) return launch_attn_mma<__half>((const __half*)qkv, (__half*)out, S, n, st);
+    if (prec == PREC_BF16) return launch_attn_mma<__nv_bfloat16>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, S, n, st);
     const size_t smem = attn_smem_bytes(n);
     static bool configured = false;
     if (!configured) {
