@@ -1,0 +1,76 @@
+"""CPU, world_size 2 over gloo: the N>1 host logic of the driver — candidate sharding, the single score
+all-gather and the replicated top-k — without any GPU."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cindm_b200.inference.inverse_design_diffusion_1d import build_parser, gather_scores, model_horizon, shard
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, batch, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard(batch, rank, world)
+    counts = [shard(batch, r, world)[1] - shard(batch, r, world)[0] for r in range(world)]
+    # every candidate's score is a deterministic function of its GLOBAL id, as with the Philox-keyed sampler
+    ids = torch.arange(lo, hi, dtype=torch.float64)
+    local = torch.stack([(ids * 37 % 11) / 11.0, ids, -ids], 1).flatten().contiguous()
+    full = gather_scores(local, [3 * c for c in counts], dist).reshape(-1, 3)
+    top = torch.topk(full[:, 0], 3, largest=False)
+    torch.save({"full": full, "top": top.indices}, os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch", [8, 7])
+def test_shard_allgather_topk_world2(tmp_path, batch):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), batch, str(tmp_path)), nprocs=world, join=True)
+    r0 = torch.load(tmp_path / "rank0.pt")
+    r1 = torch.load(tmp_path / "rank1.pt")
+    ids = torch.arange(batch, dtype=torch.float64)
+    expect = torch.stack([(ids * 37 % 11) / 11.0, ids, -ids], 1)
+    assert torch.equal(r0["full"], expect) and torch.equal(r1["full"], expect)
+    assert torch.equal(r0["top"], r1["top"])                     # replicated top-k: every rank picks the same designs
+
+
+def test_shard_covers_every_candidate_once():
+    for batch in (1, 7, 512, 4096):
+        for world in (1, 2, 3, 8):
+            ranges = [shard(batch, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == batch
+            assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+            sizes = [hi - lo for lo, hi in ranges]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_cli_keeps_reference_flags_and_defaults():
+    args = build_parser().parse_args([])
+    # defaults of inference/inverse_design_diffusion_1d.py:54-103
+    assert (args.exp_id, args.date_time, args.dataset) == ("inv_design", "09-23", "nbody-2")
+    assert (args.conditioned_steps, args.rollout_steps, args.time_interval) == (4, 20, 4)
+    assert (args.val_batch_size, args.sample_steps, args.num_features, args.gpuid) == (1000, 1000, 4, 0)
+    assert (args.n_composed, args.compose_start_step, args.compose_n_bodies) == (0, 10, 2)
+    assert (args.design_fn_mode, args.design_coef, args.consistency_coef) == ("L2", "0.05", "0.05")
+    assert (args.Unet_dim, args.initialization_mode, args.num_batchs) == (64, 0, 1)
+    assert (args.batch_size_list, args.sample_steps_list, args.seed) == ("[50]", "[1000]", 0)
+    paper = build_parser().parse_args(
+        "--exp_id=new-standard-noise_sum --date_time=02-04 --n_composed=2 --compose_n_bodies=8 --design_coef=0.2 "
+        "--consistency_coef=0.2 --design_guidance=standard-recurrence-10 --val_batch_size=500 "
+        "--model_name=Diffusion_cond-0_rollout-24_bodies-2_more_collision --sample_steps=1000 --compose_mode=mean-inside "
+        "--design_fn_mode=L2 --initialization_mode 0 --gpuid 7".split())
+    assert model_horizon(paper) == (24, 0)
+    assert paper.is_test is True
+    with pytest.raises(NotImplementedError):
+        paper.model_name = "Diffusion_cond-0_rollout-44_bodies-2"
+        model_horizon(paper)
