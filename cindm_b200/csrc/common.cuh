@@ -66,11 +66,11 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
 __device__ __forceinline__ float mish_exact(float x) { return x * tanhf(log1pf(expf(x))); }
 
 // Same function with one ex2 and one rcp: tanh(log(1+w)) = (w^2+2w)/(w^2+2w+2), w = e^x.
+// The exponent is clamped at 20 where the ratio already rounds to 1.0f, so no branch is needed for large x.
 __device__ __forceinline__ float mish_fast(float x) {
-    float w = __expf(fminf(x, 20.0f));
+    float w = exp2f(fminf(x, 20.0f) * 1.4426950408889634f);
     float n = w * (w + 2.0f);
-    float r = __fdividef(n, n + 2.0f);
-    return x > 20.0f ? x : x * r;
+    return x * __fdividef(n, n + 2.0f);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
