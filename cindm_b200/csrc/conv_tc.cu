@@ -131,6 +131,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
+          "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]),
+          "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]),
+          "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (8-row groups 1024 B apart)
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -174,8 +187,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out, const TcParams p) {
     constexpr int kBTileBytes = N_TILE * 128;
     constexpr int kStageBytes = kATileBytes + kBTileBytes;
-    constexpr int NG = (EPI == EPI_GN_MISH) ? N_TILE / CPG : 1;       // GroupNorm groups inside one N tile
-    constexpr int PSTRIDE = 2 * NG + 1;
     constexpr int ACC_STRIDE = (N_TILE == 192) ? 256 : N_TILE;        // TMEM columns between the two accumulators
     constexpr bool HAS_GN = (EPI != EPI_BIAS);
 
@@ -188,9 +199,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     float* vec_gamma = vec_bias + 512;
     float* vec_beta = vec_gamma + 512;
     float* vec_add = vec_beta + 512;
-    float* part = vec_add + 512;                                       // [128][PSTRIDE]
-    float2* stats = reinterpret_cast<float2*>(part + 128 * 17);        // [42 slices][8 groups]
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stats + 42 * 8);
+    float* part = vec_add + 512;                                       // 2 parity buffers of GroupNorm partial sums
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(part + 2 * 1408);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full = empty_bar + kStages;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -263,7 +273,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                mbar_wait(&tmem_empty[acc], acc_phase);      // the epilogue has pre-loaded this accumulator with the bias
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
                 for (int kc = 0; kc < k_chunks; ++kc) {
@@ -273,8 +283,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                     const uint32_t b_addr = a_addr + kATileBytes;
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
-                        tc_mma_f16(d_tmem, umma_smem_desc(a_addr + k * 32), umma_smem_desc(b_addr + k * 32), idesc,
-                                   (kc > 0 || k > 0) ? 1u : 0u);
+                        tc_mma_f16(d_tmem, umma_smem_desc(a_addr + k * 32), umma_smem_desc(b_addr + k * 32), idesc, 1u);
                     }
                     tc_commit(&empty_bar[stage]);                 // frees the smem stage when the MMAs retire
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -287,222 +296,198 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     } else {
         // =============================== epilogue (8 warps) ===============================
         // Two warps share each TMEM lane quarter (hardware: warp w may read lanes 32*(w%4)..+31); each takes
-        // half of the tile's columns.
-        const int q = warp & 3;                                   // TMEM lane quarter this warp may read
+        // half of the tile's columns.  The conv bias is not added here: the epilogue writes it into the
+        // accumulator (tcgen05.st) before the MMA warp starts the tile, so TMEM already holds conv + bias.
+        const int q = warp & 3;                                   // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;                         // which half of the N tile
         const int row = q * 32 + lane;                            // tile row == TMEM lane
         const int et = (warp - 2) * 32 + lane;                    // 0..255 index among epilogue threads
-        constexpr int HALF_N = N_TILE / 2;
-        constexpr int HG = (EPI == EPI_GN_MISH) ? HALF_N / CPG : 1;   // groups owned by one thread
+        constexpr bool T3 = (EPI == EPI_GN_MISH_T3);
+        constexpr int HALF_N = T3 ? 96 : N_TILE / 2;
+        constexpr int NCHUNK = HALF_N / 32;
+        constexpr int HG = (EPI == EPI_GN_MISH) ? HALF_N / CPG : 1;   // groups owned by one thread (generic GN path)
+        constexpr int GCOLS = 3 * CPG;                            // T3: accumulator columns of one GroupNorm group
+        constexpr int PART_BUF = 1408;                            // floats per parity buffer: 43 slices x 2 x 8 groups x 2
         T16* out = reinterpret_cast<T16*>(p.out);
         const T16* res = reinterpret_cast<const T16*>(p.add_res);
         const float4* bias4 = reinterpret_cast<const float4*>(vec_bias);
         const float4* gamma4 = reinterpret_cast<const float4*>(vec_gamma);
         const float4* beta4 = reinterpret_cast<const float4*>(vec_beta);
         const float4* add4 = reinterpret_cast<const float4*>(vec_add);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * HALF_N);
+        const bool stage_out = (N_TILE <= 128) && p.tma_out;
+
+        // first channel of 32-column chunk `cc` of this thread for N tile `nt`
+        auto chunk_channel = [&](int nt, int cc) -> int {
+            if (T3) {
+                const int j0 = half * 96 + cc * 32, gl = j0 / GCOLS, rem = j0 - gl * GCOLS, pp = rem / CPG;
+                return (nt * (192 / GCOLS) + gl) * CPG + (rem - pp * CPG);
+            }
+            return nt * N_TILE + half * HALF_N + cc * 32;
+        };
+        // write the conv bias of N tile `nt` into accumulator buffer `buf` (own lane, own column half)
+        auto init_accumulator = [&](int buf, int nt) {
+#pragma unroll
+            for (int cc = 0; cc < NCHUNK; ++cc) {
+                const int chb = chunk_channel(nt, cc);
+                float bv[32];
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 b4 = bias4[(chb + i) >> 2];
+                    bv[i] = b4.x; bv[i + 1] = b4.y; bv[i + 2] = b4.z; bv[i + 3] = b4.w;
+                }
+                tmem_st32(lane_base + (uint32_t)(buf * ACC_STRIDE + cc * 32), bv);
+            }
+            tmem_st_wait();
+        };
+        // loop-invariant GroupNorm geometry of this thread's row (generic path: rows of a slice are H consecutive lanes)
+        const int sl = min(row / p.H, p.slices_per_tile - 1);     // slice within the tile
+        const int row_in_slice = row - (row / p.H) * p.H;
+        uint32_t same_mask = 0;                                   // bit k: lane + 2^k belongs to the same slice
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            if (lane + (1 << k) < 32 && (row + (1 << k)) / p.H == row / p.H) same_mask |= 1u << k;
+        const bool seg_head = (lane == 0 || row_in_slice == 0) && row < p.rows_used;
+        const int seg_which = row_in_slice == 0 ? 0 : 1;          // 1: continuation of a slice that started in the previous warp
+        const bool spans = ((sl * p.H) >> 5) != ((sl * p.H + p.H - 1) >> 5);
+        const float inv_cnt = 1.0f / (float)(p.H * CPG);
+
+        {   // both accumulators start out holding the bias of the first two tiles of this CTA
+            const int t0 = blockIdx.x, t1 = blockIdx.x + gridDim.x;
+            if (t0 < num_tiles) init_accumulator(0, t0 % p.n_tiles);
+            if (t1 < num_tiles) init_accumulator(1, t1 % p.n_tiles);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&tmem_empty[0]); mbar_arrive(&tmem_empty[1]); }
+        }
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
             const long long s0 = (long long)m_tile * p.slices_per_tile;
             const int n0 = n_tile * N_TILE;
-            const int sl = min(row / p.H, p.slices_per_tile - 1);  // slice within the tile
-            const bool valid = row < p.rows_used && (s0 + sl) < p.S;
-            const long long grow = s0 * p.H + row;                // global row (slices are contiguous rows)
+            const bool valid = T3 ? (s0 + row) < p.S : (row < p.rows_used && (s0 + sl) < p.S);
+            const long long grow = s0 * p.H + row;                // global row (slices are contiguous rows); T3: slice index
+            // element offset of chunk cc of this thread's row in the [S][H][cout] output / residual tensors
+            auto chunk_offset = [&](int cc) -> long long {
+                if (T3) {
+                    const int j0 = half * 96 + cc * 32, gl = j0 / GCOLS, rem = j0 - gl * GCOLS, pp = rem / CPG;
+                    return (grow * 3 + pp) * p.cout + chunk_channel(n_tile, cc);
+                }
+                return grow * p.cout + chunk_channel(n_tile, cc);
+            };
             // the residual rows of this tile do not depend on the accumulator: start fetching them before the wait
             uint4 rv[4];
-            if (res != nullptr) {
-                long long roff;
-                if (EPI == EPI_GN_MISH_T3) {
-                    constexpr int GC = 3 * CPG;
-                    const int j0 = half * 96, gl = j0 / GC, rem = j0 - gl * GC, pp = rem / CPG;
-                    roff = ((s0 + row) * 3 + pp) * p.cout + (n_tile * (192 / GC) + gl) * CPG + (rem - pp * CPG);
-                    if (s0 + row >= p.S) roff = -1;
-                } else {
-                    roff = valid ? grow * p.cout + n0 + half * (N_TILE / 2) : -1;
-                }
-                if (roff >= 0) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(res + roff);
+            if (res != nullptr && valid) {
+                const uint4* rp = reinterpret_cast<const uint4*>(res + chunk_offset(0));
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) rv[j] = rp[j];
-                }
+                for (int j = 0; j < 4; ++j) rv[j] = rp[j];
             }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            if constexpr (EPI == EPI_GN_MISH_T3) {
-                // ---------- block-Toeplitz tile: row = slice, 192 columns = (group, position, channel) ----------
-                constexpr int GCOLS = 3 * CPG;                     // accumulator columns of one GroupNorm group
-                const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_STRIDE + half * 96);
-                const long long slice = s0 + row;
-                const bool ok = slice < p.S;
-                const int g0 = n_tile * (192 / GCOLS);
-                float v[32];
-                float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                for (int cc = 0; cc < 3; ++cc) {
-                    const int j0 = half * 96 + cc * 32;
-                    const int gl = j0 / GCOLS, rem = j0 - gl * GCOLS, pp = rem / CPG;
-                    const int chb = (g0 + gl) * CPG + (rem - pp * CPG);
-                    tmem_ld32(tbase + cc * 32, v);
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 b4 = bias4[(chb + i) >> 2];
-                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) { const float x = v[i + u] + bb[u]; s1 += x; s2 = fmaf(x, x, s2); }
-                    }
-                }
-                if (CPG == 64) {
-                    // the group spans both column halves: exchange partial sums with the partner warp (double-buffered
-                    // by accumulator parity so a fast warp cannot overwrite what its partner still has to read)
-                    float* ex = part + acc * 512;
-                    ex[(half * 128 + row) * 2] = s1; ex[(half * 128 + row) * 2 + 1] = s2;
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                    s1 += ex[((half ^ 1) * 128 + row) * 2]; s2 += ex[((half ^ 1) * 128 + row) * 2 + 1];
-                }
-                const float mean = s1 * (1.0f / (float)GCOLS);
-                const float rstd = rsqrtf(fmaxf(s2 * (1.0f / (float)GCOLS) - mean * mean, 0.f) + 1e-5f);
-#pragma unroll
-                for (int cc = 0; cc < 3; ++cc) {
-                    const int j0 = half * 96 + cc * 32;
-                    const int gl = j0 / GCOLS, rem = j0 - gl * GCOLS, pp = rem / CPG;
-                    const int chb = (g0 + gl) * CPG + (rem - pp * CPG);
-                    const long long off = (slice * 3 + pp) * p.cout + chb;
-                    tmem_ld32(tbase + cc * 32, v);
-                    uint32_t packed[16];
-                    uint4 rn[4];
-                    if (res != nullptr && ok && cc < 2) {          // next chunk's residual, in flight during this chunk's math
-                        const int j1 = half * 96 + (cc + 1) * 32;
-                        const int gl1 = j1 / GCOLS, rem1 = j1 - gl1 * GCOLS, pp1 = rem1 / CPG;
-                        const uint4* rp = reinterpret_cast<const uint4*>(
-                            res + (slice * 3 + pp1) * p.cout + (g0 + gl1) * CPG + (rem1 - pp1 * CPG));
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) rn[j] = rp[j];
-                    }
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const int ch4 = (chb + i) >> 2;
-                        const float4 b4 = bias4[ch4], ga4 = gamma4[ch4], be4 = beta4[ch4], ad4 = add4[ch4];
-                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w};
-                        const float be[4] = {be4.x, be4.y, be4.z, be4.w}, ad[4] = {ad4.x, ad4.y, ad4.z, ad4.w};
-                        float y[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const float x = fmaf(v[i + u] + bb[u] - mean, rstd * ga[u], be[u]);
-                            y[u] = mish_fast(x) + ad[u];
-                        }
-                        if (res != nullptr) {
-                            const uint32_t* rw = reinterpret_cast<const uint32_t*>(rv);
-                            const float2 r0 = unpack2<T16>(rw[i >> 1]), r1 = unpack2<T16>(rw[(i >> 1) + 1]);
-                            y[0] += r0.x; y[1] += r0.y; y[2] += r1.x; y[3] += r1.y;
-                        }
-                        packed[i >> 1] = pack2<T16>(y[0], y[1]);
-                        packed[(i >> 1) + 1] = pack2<T16>(y[2], y[3]);
-                    }
-                    if (ok) {
-                        uint4* op = reinterpret_cast<uint4*>(out + off);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            op[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-                    }
-                    if (res != nullptr && cc < 2) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) rv[j] = rn[j];
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-                continue;
-            }
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_STRIDE + half * HALF_N);
-            const int cbase = n0 + half * HALF_N;                 // first channel this thread handles
+            const uint32_t taddr = lane_base + (uint32_t)(acc * ACC_STRIDE);
             float v[32];
-            float g_mean[HG], g_rstd[HG];
+            float g_sc[HG], g_sh[HG];                             // per group: rstd and -mean * rstd
+            float t3_rstd = 0.f, t3_nm = 0.f;
             if (EPI == EPI_GN_MISH) {
-                // ---- pass 1: per-row partial sums of every group in this thread's column half ----
+                // ---- pass 1: per-row sums of every group in this thread's column half ----
                 float s1[HG], s2[HG];
 #pragma unroll
                 for (int g = 0; g < HG; ++g) { s1[g] = 0.f; s2[g] = 0.f; }
 #pragma unroll
-                for (int c = 0; c < HALF_N; c += 32) {
-                    tmem_ld32(taddr + c, v);
+                for (int cc = 0; cc < NCHUNK; ++cc) {
+                    tmem_ld32(taddr + cc * 32, v);
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 b4 = bias4[(cbase + c + i) >> 2];
-                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const float x = v[i + u] + bb[u];
-                            const int g = (c + i + u) / CPG;
-                            s1[g] += x;
-                            s2[g] = fmaf(x, x, s2[g]);
-                        }
+                    for (int i = 0; i < 32; ++i) {
+                        const int g = (cc * 32 + i) / CPG;
+                        s1[g] += v[i];
+                        s2[g] = fmaf(v[i], v[i], s2[g]);
                     }
                 }
+                // ---- segmented warp reduction over the rows (lanes) of each slice ----
 #pragma unroll
-                for (int g = 0; g < HG; ++g) {
-                    part[row * PSTRIDE + 2 * (half * HG + g)] = s1[g];
-                    part[row * PSTRIDE + 2 * (half * HG + g) + 1] = s2[g];
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                // ---- reduce over the H rows of each slice ----
-                const float inv_cnt = 1.0f / (float)(p.H * CPG);
-                for (int idx = et; idx < p.slices_per_tile * NG; idx += 256) {
-                    const int s_l = idx / NG, g = idx - s_l * NG;
-                    float a = 0.f, b = 0.f;
-                    for (int h = 0; h < p.H; ++h) {
-                        a += part[(s_l * p.H + h) * PSTRIDE + 2 * g];
-                        b += part[(s_l * p.H + h) * PSTRIDE + 2 * g + 1];
+                for (int k = 0; k < 5; ++k) {
+                    const bool same = (same_mask >> k) & 1u;
+#pragma unroll
+                    for (int g = 0; g < HG; ++g) {
+                        const float o1 = __shfl_down_sync(0xffffffffu, s1[g], 1 << k);
+                        const float o2 = __shfl_down_sync(0xffffffffu, s2[g], 1 << k);
+                        if (same) { s1[g] += o1; s2[g] += o2; }
                     }
-                    const float mean = a * inv_cnt;
-                    const float var = fmaxf(b * inv_cnt - mean * mean, 0.f);
-                    stats[s_l * 8 + g] = make_float2(mean, rsqrtf(var + 1e-5f));
                 }
-                if (N_TILE <= 128 && p.tma_out && et == 0) tma_store_wait_read();   // staging is free again after this barrier
+                float* pb = part + acc * PART_BUF;                // parity-buffered: a fast warp cannot run two tiles ahead
+                if (seg_head) {
+#pragma unroll
+                    for (int g = 0; g < HG; ++g)
+                        *reinterpret_cast<float2*>(pb + ((sl * 2 + seg_which) * 8 + half * HG + g) * 2) = make_float2(s1[g], s2[g]);
+                }
+                if (stage_out && et == 0) tma_store_wait_read();  // staging is free again after this barrier
                 asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
                 for (int g = 0; g < HG; ++g) {
-                    const float2 st = stats[sl * 8 + half * HG + g];
-                    g_mean[g] = st.x; g_rstd[g] = st.y;
+                    float2 tot = *reinterpret_cast<const float2*>(pb + ((sl * 2) * 8 + half * HG + g) * 2);
+                    if (spans) {
+                        const float2 t2 = *reinterpret_cast<const float2*>(pb + ((sl * 2 + 1) * 8 + half * HG + g) * 2);
+                        tot.x += t2.x; tot.y += t2.y;
+                    }
+                    const float mean = tot.x * inv_cnt;
+                    const float rstd = rsqrtf(fmaxf(tot.y * inv_cnt - mean * mean, 0.f) + 1e-5f);
+                    g_sc[g] = rstd; g_sh[g] = -mean * rstd;
                 }
+            } else if (T3) {
+                // ---- block-Toeplitz tile: row = slice; the group statistics live in this row's own columns ----
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int cc = 0; cc < NCHUNK; ++cc) {
+                    tmem_ld32(taddr + cc * 32, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
+                }
+                if (CPG == 64) {
+                    // the group spans both column halves: exchange partial sums with the partner warp
+                    float* ex = part + acc * PART_BUF;
+                    *reinterpret_cast<float2*>(ex + (half * 128 + row) * 2) = make_float2(s1, s2);
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    const float2 o = *reinterpret_cast<const float2*>(ex + ((half ^ 1) * 128 + row) * 2);
+                    s1 += o.x; s2 += o.y;
+                }
+                const float mean = s1 * (1.0f / (float)GCOLS);
+                t3_rstd = rsqrtf(fmaxf(s2 * (1.0f / (float)GCOLS) - mean * mean, 0.f) + 1e-5f);
+                t3_nm = -mean * t3_rstd;
+            } else if (stage_out) {
+                if (et == 0) tma_store_wait_read();               // the previous tile's store has finished reading staging
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             // ---- pass 2 (or the only pass): normalise / activate / add / store ----
-            const bool stage_out = (N_TILE <= 128) && p.tma_out;
-            if (stage_out && EPI == EPI_BIAS) {
-                if (et == 0) tma_store_wait_read();                // the previous tile's store has finished reading staging
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-            }
 #pragma unroll
-            for (int c = 0; c < HALF_N; c += 32) {
-                tmem_ld32(taddr + c, v);
+            for (int cc = 0; cc < NCHUNK; ++cc) {
+                tmem_ld32(taddr + cc * 32, v);
+                const int chb = chunk_channel(n_tile, cc);
                 uint32_t packed[16];
                 uint4 rn[4];
-                if (res != nullptr && valid && c + 32 < HALF_N) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(res + grow * p.cout + cbase + c + 32);
+                if (res != nullptr && valid && cc + 1 < NCHUNK) {  // next chunk's residual, in flight during this chunk's math
+                    const uint4* rp = reinterpret_cast<const uint4*>(res + chunk_offset(cc + 1));
 #pragma unroll
                     for (int j = 0; j < 4; ++j) rn[j] = rp[j];
                 }
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    const int ch4 = (cbase + c + i) >> 2;
-                    const float4 b4 = bias4[ch4];
-                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
                     float y[4];
-                    if (EPI == EPI_GN_MISH) {
+                    if (HAS_GN) {
+                        const int ch4 = (chb + i) >> 2;
                         const float4 ga4 = gamma4[ch4], be4 = beta4[ch4], ad4 = add4[ch4];
                         const float ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w}, be[4] = {be4.x, be4.y, be4.z, be4.w};
                         const float ad[4] = {ad4.x, ad4.y, ad4.z, ad4.w};
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const int g = (c + i + u) / CPG;
-                            const float sc = g_rstd[g] * ga[u];
-                            const float x = fmaf(v[i + u] + bb[u] - g_mean[g], sc, be[u]);
+                            const int g = T3 ? 0 : (cc * 32 + i + u) / CPG;
+                            const float rs = T3 ? t3_rstd : g_sc[g], nm = T3 ? t3_nm : g_sh[g];
+                            const float sc = rs * ga[u];
+                            const float x = fmaf(v[i + u], sc, fmaf(nm, ga[u], be[u]));      // (v - mean) * rstd * gamma + beta
                             y[u] = mish_fast(x) + ad[u];
                         }
                     } else {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) y[u] = v[i + u] + bb[u];
+                        for (int u = 0; u < 4; ++u) y[u] = v[i + u];
                     }
                     if (res != nullptr) {
                         const uint32_t* rw = reinterpret_cast<const uint32_t*>(rv);
@@ -514,7 +499,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 }
                 if (stage_out) {
                     // 128-byte-swizzled staging slab of 64 channels: 16-byte chunk index XOR (row & 7)
-                    const int col = half * HALF_N + c;             // column inside the N tile
+                    const int col = half * HALF_N + cc * 32;       // column inside the N tile
                     uint8_t* slab = staging + (col >> 6) * kATileBytes + row * 128;
                     const int ck = (col & 63) >> 3;
 #pragma unroll
@@ -522,19 +507,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                         *reinterpret_cast<uint4*>(slab + (((ck + j) ^ (row & 7)) << 4)) =
                             make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
                 } else if (valid) {
-                    uint4* op = reinterpret_cast<uint4*>(out + (grow * p.out_mul + p.out_add) * p.cout + cbase + c);
+                    const long long off = T3 ? chunk_offset(cc) : (grow * p.out_mul + p.out_add) * p.cout + chb;
+                    uint4* op = reinterpret_cast<uint4*>(out + off);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         op[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
                 }
-                if (res != nullptr && c + 32 < HALF_N) {
+                if (res != nullptr && cc + 1 < NCHUNK) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) rv[j] = rn[j];
                 }
             }
+            // ---- hand the accumulator back, pre-loaded with the bias of the tile that will use it next ----
+            {
+                const int nxt = tile + 2 * gridDim.x;
+                if (nxt < num_tiles) init_accumulator(acc, nxt % p.n_tiles);
+            }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);          // TMEM is drained: the MMA warp may reuse this accumulator
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (stage_out) {
                 fence_proxy_async();                               // generic-proxy smem writes -> visible to the TMA engine
                 asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -547,7 +538,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if ((N_TILE <= 128) && p.tma_out && et == 0) tma_store_wait_all();   // global writes complete before the CTA exits
+        if (stage_out && et == 0) tma_store_wait_all();           // global writes complete before the CTA exits
     }
     tc_fence_before();
     __syncthreads();
@@ -603,7 +594,7 @@ int encode_weight_map(CUtensorMap* map, const void* base, int prec, int rows, in
 template <int N_TILE>
 constexpr size_t smem_bytes_for() {
     return 1024 + (size_t)kStages * (kATileBytes + N_TILE * 128) + (N_TILE <= 128 ? (N_TILE / 64) * kATileBytes : 0) +
-           4 * 512 * 4 + 128 * 17 * 4 + 42 * 8 * 8 + (2 * kStages + 4) * 8 + 16;
+           4 * 512 * 4 + 2 * 1408 * 4 + (2 * kStages + 4) * 8 + 16;
 }
 
 int num_sms() {
