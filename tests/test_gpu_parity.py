@@ -337,3 +337,23 @@ def test_composed_eps_tcgen05_fp16(diffusion, golden, case):
     g = golden("composed_eps.npz")
     eps = diffusion.composed_eps(torch.from_numpy(g[case + ":x"]), t, nc, start, n, mode)
     assert rel_l2(eps, g[case + ":eps"]) < HALF_TOL
+
+
+def test_driver_cli_end_to_end(tmp_path):
+    """The mirrored CLI: sample (1000 DDPM steps, small batch), score on the GPU, write the record pickle."""
+    import pickle
+    from cindm_b200.inference.inverse_design_diffusion_1d import main
+    results = main(["--exp_id=test", "--date_time=00-00", "--n_composed=1", "--compose_n_bodies=4", "--compose_mode=mean-inside",
+                    "--design_guidance=standard", "--design_coef=0.2", "--consistency_coef=0.2", "--batch_size_list=[6]",
+                    "--model_name=Diffusion_cond-0_rollout-24_bodies-2", f"--results_dir={tmp_path}", "--top_k=2"])
+    rec = results[0]
+    for key in ("pred", "pred_simu", "design_obj_simu", "design_obj_simu_CI", "RMSE", "RMSE_CI", "MAE", "MAE_CI",
+                "design_coef", "consistency_coef", "design_guidance"):                     # the reference's record keys (:287-353)
+        assert key in rec, key
+    assert rec["pred"].shape == (6, 34, 16) and rec["pred_simu"].shape == (6, 33, 16)
+    assert np.isfinite(rec["pred"]).all() and np.abs(rec["pred"]).max() < 1.5            # x0 is clamped to [-1, 1] at every step
+    assert len(rec["top_k_indices"]) == 2
+    files = list((tmp_path / "test_00-00").glob("record_*.p"))
+    assert len(files) == 1
+    with open(files[0], "rb") as f:
+        assert "MAE" in pickle.load(f)
