@@ -68,9 +68,11 @@ __device__ __forceinline__ float mish_exact(float x) { return x * tanhf(log1pf(e
 // Same function with one ex2 and one rcp: tanh(log(1+w)) = (w^2+2w)/(w^2+2w+2), w = e^x.
 // The exponent is clamped at 20 where the ratio already rounds to 1.0f, so no branch is needed for large x.
 __device__ __forceinline__ float mish_fast(float x) {
-    float w = exp2f(fminf(x, 20.0f) * 1.4426950408889634f);
-    float n = w * (w + 2.0f);
-    return x * __fdividef(n, n + 2.0f);
+    float w, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(fminf(x, 20.0f) * 1.4426950408889634f));
+    const float n = w * (w + 2.0f);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n + 2.0f));
+    return x * (n * r);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -190,8 +190,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     constexpr int ACC_STRIDE = (N_TILE == 192) ? 256 : N_TILE;        // TMEM columns between the two accumulators
     constexpr bool HAS_GN = (EPI != EPI_BIAS);
 
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // dynamic shared memory starts 1024-byte aligned (required by the 128-byte swizzle); using the array directly
+    // (no integer round-trip) keeps every access in the shared address space (LDS/STS instead of generic LD/ST)
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* tiles = smem;                                             // kStages x (A | B)
     constexpr int kStagingBytes = (N_TILE <= 128) ? (N_TILE / 64) * kATileBytes : 0;   // [N_TILE/64 slabs][128 rows][128 B]
     uint8_t* staging = smem + kStages * kStageBytes;                   // 1024-byte aligned (stage sizes are multiples of 1 KB)
