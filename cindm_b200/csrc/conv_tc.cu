@@ -24,7 +24,9 @@ namespace cindm {
 
 namespace {
 
-constexpr int kStages = 4;
+// pipeline depth per N tile: as deep as the 227 KB of shared memory allow (A 16 KB + B N*128 B per stage,
+// plus the output staging slabs of the N <= 128 kernels and ~20 KB of vectors / partials / barriers)
+constexpr int stages_for(int n_tile) { return n_tile == 256 ? 4 : (n_tile == 192 ? 5 : (n_tile == 128 ? 5 : 6)); }
 constexpr int kBlockK = 64;                  // 64 x 16-bit = one 128-byte swizzle row
 constexpr int kATileBytes = 128 * 128;       // 128 rows x 128 B
 constexpr int kThreads = 320;             // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
@@ -185,6 +187,7 @@ template <typename T16, int N_TILE, int CPG, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out, const TcParams p) {
+    constexpr int kStages = stages_for(N_TILE);
     constexpr int kBTileBytes = N_TILE * 128;
     constexpr int kStageBytes = kATileBytes + kBTileBytes;
     constexpr int ACC_STRIDE = (N_TILE == 192) ? 256 : N_TILE;        // TMEM columns between the two accumulators
@@ -594,8 +597,8 @@ int encode_weight_map(CUtensorMap* map, const void* base, int prec, int rows, in
 
 template <int N_TILE>
 constexpr size_t smem_bytes_for() {
-    return 1024 + (size_t)kStages * (kATileBytes + N_TILE * 128) + (N_TILE <= 128 ? (N_TILE / 64) * kATileBytes : 0) +
-           4 * 512 * 4 + 2 * 1408 * 4 + (2 * kStages + 4) * 8 + 16;
+    return 1024 + (size_t)stages_for(N_TILE) * (kATileBytes + N_TILE * 128) + (N_TILE <= 128 ? (N_TILE / 64) * kATileBytes : 0) +
+           4 * 512 * 4 + 2 * 1408 * 4 + (2 * stages_for(N_TILE) + 4) * 8 + 16;
 }
 
 int num_sms() {
