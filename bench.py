@@ -312,6 +312,14 @@ def run_b200(args, rank, local_rank, world):
         c["launches"] += int(groups); c["ms"] += float(total_ms); c["work"] += float(work)
     eval_ms = sum(c["ms"] for c in classes.values())
     S = WINDOWS * PAIRS * B
+    traffic = None
+    try:   # DRAM bytes of the same kernel class from the committed ncu capture (profiles/, per launch like `achieved`)
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1b_evaluation_traffic.json")))
+        for name, c in prof["classes"].items():
+            if "conv_tc_kernel" in name:
+                traffic = (c["dram_read_bytes"] + c["dram_write_bytes"]) / c["launches"]
+    except Exception:
+        pass
     if "conv_tc" in classes and classes["conv_tc"]["ms"] > 0:
         c = classes["conv_tc"]
         achieved = c["work"] / (c["ms"] * 1e-3) / 1e12
@@ -320,7 +328,9 @@ def run_b200(args, rank, local_rank, world):
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
                     "algorithmic_flop_per_launch_group": c["work"] / c["launches"], "avg_launch_ms": c["ms"] / c["launches"],
-                    "share_of_evaluation": c["ms"] / eval_ms, "traffic": None}
+                    "share_of_evaluation": c["ms"] / eval_ms, "traffic": traffic,
+                    "traffic_note": "ncu dram__bytes_read+write per conv_tc launch (profiles/r1b_evaluation_traffic.json); "
+                                    "algorithmic HBM bytes per launch are ~264 MB (read + write one 132 MB activation tensor)"}
     elif "conv_simt" in classes:
         c = classes["conv_simt"]
         achieved = c["work"] / (c["ms"] * 1e-3) / 1e12
