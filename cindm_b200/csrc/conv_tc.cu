@@ -26,7 +26,9 @@ namespace {
 
 // pipeline depth per N tile: as deep as the 227 KB of shared memory allow (A 16 KB + B N*128 B per stage,
 // plus the output staging slabs of the N <= 128 kernels and ~20 KB of vectors / partials / barriers)
-constexpr int stages_for(int n_tile) { return n_tile == 256 ? 4 : (n_tile == 192 ? 5 : (n_tile == 128 ? 5 : 6)); }
+constexpr int stages_for(int n_tile, int cg) {
+    return cg == 2 ? (n_tile == 256 ? 6 : 7) : (n_tile == 256 ? 4 : (n_tile == 192 ? 5 : (n_tile == 128 ? 5 : 6)));
+}
 constexpr int kBlockK = 64;                  // 64 x 16-bit = one 128-byte swizzle row
 constexpr int kATileBytes = 128 * 128;       // 128 rows x 128 B
 constexpr int kThreads = 320;             // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
@@ -97,6 +99,50 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) variants: the pair shares one 256-row MMA, each CTA stages its own A rows and half of B
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA loads whose completion is counted on the LEADER CTA's mbarrier (peer bit of the shared::cluster address cleared)
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_on_cta(uint64_t* bar, uint32_t cta) {      // arrive on the same barrier in CTA `cta` of the cluster
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 remaddr;\n\t"
+        "mapa.shared::cluster.u32 remaddr, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remaddr];\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {                          // arrives on this barrier in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -183,12 +229,13 @@ __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t u) {
 }
 
 // ------------------------------------------------------------------ the kernel
-template <typename T16, int N_TILE, int CPG, int EPI>
+template <typename T16, int N_TILE, int CPG, int EPI, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out, const TcParams p) {
-    constexpr int kStages = stages_for(N_TILE);
-    constexpr int kBTileBytes = N_TILE * 128;
+    // CG == 2: two CTAs of a cluster form one 256 x N_TILE MMA; each stages its own 128 A rows and N_TILE/2 rows of B
+    constexpr int kStages = stages_for(N_TILE, CG);
+    constexpr int kBTileBytes = N_TILE * 128 / CG;
     constexpr int kStageBytes = kATileBytes + kBTileBytes;
     constexpr int ACC_STRIDE = (N_TILE == 192) ? 256 : N_TILE;        // TMEM columns between the two accumulators
     constexpr bool HAS_GN = (EPI != EPI_BIAS);
@@ -211,17 +258,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_tiles = p.m_tiles * p.n_tiles;
+    const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    // tiles are handed out per cluster: pair-tile t = (m_pair, n_tile); this CTA works on m_tile = m_pair * CG + rank
+    const int num_tiles = ((p.m_tiles + CG - 1) / CG) * p.n_tiles;
+    const int tile_first = blockIdx.x / CG, tile_step = gridDim.x / CG;
     const int k_chunks = p.taps * p.k_chunks_per_tap;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8 * CG); }
         fence_barrier_init();
         tma_prefetch_desc(&map_a0);
         tma_prefetch_desc(&map_b);
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == 1) { if (CG == 2) tmem_alloc_pair(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
     // per-layer channel vectors -> smem (epilogue broadcast reads)
     {
         const float* addv = p.add_vec;
@@ -233,7 +284,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();      // barrier inits / TMEM allocation visible to the whole pair
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -241,27 +292,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         // =============================== TMA producer ===============================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+                const int m_pair = tile / p.n_tiles, n_tile = tile - m_pair * p.n_tiles;
+                const int m_tile = m_pair * CG + (int)cta_rank;
                 const int s0 = m_tile * p.slices_per_tile;
-                const uint32_t tx_bytes = (uint32_t)(p.rows_used * 128 + kBTileBytes);
+                const uint32_t tx_bytes = (uint32_t)(p.rows_used * 128 + kBTileBytes) * CG;   // leader counts both CTAs' bytes
+                const int b_row0 = n_tile * N_TILE + (int)cta_rank * (N_TILE / CG);
                 for (int tap = 0; tap < p.taps; ++tap) {
                     for (int kc = 0; kc < p.k_chunks_per_tap; ++kc) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* a_dst = tiles + stage * kStageBytes;
                         uint8_t* b_dst = a_dst + kATileBytes;
-                        mbar_expect_tx(&full_bar[stage], tx_bytes);
+                        if (leader) mbar_expect_tx(&full_bar[stage], tx_bytes);
+                        // A coordinates (channel, H start, first slice) and B coordinates (k, weight row) of this K block
+                        int a_c, a_h, b_k, b_r;
+                        bool second;
                         if (EPI == EPI_GN_MISH_T3) {
                             // K index = (input position q, channel ci); the A matrix is the [S][3*C] view of the tensor
                             const int qpos = kc / p.kpp, ci = (kc - qpos * p.kpp) * kBlockK;
-                            if (ci < p.c0) tma_load_3d(&map_a0, &full_bar[stage], a_dst, qpos * p.c0 + ci, 0, s0);
-                            else           tma_load_3d(&map_a1, &full_bar[stage], a_dst, qpos * p.c1 + ci - p.c0, 0, s0);
-                            tma_load_2d(&map_b, &full_bar[stage], b_dst, kc * kBlockK, n_tile * N_TILE);
+                            second = ci >= p.c0;
+                            a_c = second ? qpos * p.c1 + ci - p.c0 : qpos * p.c0 + ci;
+                            a_h = 0; b_k = kc * kBlockK; b_r = b_row0;
                         } else {
                             const int ci = kc * kBlockK;
-                            if (ci < p.c0) tma_load_3d(&map_a0, &full_bar[stage], a_dst, ci, p.tap_hoff[tap], s0);
-                            else           tma_load_3d(&map_a1, &full_bar[stage], a_dst, ci - p.c0, p.tap_hoff[tap], s0);
-                            tma_load_2d(&map_b, &full_bar[stage], b_dst, ci, p.tap_wrow[tap] + n_tile * N_TILE);
+                            second = ci >= p.c0;
+                            a_c = second ? ci - p.c0 : ci;
+                            a_h = p.tap_hoff[tap]; b_k = ci; b_r = p.tap_wrow[tap] + b_row0;
+                        }
+                        if (CG == 2) {
+                            tma_load_3d_pair(second ? &map_a1 : &map_a0, &full_bar[stage], a_dst, a_c, a_h, s0);
+                            tma_load_2d_pair(&map_b, &full_bar[stage], b_dst, b_k, b_r);
+                        } else {
+                            tma_load_3d(second ? &map_a1 : &map_a0, &full_bar[stage], a_dst, a_c, a_h, s0);
+                            tma_load_2d(&map_b, &full_bar[stage], b_dst, b_k, b_r);
                         }
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
@@ -271,12 +334,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         __syncwarp();
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
-        if (lane == 0) {
+        if (lane == 0 && leader) {
             constexpr uint32_t idesc = (1u << 4) | (Fmt<T16>::kind << 7) | (Fmt<T16>::kind << 10) |
-                                       ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                                       ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
                 mbar_wait(&tmem_empty[acc], acc_phase);      // the epilogue has pre-loaded this accumulator with the bias
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
@@ -287,12 +350,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                     const uint32_t b_addr = a_addr + kATileBytes;
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
-                        tc_mma_f16(d_tmem, umma_smem_desc(a_addr + k * 32), umma_smem_desc(b_addr + k * 32), idesc, 1u);
+                        if (CG == 2) tc_mma_f16_pair(d_tmem, umma_smem_desc(a_addr + k * 32), umma_smem_desc(b_addr + k * 32), idesc, 1u);
+                        else tc_mma_f16(d_tmem, umma_smem_desc(a_addr + k * 32), umma_smem_desc(b_addr + k * 32), idesc, 1u);
                     }
-                    tc_commit(&empty_bar[stage]);                 // frees the smem stage when the MMAs retire
+                    if (CG == 2) tc_commit_pair(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);   // frees the smem stage (both CTAs)
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&tmem_full[acc]);                       // accumulator ready for the epilogue
+                if (CG == 2) tc_commit_pair(&tmem_full[acc]); else tc_commit(&tmem_full[acc]);           // accumulator ready for the epilogue(s)
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -357,16 +421,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const float inv_cnt = 1.0f / (float)(p.H * CPG);
 
         {   // both accumulators start out holding the bias of the first two tiles of this CTA
-            const int t0 = blockIdx.x, t1 = blockIdx.x + gridDim.x;
+            const int t0 = tile_first, t1 = tile_first + tile_step;
             if (t0 < num_tiles) init_accumulator(0, t0 % p.n_tiles);
             if (t1 < num_tiles) init_accumulator(1, t1 % p.n_tiles);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&tmem_empty[0]); mbar_arrive(&tmem_empty[1]); }
+            if (lane == 0) {
+                if (CG == 2) { mbar_arrive_on_cta(&tmem_empty[0], 0); mbar_arrive_on_cta(&tmem_empty[1], 0); }
+                else { mbar_arrive(&tmem_empty[0]); mbar_arrive(&tmem_empty[1]); }
+            }
         }
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+            const int m_pair = tile / p.n_tiles, n_tile = tile - m_pair * p.n_tiles;
+            const int m_tile = m_pair * CG + (int)cta_rank;
             const long long s0 = (long long)m_tile * p.slices_per_tile;
             const int n0 = n_tile * N_TILE;
             const bool valid = T3 ? (s0 + row) < p.S : (row < p.rows_used && (s0 + sl) < p.S);
@@ -524,12 +592,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             }
             // ---- hand the accumulator back, pre-loaded with the bias of the tile that will use it next ----
             {
-                const int nxt = tile + 2 * gridDim.x;
+                const int nxt = tile + 2 * tile_step;
                 if (nxt < num_tiles) init_accumulator(acc, nxt % p.n_tiles);
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) { if (CG == 2) mbar_arrive_on_cta(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
             if (stage_out) {
                 fence_proxy_async();                               // generic-proxy smem writes -> visible to the TMA engine
                 asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -545,10 +613,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if (stage_out && et == 0) tma_store_wait_all();           // global writes complete before the CTA exits
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();      // nobody leaves while its partner may still touch its smem / TMEM
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (CG == 2) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -595,10 +663,10 @@ int encode_weight_map(CUtensorMap* map, const void* base, int prec, int rows, in
     return 0;
 }
 
-template <int N_TILE>
+template <int N_TILE, int CG>
 constexpr size_t smem_bytes_for() {
-    return 1024 + (size_t)stages_for(N_TILE) * (kATileBytes + N_TILE * 128) + (N_TILE <= 128 ? (N_TILE / 64) * kATileBytes : 0) +
-           4 * 512 * 4 + 2 * 1408 * 4 + (2 * stages_for(N_TILE) + 4) * 8 + 16;
+    return 1024 + (size_t)stages_for(N_TILE, CG) * (kATileBytes + N_TILE * 128 / CG) + (N_TILE <= 128 ? (N_TILE / 64) * kATileBytes : 0) +
+           4 * 512 * 4 + 2 * 1408 * 4 + (2 * stages_for(N_TILE, CG) + 4) * 8 + 16;
 }
 
 int num_sms() {
@@ -612,19 +680,26 @@ int num_sms() {
     return n;
 }
 
-template <typename T16, int N_TILE, int CPG, int EPI>
+template <typename T16, int N_TILE, int CPG, int EPI, int CG>
 int launch_instance(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& mo, const TcParams& p,
                     cudaStream_t st) {
-    auto kern = conv_tc_kernel<T16, N_TILE, CPG, EPI>;
-    constexpr size_t smem = smem_bytes_for<N_TILE>();
+    auto kern = conv_tc_kernel<T16, N_TILE, CPG, EPI, CG>;
+    constexpr size_t smem = smem_bytes_for<N_TILE, CG>();
     static bool configured = false;
     if (!configured) {
         CINDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    int tiles = p.m_tiles * p.n_tiles;
-    int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, kThreads, smem, st>>>(a0, a1, b, mo, p);
+    const int tiles = ((p.m_tiles + CG - 1) / CG) * p.n_tiles;          // (pair-)tiles
+    const int slots = num_sms() / CG;                                   // clusters that fit on the machine
+    const int grid = (tiles < slots ? tiles : slots) * CG;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CINDM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a0, a1, b, mo, p));
     CINDM_CHECK_LAUNCH();
     return 0;
 }
@@ -634,24 +709,24 @@ int dispatch(const ConvTcLaunch& a, const CUtensorMap& m0, const CUtensorMap& m1
              const TcParams& p, int n_tile, cudaStream_t st) {
     if (a.epilogue == EPI_GN_MISH_T3) {
         switch (p.cout) {
-            case 256: return launch_instance<T16, 192, 32, EPI_GN_MISH_T3>(m0, m1, mb, mo, p, st);
-            case 512: return launch_instance<T16, 192, 64, EPI_GN_MISH_T3>(m0, m1, mb, mo, p, st);
+            case 256: return launch_instance<T16, 192, 32, EPI_GN_MISH_T3, 2>(m0, m1, mb, mo, p, st);
+            case 512: return launch_instance<T16, 192, 64, EPI_GN_MISH_T3, 2>(m0, m1, mb, mo, p, st);
         }
         return fail(-2, "conv_tc: the block-Toeplitz path is built for 256 / 512 output channels");
     }
     if (a.epilogue == EPI_GN_MISH) {
         switch (p.cout) {
-            case 64: return launch_instance<T16, 64, 8, EPI_GN_MISH>(m0, m1, mb, mo, p, st);
-            case 128: return launch_instance<T16, 128, 16, EPI_GN_MISH>(m0, m1, mb, mo, p, st);
-            case 256: return launch_instance<T16, 256, 32, EPI_GN_MISH>(m0, m1, mb, mo, p, st);
-            case 512: return launch_instance<T16, 256, 64, EPI_GN_MISH>(m0, m1, mb, mo, p, st);
+            case 64: return launch_instance<T16, 64, 8, EPI_GN_MISH, 1>(m0, m1, mb, mo, p, st);
+            case 128: return launch_instance<T16, 128, 16, EPI_GN_MISH, 1>(m0, m1, mb, mo, p, st);
+            case 256: return launch_instance<T16, 256, 32, EPI_GN_MISH, 2>(m0, m1, mb, mo, p, st);
+            case 512: return launch_instance<T16, 256, 64, EPI_GN_MISH, 2>(m0, m1, mb, mo, p, st);
         }
         return fail(-2, "conv_tc: unsupported channel count for the GroupNorm epilogue");
     }
     switch (n_tile) {
-        case 64: return launch_instance<T16, 64, 8, EPI_BIAS>(m0, m1, mb, mo, p, st);
-        case 128: return launch_instance<T16, 128, 8, EPI_BIAS>(m0, m1, mb, mo, p, st);
-        case 256: return launch_instance<T16, 256, 8, EPI_BIAS>(m0, m1, mb, mo, p, st);
+        case 64: return launch_instance<T16, 64, 8, EPI_BIAS, 1>(m0, m1, mb, mo, p, st);
+        case 128: return launch_instance<T16, 128, 8, EPI_BIAS, 1>(m0, m1, mb, mo, p, st);
+        case 256: return launch_instance<T16, 256, 8, EPI_BIAS, 1>(m0, m1, mb, mo, p, st);
     }
     return fail(-2, "conv_tc: unsupported N tile");
 }
@@ -681,7 +756,7 @@ static int launch_conv_tc_one(const ConvTcLaunch& a, int parity, cudaStream_t st
         CINDM_TRY(encode_act_map(&m0, a.in0, a.prec, a.S, 1, 3 * a.c0, 128, 1, 1));
         if (a.in1) CINDM_TRY(encode_act_map(&m1, a.in1, a.prec, a.S, 1, 3 * a.c1, 128, 1, 1));
         else m1 = m0;
-        CINDM_TRY(encode_weight_map(&mb, w.w16t[a.prec], a.prec, 3 * w.cout, 3 * w.cin, 192));
+        CINDM_TRY(encode_weight_map(&mb, w.w16t[a.prec], a.prec, 3 * w.cout, 3 * w.cin, 192 / 2));   // CTA pair: half of B each
         p.tma_out = 0;
         if (a.prec == PREC_F16) return dispatch<__half>(a, m0, m1, mb, m0, p, 192, st);
         return dispatch<__nv_bfloat16>(a, m0, m1, mb, m0, p, 192, st);
@@ -720,7 +795,8 @@ static int launch_conv_tc_one(const ConvTcLaunch& a, int parity, cudaStream_t st
     CINDM_TRY(encode_act_map(&m0, a.in0, a.prec, a.S, a.H, a.c0, p.slices_per_tile, p.H, h_stride));
     if (a.in1) CINDM_TRY(encode_act_map(&m1, a.in1, a.prec, a.S, a.H, a.c1, p.slices_per_tile, p.H, h_stride));
     else m1 = m0;
-    CINDM_TRY(encode_weight_map(&mb, w.w16[a.prec], a.prec, w.taps * w.cout, w.cin, n_tile));
+    const int cg = (a.epilogue == EPI_GN_MISH && n_tile == 256) ? 2 : 1;       // the N = 256 GroupNorm kernels run as CTA pairs
+    CINDM_TRY(encode_weight_map(&mb, w.w16[a.prec], a.prec, w.taps * w.cout, w.cin, n_tile / cg));
     // output tile through shared memory + TMA store: whole-row 128-byte bursts instead of 32 scattered 16-byte
     // stores per warp instruction (the transposed conv's interleaved rows keep the direct stores)
     CUtensorMap mo = m0;
