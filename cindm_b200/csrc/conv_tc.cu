@@ -15,6 +15,7 @@
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-9 epilogue
 // (two warps per TMEM lane quarter, each owning half of the tile's columns).
 #include <cstdio>
+#include <cstdlib>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -704,13 +705,22 @@ int launch_instance(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensor
     return 0;
 }
 
+// CTA-pair (cta_group::2) MMA for the N >= 192 kernels; CINDM_CONV_PAIR=0 selects the single-CTA variant (A/B runs)
+bool pair_mode() {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("CINDM_CONV_PAIR"); mode = (e && e[0] == '0') ? 0 : 1; }
+    return mode == 1;
+}
+
 template <typename T16>
 int dispatch(const ConvTcLaunch& a, const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& mb, const CUtensorMap& mo,
              const TcParams& p, int n_tile, cudaStream_t st) {
     if (a.epilogue == EPI_GN_MISH_T3) {
         switch (p.cout) {
-            case 256: return launch_instance<T16, 192, 32, EPI_GN_MISH_T3, 2>(m0, m1, mb, mo, p, st);
-            case 512: return launch_instance<T16, 192, 64, EPI_GN_MISH_T3, 2>(m0, m1, mb, mo, p, st);
+            case 256: return pair_mode() ? launch_instance<T16, 192, 32, EPI_GN_MISH_T3, 2>(m0, m1, mb, mo, p, st)
+                                         : launch_instance<T16, 192, 32, EPI_GN_MISH_T3, 1>(m0, m1, mb, mo, p, st);
+            case 512: return pair_mode() ? launch_instance<T16, 192, 64, EPI_GN_MISH_T3, 2>(m0, m1, mb, mo, p, st)
+                                         : launch_instance<T16, 192, 64, EPI_GN_MISH_T3, 1>(m0, m1, mb, mo, p, st);
         }
         return fail(-2, "conv_tc: the block-Toeplitz path is built for 256 / 512 output channels");
     }
@@ -718,8 +728,10 @@ int dispatch(const ConvTcLaunch& a, const CUtensorMap& m0, const CUtensorMap& m1
         switch (p.cout) {
             case 64: return launch_instance<T16, 64, 8, EPI_GN_MISH, 1>(m0, m1, mb, mo, p, st);
             case 128: return launch_instance<T16, 128, 16, EPI_GN_MISH, 1>(m0, m1, mb, mo, p, st);
-            case 256: return launch_instance<T16, 256, 32, EPI_GN_MISH, 2>(m0, m1, mb, mo, p, st);
-            case 512: return launch_instance<T16, 256, 64, EPI_GN_MISH, 2>(m0, m1, mb, mo, p, st);
+            case 256: return pair_mode() ? launch_instance<T16, 256, 32, EPI_GN_MISH, 2>(m0, m1, mb, mo, p, st)
+                                         : launch_instance<T16, 256, 32, EPI_GN_MISH, 1>(m0, m1, mb, mo, p, st);
+            case 512: return pair_mode() ? launch_instance<T16, 256, 64, EPI_GN_MISH, 2>(m0, m1, mb, mo, p, st)
+                                         : launch_instance<T16, 256, 64, EPI_GN_MISH, 1>(m0, m1, mb, mo, p, st);
         }
         return fail(-2, "conv_tc: unsupported channel count for the GroupNorm epilogue");
     }
@@ -756,7 +768,7 @@ static int launch_conv_tc_one(const ConvTcLaunch& a, int parity, cudaStream_t st
         CINDM_TRY(encode_act_map(&m0, a.in0, a.prec, a.S, 1, 3 * a.c0, 128, 1, 1));
         if (a.in1) CINDM_TRY(encode_act_map(&m1, a.in1, a.prec, a.S, 1, 3 * a.c1, 128, 1, 1));
         else m1 = m0;
-        CINDM_TRY(encode_weight_map(&mb, w.w16t[a.prec], a.prec, 3 * w.cout, 3 * w.cin, 192 / 2));   // CTA pair: half of B each
+        CINDM_TRY(encode_weight_map(&mb, w.w16t[a.prec], a.prec, 3 * w.cout, 3 * w.cin, pair_mode() ? 96 : 192));   // CTA pair: half of B each
         p.tma_out = 0;
         if (a.prec == PREC_F16) return dispatch<__half>(a, m0, m1, mb, m0, p, 192, st);
         return dispatch<__nv_bfloat16>(a, m0, m1, mb, m0, p, 192, st);
@@ -795,7 +807,7 @@ static int launch_conv_tc_one(const ConvTcLaunch& a, int parity, cudaStream_t st
     CINDM_TRY(encode_act_map(&m0, a.in0, a.prec, a.S, a.H, a.c0, p.slices_per_tile, p.H, h_stride));
     if (a.in1) CINDM_TRY(encode_act_map(&m1, a.in1, a.prec, a.S, a.H, a.c1, p.slices_per_tile, p.H, h_stride));
     else m1 = m0;
-    const int cg = (a.epilogue == EPI_GN_MISH && n_tile == 256) ? 2 : 1;       // the N = 256 GroupNorm kernels run as CTA pairs
+    const int cg = (a.epilogue == EPI_GN_MISH && n_tile == 256 && pair_mode()) ? 2 : 1;       // the N = 256 GroupNorm kernels run as CTA pairs
     CINDM_TRY(encode_weight_map(&mb, w.w16[a.prec], a.prec, w.taps * w.cout, w.cin, n_tile / cg));
     // output tile through shared memory + TMA store: whole-row 128-byte bursts instead of 32 scattered 16-byte
     // stores per warp instruction (the transposed conv's interleaved rows keep the direct stores)

@@ -251,6 +251,8 @@ class TemporalUnet1D:
         """x: [S, horizon, transition_dim]; time: [S] (all equal, as on the sampling path) -> [S, horizon, transition_dim]."""
         eng = self.engine()
         x = x.to(self._device, torch.float32).contiguous()
+        if x.shape[0] == 0:
+            return torch.empty_like(x)
         t = int(time.reshape(-1)[0].item()) if torch.is_tensor(time) else int(time)
         if torch.is_tensor(time) and time.numel() > 1 and not bool((time == time.reshape(-1)[0]).all()):
             raise NotImplementedError("per-sample timesteps are not on the sampling path")

@@ -357,3 +357,51 @@ def test_driver_cli_end_to_end(tmp_path):
     assert len(files) == 1
     with open(files[0], "rb") as f:
         assert "MAE" in pickle.load(f)
+
+
+def test_full_size_c4_candidate_independence(diffusion):
+    """BASELINE.json's full per-GPU size (C4: 512 candidates, 8 bodies, 3 windows -> 43 008 slices per evaluation) through
+    a size-independent property: every candidate is an independent unit, so sampling candidates [100, 164) alone must
+    reproduce, bit for bit, what they get inside the full batch (different tile packing, same Philox counters)."""
+    from cindm_b200.model.diffusion_1d import get_design_fn
+    set_precision(diffusion, "fp16", "tcgen05")
+    fn = get_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, coef=0.2, time_consistency_coef=0.2)
+    kw = dict(n_composed=2, compose_start_step=10, compose_n_bodies=8, compose_mode="mean-inside", design_fn=fn,
+              design_guidance="standard-recurrence-2")
+    steps = diffusion.num_timesteps
+    try:
+        diffusion.num_timesteps = 2                   # two DDPM steps (t = 1, 0) of the 1000-step schedule, R = 2
+        diffusion.seed, diffusion.candidate_offset = 5, 0
+        full = diffusion.p_sample_loop((512, 24, 8), None, **kw)
+        diffusion.candidate_offset = 100
+        part = diffusion.p_sample_loop((64, 24, 8), None, **kw)
+    finally:
+        diffusion.num_timesteps = steps
+        diffusion.candidate_offset = 0
+    assert torch.isfinite(full).all()
+    assert torch.equal(full[100:164], part)
+    # and the composed epsilon of the full batch agrees with the fp32 path within the 16-bit bar
+    x = full.clone()
+    e16 = diffusion.composed_eps(x, 321, 2, 10, 8)
+    set_precision(diffusion, "fp32", "simt")
+    e32 = diffusion.composed_eps(x[:24], 321, 2, 10, 8)
+    assert rel_l2(e16[:24], e32) < HALF_TOL
+
+
+@pytest.mark.parametrize("n,nc,start,mode", [(3, 3, 10, "mean-inside"), (2, 0, 10, "sum-inside"), (5, 1, 7, "mean-inside")])
+def test_composed_eps_odd_shapes_vs_oracle(diffusion, test_weights, n, nc, start, mode):
+    """Body counts / window strides the golden set does not contain, against the CPU oracle (fp32 and fp16 bars)."""
+    from oracle import sampler_ref
+    gen = torch.Generator().manual_seed(n * 10 + nc)
+    x = torch.randn(2, 24 + nc * start, 4 * n, generator=gen)
+    ref = sampler_ref.composed_eps(test_weights, x, 444, nc, start, n, mode)
+    set_precision(diffusion, "fp32", "simt")
+    assert rel_l2(diffusion.composed_eps(x, 444, nc, start, n, mode), ref) < FP32_TOL
+    set_precision(diffusion, "fp16", "tcgen05")
+    assert rel_l2(diffusion.composed_eps(x, 444, nc, start, n, mode), ref) < HALF_TOL
+
+
+def test_empty_batch_is_a_no_op(diffusion):
+    set_precision(diffusion, "fp16", "tcgen05")
+    out = diffusion.model(torch.zeros(0, 24, 8), torch.zeros(0, dtype=torch.long), None)
+    assert tuple(out.shape) == (0, 24, 8)
