@@ -251,8 +251,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     float* vec_gamma = vec_bias + 512;
     float* vec_beta = vec_gamma + 512;
     float* vec_add = vec_beta + 512;
-    float* part = vec_add + 512;                                       // 2 parity buffers of GroupNorm partial sums
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(part + 2 * 1408);
+    float* part = vec_add + 512;                                       // GroupNorm partial sums [128][8] float2 + totals [43][8] float2
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(part + 2048 + 704);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full = empty_bar + kStages;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -376,7 +376,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         constexpr int NCHUNK = HALF_N / 32;
         constexpr int HG = (EPI == EPI_GN_MISH) ? HALF_N / CPG : 1;   // groups owned by one thread (generic GN path)
         constexpr int GCOLS = 3 * CPG;                            // T3: accumulator columns of one GroupNorm group
-        constexpr int PART_BUF = 1408;                            // floats per parity buffer: 43 slices x 2 x 8 groups x 2
+        constexpr int PART_BUF = 1024;                            // T3: floats per parity buffer of the half-row exchange
         T16* out = reinterpret_cast<T16*>(p.out);
         const T16* res = reinterpret_cast<const T16*>(p.add_res);
         const float4* bias4 = reinterpret_cast<const float4*>(vec_bias);
@@ -412,13 +412,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         // loop-invariant GroupNorm geometry of this thread's row (generic path: rows of a slice are H consecutive lanes)
         const int sl = min(row / p.H, p.slices_per_tile - 1);     // slice within the tile
         const int row_in_slice = row - (row / p.H) * p.H;
-        uint32_t same_mask = 0;                                   // bit k: lane + 2^k belongs to the same slice
-#pragma unroll
-        for (int k = 0; k < 5; ++k)
-            if (lane + (1 << k) < 32 && (row + (1 << k)) / p.H == row / p.H) same_mask |= 1u << k;
-        const bool seg_head = (lane == 0 || row_in_slice == 0) && row < p.rows_used;
-        const int seg_which = row_in_slice == 0 ? 0 : 1;          // 1: continuation of a slice that started in the previous warp
-        const bool spans = ((sl * p.H) >> 5) != ((sl * p.H + p.H - 1) >> 5);
         const float inv_cnt = 1.0f / (float)(p.H * CPG);
 
         {   // both accumulators start out holding the bias of the first two tiles of this CTA
@@ -476,34 +469,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                         s2[g] = fmaf(v[i], v[i], s2[g]);
                     }
                 }
-                // ---- segmented warp reduction over the rows (lanes) of each slice ----
+                // ---- reduce over the H rows of each slice in a FIXED order (h = 0..H-1), so that a slice's statistics do
+                //      not depend on where it sits inside the tile: results are invariant to batch size / sharding ----
+                float2* pr = reinterpret_cast<float2*>(part);                       // [128 rows][8 groups]
+                float2* tot = reinterpret_cast<float2*>(part + 2048);               // [43 slices][8 groups]
 #pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    const bool same = (same_mask >> k) & 1u;
-#pragma unroll
-                    for (int g = 0; g < HG; ++g) {
-                        const float o1 = __shfl_down_sync(0xffffffffu, s1[g], 1 << k);
-                        const float o2 = __shfl_down_sync(0xffffffffu, s2[g], 1 << k);
-                        if (same) { s1[g] += o1; s2[g] += o2; }
+                for (int g = 0; g < HG; ++g) pr[row * 8 + half * HG + g] = make_float2(s1[g], s2[g]);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (row < p.rows_used) {
+                    for (int g = row_in_slice; g < HG; g += p.H) {
+                        float a = 0.f, b2 = 0.f;
+                        const float2* src = pr + (sl * p.H) * 8 + half * HG + g;
+                        for (int h = 0; h < p.H; ++h) { const float2 t = src[h * 8]; a += t.x; b2 += t.y; }
+                        tot[sl * 8 + half * HG + g] = make_float2(a, b2);
                     }
-                }
-                float* pb = part + acc * PART_BUF;                // parity-buffered: a fast warp cannot run two tiles ahead
-                if (seg_head) {
-#pragma unroll
-                    for (int g = 0; g < HG; ++g)
-                        *reinterpret_cast<float2*>(pb + ((sl * 2 + seg_which) * 8 + half * HG + g) * 2) = make_float2(s1[g], s2[g]);
                 }
                 if (stage_out && et == 0) tma_store_wait_read();  // staging is free again after this barrier
                 asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
                 for (int g = 0; g < HG; ++g) {
-                    float2 tot = *reinterpret_cast<const float2*>(pb + ((sl * 2) * 8 + half * HG + g) * 2);
-                    if (spans) {
-                        const float2 t2 = *reinterpret_cast<const float2*>(pb + ((sl * 2 + 1) * 8 + half * HG + g) * 2);
-                        tot.x += t2.x; tot.y += t2.y;
-                    }
-                    const float mean = tot.x * inv_cnt;
-                    const float rstd = rsqrtf(fmaxf(tot.y * inv_cnt - mean * mean, 0.f) + 1e-5f);
+                    const float2 t = tot[sl * 8 + half * HG + g];
+                    const float mean = t.x * inv_cnt;
+                    const float rstd = rsqrtf(fmaxf(t.y * inv_cnt - mean * mean, 0.f) + 1e-5f);
                     g_sc[g] = rstd; g_sh[g] = -mean * rstd;
                 }
             } else if (T3) {
@@ -667,7 +654,7 @@ int encode_weight_map(CUtensorMap* map, const void* base, int prec, int rows, in
 template <int N_TILE, int CG>
 constexpr size_t smem_bytes_for() {
     return 1024 + (size_t)stages_for(N_TILE, CG) * (kATileBytes + N_TILE * 128 / CG) + (N_TILE <= 128 ? (N_TILE / 64) * kATileBytes : 0) +
-           4 * 512 * 4 + 2 * 1408 * 4 + (2 * stages_for(N_TILE, CG) + 4) * 8 + 16;
+           4 * 512 * 4 + (2048 + 704) * 4 + (2 * stages_for(N_TILE, CG) + 4) * 8 + 16;
 }
 
 int num_sms() {
