@@ -451,6 +451,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = lane_base + (uint32_t)(acc * ACC_STRIDE);
+            // accumulator values are read from TMEM once when they fit in registers (<= 64 columns per thread)
+            constexpr bool KEEP = HAS_GN && NCHUNK <= 2;
+            float vk[KEEP ? NCHUNK : 1][32];
             float v[32];
             float g_sc[HG], g_sh[HG];                             // per group: rstd and -mean * rstd
             float t3_rstd = 0.f, t3_nm = 0.f;
@@ -461,12 +464,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 for (int g = 0; g < HG; ++g) { s1[g] = 0.f; s2[g] = 0.f; }
 #pragma unroll
                 for (int cc = 0; cc < NCHUNK; ++cc) {
-                    tmem_ld32(taddr + cc * 32, v);
+                    float (&vv)[32] = KEEP ? vk[KEEP ? cc : 0] : v;
+                    tmem_ld32(taddr + cc * 32, vv);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const int g = (cc * 32 + i) / CPG;
-                        s1[g] += v[i];
-                        s2[g] = fmaf(v[i], v[i], s2[g]);
+                        s1[g] += vv[i];
+                        s2[g] = fmaf(vv[i], vv[i], s2[g]);
                     }
                 }
                 // ---- reduce over the H rows of each slice in a FIXED order (h = 0..H-1), so that a slice's statistics do
@@ -520,7 +524,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             // ---- pass 2 (or the only pass): normalise / activate / add / store ----
 #pragma unroll
             for (int cc = 0; cc < NCHUNK; ++cc) {
-                tmem_ld32(taddr + cc * 32, v);
+                if (KEEP && EPI == EPI_GN_MISH) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = vk[KEEP ? cc : 0][i];
+                } else {
+                    tmem_ld32(taddr + cc * 32, v);
+                }
                 const int chb = chunk_channel(n_tile, cc);
                 uint32_t packed[16];
                 uint4 rn[4];

@@ -405,3 +405,16 @@ def test_empty_batch_is_a_no_op(diffusion):
     set_precision(diffusion, "fp16", "tcgen05")
     out = diffusion.model(torch.zeros(0, 24, 8), torch.zeros(0, dtype=torch.long), None)
     assert tuple(out.shape) == (0, 24, 8)
+
+
+def test_stale_script_mirrors_run_on_the_live_operator(tmp_path):
+    from cindm_b200.inference import inference_1d_composing_multibodies as mb
+    from cindm_b200.inference import inference_1d_composing_time_steps as ts
+    p = ts.main(["--time_compose_method=EBMs_compose", "--n_composed=2", "--val_batch_size=3", f"--results_dir={tmp_path}"])
+    assert tuple(p.shape) == (3, 44, 8) and torch.isfinite(p).all()
+    p = mb.main(["--multi_bodies_method=EBMs_compose", "--n_composed=2", "--val_batch_size=2", f"--results_dir={tmp_path}"])
+    assert tuple(p.shape) == (2, 24, 16) and torch.isfinite(p).all()
+    p = mb.main(["--multi_bodies_method=SimuSolver", "--n_composed=4", "--val_batch_size=5", f"--results_dir={tmp_path}"])
+    assert tuple(p.shape) == (5, 20, 32)
+    with pytest.raises(NotImplementedError):
+        ts.main(["--time_compose_method=autoregress"])

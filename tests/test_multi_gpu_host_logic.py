@@ -74,3 +74,19 @@ def test_cli_keeps_reference_flags_and_defaults():
     with pytest.raises(NotImplementedError):
         paper.model_name = "Diffusion_cond-0_rollout-44_bodies-2"
         model_horizon(paper)
+
+
+def test_stale_script_flags_are_kept():
+    """inference_1d_composing_time_steps.py:25-67 and inference_1d_composing_multibodies.py:25-66: names and defaults."""
+    from cindm_b200.inference import inference_1d_composing_multibodies as mb
+    from cindm_b200.inference import inference_1d_composing_time_steps as ts
+    a = ts.build_parser().parse_args([])
+    assert (a.date_time, a.val_batch_size, a.sample_steps, a.time_compose_method, a.n_composed) == ("2023-09-14", 1000, 1000, "autoregress", 1)
+    assert (a.conditioned_steps, a.rollout_steps, a.time_interval, a.milestone, a.is_single_step_prediction) == (4, 20, 4, 100, False)
+    for k in ("checkpoint_path_basic_model", "checkpoint_path_unconditioned", "checkpoint_path_single_step", "checkpoint_path_direct",
+              "checkpoint_path_GNS", "checkpoint_path_forward_model"):
+        assert getattr(a, k) is None
+    b = mb.build_parser().parse_args([])
+    assert (b.date_time, b.val_batch_size, b.sample_steps, b.multi_bodies_method, b.n_composed) == (
+        "2023-09-07_test_for_2_bodies", 1, 250, "EBMs_compose", 2)
+    assert b.checkpoint_path_direct_diffusion is None
