@@ -186,6 +186,7 @@ def run_b200(args, rank, local_rank, world):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     L = _lib.lib()

@@ -433,7 +433,7 @@ struct StemParams {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(256) stem_kernel(StemParams p) {
+__global__ void __launch_bounds__(256, 2) stem_kernel(StemParams p) {
     __shared__ float xs[4][24 + 4][8];                      // per-slice input with 2 zero rows of padding each side
     const int sub = threadIdx.x >> 6, co = threadIdx.x & 63;
     const long long s = (long long)blockIdx.x * 4 + sub;
