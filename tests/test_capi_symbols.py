@@ -93,3 +93,20 @@ def test_state_dict_layout_matches_reference_keys():
     dif.load_state_dict(sd)
     with pytest.raises(RuntimeError):
         dif.load_state_dict({k: v for k, v in sd.items() if k != "model.final_conv.1.bias"})
+
+
+def test_c_abi_reports_errors_instead_of_throwing(library):
+    """Argument validation happens before any CUDA call: negative code + message, nothing thrown across the boundary."""
+    from cindm_b200 import _lib
+    L = _lib.lib()
+    handle = ctypes.c_void_p()
+    for bad in (_lib.Config(44, 8, 64, 1000), _lib.Config(24, 8, 96, 1000), _lib.Config(24, 16, 64, 1000), _lib.Config(24, 8, 64, 0)):
+        rc = L.cindm_create(ctypes.byref(bad), ctypes.byref(handle))
+        assert rc < 0 and L.cindm_last_error()
+    assert L.cindm_create(None, ctypes.byref(handle)) < 0
+    assert L.cindm_build_index_maps(1, 0, 10, 24, None, None, None, None) < 0          # fewer than two bodies
+    assert L.cindm_build_index_maps(4, -1, 10, 24, None, None, None, None) < 0
+    assert L.cindm_schedule_tables(0, None) < 0
+    with pytest.raises(_lib.CindmError):
+        _lib.check(L.cindm_schedule_tables(0, None))
+    assert L.cindm_destroy(None) == 0

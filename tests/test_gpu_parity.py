@@ -418,3 +418,24 @@ def test_stale_script_mirrors_run_on_the_live_operator(tmp_path):
     assert tuple(p.shape) == (5, 20, 32)
     with pytest.raises(NotImplementedError):
         ts.main(["--time_compose_method=autoregress"])
+
+
+def test_initialization_modes(diffusion):
+    """initialization_mode 1 starts from the given trajectories, 2 from trajectories + N(0,1) (reference :1672-1678)."""
+    set_precision(diffusion, "fp32", "simt")
+    steps = diffusion.num_timesteps
+    gen = torch.Generator().manual_seed(3)
+    init = torch.rand(2, 24, 8, generator=gen)
+    kw = dict(n_composed=0, compose_start_step=10, compose_n_bodies=2, compose_mode="mean-inside", design_guidance="standard")
+    try:
+        diffusion.num_timesteps = 1                         # a single step at t = 0: no noise is added
+        diffusion.seed = 11
+        a = diffusion.p_sample_loop((2, 24, 8), None, initialization_mode=1, initialization_img=init, **kw).cpu()
+        x_direct, _ = diffusion.p_sample_compose_inside(init, None, 0, compose_mode="mean-inside", n_composed=0,
+                                                        compose_start_step=10, single_model_step=24, compose_n_bodies=2)
+        assert torch.equal(a, x_direct.cpu())
+        b = diffusion.p_sample_loop((2, 24, 8), None, initialization_mode=2, initialization_img=init, **kw).cpu()
+        c = diffusion.p_sample_loop((2, 24, 8), None, initialization_mode=0, **kw).cpu()
+        assert not torch.equal(a, b) and not torch.equal(b, c)
+    finally:
+        diffusion.num_timesteps = steps
