@@ -32,7 +32,11 @@ constexpr int stages_for(int n_tile, int cg) {
 }
 constexpr int kBlockK = 64;                  // 64 x 16-bit = one 128-byte swizzle row
 constexpr int kATileBytes = 128 * 128;       // 128 rows x 128 B
-constexpr int kThreads = 320;             // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+// warp 0 TMA, warp 1 MMA, then the epilogue warps: 8 (two per TMEM lane quarter, each owning half of the tile's columns)
+// or 16 (four per lane quarter, a quarter of the columns each) for the 128- and 256-column tiles, whose epilogue is
+// bound by instruction issue with too few warps to hide latency.
+constexpr int epi_warps_for(int n_tile, int epi) { return (epi == EPI_GN_MISH_T3 || n_tile == 64 || n_tile == 192) ? 8 : 16; }
+constexpr int threads_for(int n_tile, int epi) { return 64 + 32 * epi_warps_for(n_tile, epi); }
 
 struct TcParams {
     const float* bias;        // [cout] or null
@@ -231,7 +235,7 @@ __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t u) {
 
 // ------------------------------------------------------------------ the kernel
 template <typename T16, int N_TILE, int CPG, int EPI, int CG>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(threads_for(N_TILE, EPI), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out, const TcParams p) {
     // CG == 2: two CTAs of a cluster form one 256 x N_TILE MMA; each stages its own 128 A rows and N_TILE/2 rows of B
@@ -268,7 +272,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8 * CG); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], epi_warps_for(N_TILE, EPI) * CG); }
         fence_barrier_init();
         tma_prefetch_desc(&map_a0);
         tma_prefetch_desc(&map_b);
@@ -278,7 +282,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     {
         const float* addv = p.add_vec;
         if (addv && p.t_dev) addv += (long long)(*p.t_dev) * p.cout;
-        for (int c = threadIdx.x; c < p.cout; c += kThreads) {
+        for (int c = threadIdx.x; c < p.cout; c += blockDim.x) {
             vec_bias[c] = p.bias ? p.bias[c] : 0.f;
             if (HAS_GN) { vec_gamma[c] = p.gamma[c]; vec_beta[c] = p.beta[c]; }
             vec_add[c] = addv ? addv[c] : 0.f;
@@ -368,11 +372,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         // half of the tile's columns.  The conv bias is not added here: the epilogue writes it into the
         // accumulator (tcgen05.st) before the MMA warp starts the tile, so TMEM already holds conv + bias.
         const int q = warp & 3;                                   // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;                         // which half of the N tile
+        constexpr int EW = epi_warps_for(N_TILE, EPI);            // epilogue warps
+        constexpr int PARTS = EW / 4;                             // column parts per lane quarter (2 or 4)
+        const int half = (warp - 2) >> 2;                         // which column part of the N tile this warp owns
         const int row = q * 32 + lane;                            // tile row == TMEM lane
         const int et = (warp - 2) * 32 + lane;                    // 0..255 index among epilogue threads
         constexpr bool T3 = (EPI == EPI_GN_MISH_T3);
-        constexpr int HALF_N = T3 ? 96 : N_TILE / 2;
+        constexpr int HALF_N = T3 ? 96 : N_TILE / PARTS;          // columns per thread
         constexpr int NCHUNK = HALF_N / 32;
         constexpr int HG = (EPI == EPI_GN_MISH) ? HALF_N / CPG : 1;   // groups owned by one thread (generic GN path)
         constexpr int GCOLS = 3 * CPG;                            // T3: accumulator columns of one GroupNorm group
@@ -452,7 +458,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             tc_fence_after();
             const uint32_t taddr = lane_base + (uint32_t)(acc * ACC_STRIDE);
             // accumulator values are read from TMEM once when they fit in registers (<= 64 columns per thread)
-            constexpr bool KEEP = HAS_GN && NCHUNK <= 2;
+            constexpr bool KEEP = HAS_GN && (NCHUNK == 1 || (NCHUNK == 2 && EW == 8));
             float vk[KEEP ? NCHUNK : 1][32];
             float v[32];
             float g_sc[HG], g_sh[HG];                             // per group: rstd and -mean * rstd
@@ -479,7 +485,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 float2* tot = reinterpret_cast<float2*>(part + 2048);               // [43 slices][8 groups]
 #pragma unroll
                 for (int g = 0; g < HG; ++g) pr[row * 8 + half * HG + g] = make_float2(s1[g], s2[g]);
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
                 if (row < p.rows_used) {
                     for (int g = row_in_slice; g < HG; g += p.H) {
                         float a = 0.f, b2 = 0.f;
@@ -489,7 +495,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                     }
                 }
                 if (stage_out && et == 0) tma_store_wait_read();  // staging is free again after this barrier
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
 #pragma unroll
                 for (int g = 0; g < HG; ++g) {
                     const float2 t = tot[sl * 8 + half * HG + g];
@@ -510,7 +516,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                     // the group spans both column halves: exchange partial sums with the partner warp
                     float* ex = part + acc * PART_BUF;
                     *reinterpret_cast<float2*>(ex + (half * 128 + row) * 2) = make_float2(s1, s2);
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
                     const float2 o = *reinterpret_cast<const float2*>(ex + ((half ^ 1) * 128 + row) * 2);
                     s1 += o.x; s2 += o.y;
                 }
@@ -519,7 +525,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 t3_nm = -mean * t3_rstd;
             } else if (stage_out) {
                 if (et == 0) tma_store_wait_read();               // the previous tile's store has finished reading staging
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
             }
             // ---- pass 2 (or the only pass): normalise / activate / add / store ----
 #pragma unroll
@@ -597,7 +603,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             if (lane == 0) { if (CG == 2) mbar_arrive_on_cta(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
             if (stage_out) {
                 fence_proxy_async();                               // generic-proxy smem writes -> visible to the TMA engine
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
                 if (et == 0) {
 #pragma unroll
                     for (int sl64 = 0; sl64 < N_TILE / 64; ++sl64)
@@ -691,7 +697,7 @@ int launch_instance(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensor
     const int slots = num_sms() / CG;                                   // clusters that fit on the machine
     const int grid = (tiles < slots ? tiles : slots) * CG;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads_for(N_TILE, EPI)); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
