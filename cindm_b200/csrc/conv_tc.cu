@@ -35,7 +35,7 @@ constexpr int kATileBytes = 128 * 128;       // 128 rows x 128 B
 // warp 0 TMA, warp 1 MMA, then the epilogue warps: 8 (two per TMEM lane quarter, each owning half of the tile's columns)
 // or 16 (four per lane quarter, a quarter of the columns each) for the 128- and 256-column tiles, whose epilogue is
 // bound by instruction issue with too few warps to hide latency.
-constexpr int epi_warps_for(int n_tile, int epi) { return (epi == EPI_GN_MISH_T3 || n_tile == 64 || n_tile == 192) ? 8 : 16; }
+constexpr int epi_warps_for(int n_tile, int epi) { return 8; }   // 16 (a quarter of the columns per warp) was measured slower: 96-register cap, spills
 constexpr int threads_for(int n_tile, int epi) { return 64 + 32 * epi_warps_for(n_tile, epi); }
 
 struct TcParams {
