@@ -126,7 +126,7 @@ __device__ __forceinline__ void mbar_arrive_on_cta(uint64_t* bar, uint32_t cta) 
         "{\n\t"
         ".reg .b32 remaddr;\n\t"
         "mapa.shared::cluster.u32 remaddr, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remaddr];\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [remaddr];\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t cols) {
@@ -453,6 +453,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 const uint4* rp = reinterpret_cast<const uint4*>(res + chunk_offset(0));
 #pragma unroll
                 for (int j = 0; j < 4; ++j) rv[j] = rp[j];
+            }
+            // ... and pull the NEXT tile's residual rows into L2 now, a whole tile ahead of their use
+            if (res != nullptr) {
+                const int nt_tile = tile + tile_step;
+                if (nt_tile < num_tiles) {
+                    const int nm_pair = nt_tile / p.n_tiles, nn_tile = nt_tile - nm_pair * p.n_tiles;
+                    const long long ns0 = (long long)(nm_pair * CG + (int)cta_rank) * p.slices_per_tile;
+                    const long long ngrow = ns0 * p.H + row;
+                    const bool nvalid = T3 ? (ns0 + row) < p.S : (row < p.rows_used && (ns0 + sl) < p.S);
+                    if (nvalid) {
+#pragma unroll
+                        for (int cc = 0; cc < NCHUNK; cc += 2) {       // 64 channels = one 128-byte line
+                            long long off;
+                            if (T3) {
+                                const int j0 = half * 96 + cc * 32, gl = j0 / GCOLS, rem = j0 - gl * GCOLS, pp = rem / CPG;
+                                off = (ngrow * 3 + pp) * p.cout + chunk_channel(nn_tile, cc);
+                            } else {
+                                off = ngrow * p.cout + chunk_channel(nn_tile, cc);
+                            }
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(res + off));
+                        }
+                    }
+                }
             }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
