@@ -256,7 +256,30 @@ __global__ void __launch_bounds__(256) attn_core_mma_kernel(const T* __restrict_
     const int g = lane >> 2, t = lane & 3;
     constexpr int ROWS = 16 * KS;
     const T zero = from_f32<T>(0.f);
-    for (long long task = (long long)blockIdx.x * 8 + warp; task < tasks; task += (long long)gridDim.x * 8) {
+    // Software pipeline (KS == 1, i.e. n <= 16: seven of the eight attention blocks): the NEXT task's k / v / q rows are
+    // fetched into registers while the current task runs its tensor-core phase, so a warp never sits on DRAM latency.
+    constexpr bool PREFETCH = (KS == 1);
+    T kraw[PREFETCH ? ROWS : 1];
+    uint4 vraw[PREFETCH ? ROWS / 8 : 1], qraw[PREFETCH ? ROWS / 8 : 1];
+    auto fetch = [&](long long tk) {
+        const long long fs = tk >> 2;
+        const T* fb = qkv + fs * (long long)n * 384 + (int)(tk & 3) * 32;
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) kraw[PREFETCH ? j : 0] = j < n ? fb[j * 384 + 128 + lane] : zero;
+#pragma unroll
+        for (int r0 = 0; r0 < ROWS; r0 += 8) {
+            const int j = r0 + (lane >> 2), part = lane & 3;
+            uint4 vv = make_uint4(0, 0, 0, 0), qq = make_uint4(0, 0, 0, 0);
+            if (j < n) {
+                vv = *reinterpret_cast<const uint4*>(fb + j * 384 + 256 + part * 8);
+                qq = *reinterpret_cast<const uint4*>(fb + j * 384 + part * 8);
+            }
+            vraw[PREFETCH ? r0 / 8 : 0] = vv; qraw[PREFETCH ? r0 / 8 : 0] = qq;
+        }
+    };
+    const long long task0 = (long long)blockIdx.x * 8 + warp, task_step = (long long)gridDim.x * 8;
+    if (PREFETCH && task0 < tasks) fetch(task0);
+    for (long long task = task0; task < tasks; task += task_step) {
         const long long s = task >> 2;
         const int h = (int)(task & 3);
         const T* base = qkv + s * (long long)n * 384 + h * 32;
@@ -266,7 +289,8 @@ __global__ void __launch_bounds__(256) attn_core_mma_kernel(const T* __restrict_
             float m = -INFINITY;
 #pragma unroll
             for (int j = 0; j < ROWS; ++j) {
-                kv[j] = j < n ? to_f32<T>(base[j * 384 + 128 + lane]) : -INFINITY;
+                if (PREFETCH) kv[j] = j < n ? to_f32<T>(kraw[PREFETCH ? j : 0]) : -INFINITY;
+                else kv[j] = j < n ? to_f32<T>(base[j * 384 + 128 + lane]) : -INFINITY;
                 m = fmaxf(m, kv[j]);
             }
             float sum = 0.f;
@@ -281,13 +305,15 @@ __global__ void __launch_bounds__(256) attn_core_mma_kernel(const T* __restrict_
         for (int r0 = 0; r0 < ROWS; r0 += 8) {
             const int j = r0 + (lane >> 2), part = lane & 3;
             uint4 vv = make_uint4(0, 0, 0, 0), qq = make_uint4(0, 0, 0, 0);
-            if (j < n) {
+            if (PREFETCH) { vv = vraw[PREFETCH ? r0 / 8 : 0]; qq = qraw[PREFETCH ? r0 / 8 : 0]; }
+            else if (j < n) {
                 vv = *reinterpret_cast<const uint4*>(base + j * 384 + 256 + part * 8);
                 qq = *reinterpret_cast<const uint4*>(base + j * 384 + part * 8);
             }
             *reinterpret_cast<uint4*>(sV + j * kMmaRow + part * 8) = vv;
             *reinterpret_cast<uint4*>(sQ + j * kMmaRow + part * 8) = qq;
         }
+        if (PREFETCH && task + task_step < tasks) fetch(task + task_step);      // in flight during the MMA phase below
         __syncwarp();
         // ---- ctx^T = V^T K_s : M = e (2 tiles of 16), N = d (4 tiles of 8), K = positions
         float ct[2][4][4];
