@@ -80,6 +80,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Same wait, but a failed probe backs off with nanosleep: the single-thread producer / MMA roles and idle epilogue
+// warps then stop competing with the working epilogue warps of their SM sub-partition for issue slots (and power).
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    while (true) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P1;\n\t"
+            "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(40);
+    }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -305,7 +321,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 const int b_row0 = n_tile * N_TILE + (int)cta_rank * (N_TILE / CG);
                 for (int tap = 0; tap < p.taps; ++tap) {
                     for (int kc = 0; kc < p.k_chunks_per_tap; ++kc) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_wait_backoff(&empty_bar[stage], phase ^ 1);
                         uint8_t* a_dst = tiles + stage * kStageBytes;
                         uint8_t* b_dst = a_dst + kATileBytes;
                         if (leader) mbar_expect_tx(&full_bar[stage], tx_bytes);
@@ -345,11 +361,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
-                mbar_wait(&tmem_empty[acc], acc_phase);      // the epilogue has pre-loaded this accumulator with the bias
+                mbar_wait_backoff(&tmem_empty[acc], acc_phase);   // the epilogue has pre-loaded this accumulator with the bias
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
                 for (int kc = 0; kc < k_chunks; ++kc) {
-                    mbar_wait(&full_bar[stage], phase);
+                    mbar_wait_backoff(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(tiles + stage * kStageBytes);
                     const uint32_t b_addr = a_addr + kATileBytes;
@@ -477,7 +493,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                     }
                 }
             }
-            mbar_wait(&tmem_full[acc], acc_phase);
+            mbar_wait_backoff(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = lane_base + (uint32_t)(acc * ACC_STRIDE);
             // accumulator values are read from TMEM once when they fit in registers (<= 64 columns per thread)
