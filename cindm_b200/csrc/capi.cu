@@ -135,7 +135,6 @@ int cindm_destroy(cindm_engine* e) {
     if (e->ws.base) cudaFree(e->ws.base);
     if (e->sched_dev) cudaFree(e->sched_dev);
     if (e->sb.x_alt) cudaFree(e->sb.x_alt);
-    if (e->sb.pred) cudaFree(e->sb.pred);
     if (e->sb.eps) cudaFree(e->sb.eps);
     if (e->sb.t_dev) cudaFree(e->sb.t_dev);
     graph_cache_clear(e);

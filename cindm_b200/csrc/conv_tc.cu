@@ -32,10 +32,9 @@ constexpr int stages_for(int n_tile, int cg) {
 }
 constexpr int kBlockK = 64;                  // 64 x 16-bit = one 128-byte swizzle row
 constexpr int kATileBytes = 128 * 128;       // 128 rows x 128 B
-// warp 0 TMA, warp 1 MMA, then the epilogue warps: 8 (two per TMEM lane quarter, each owning half of the tile's columns)
-// or 16 (four per lane quarter, a quarter of the columns each) for the 128- and 256-column tiles, whose epilogue is
-// bound by instruction issue with too few warps to hide latency.
-constexpr int epi_warps_for(int n_tile, int epi) { return 8; }   // 16 (a quarter of the columns per warp) was measured slower: 96-register cap, spills
+// warp 0 TMA, warp 1 MMA, then the epilogue warps: 4*PARTS of them, PARTS per TMEM lane quarter, each owning 1/PARTS of
+// the tile's columns.  PARTS = 2 everywhere: 4 (16 epilogue warps) was measured slower (96-register cap, spills).
+constexpr int epi_warps_for(int /*n_tile*/, int /*epi*/) { return 8; }
 constexpr int threads_for(int n_tile, int epi) { return 64 + 32 * epi_warps_for(n_tile, epi); }
 
 struct TcParams {
@@ -69,19 +68,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// Same wait, but a failed probe backs off with nanosleep: the single-thread producer / MMA roles and idle epilogue
-// warps then stop competing with the working epilogue warps of their SM sub-partition for issue slots (and power).
+// Phase wait; a failed probe backs off with nanosleep so that the single-thread producer / MMA roles and idle epilogue
+// warps do not compete with the working epilogue warps of their SM sub-partition for issue slots (and power).
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     while (true) {

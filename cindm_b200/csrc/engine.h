@@ -69,7 +69,6 @@ struct SampleBuffers {           // sized by cindm_sample on first use
     cudaGraphExec_t graph_exec = nullptr;
     long long graph_nodes = 0;
     float* x_alt = nullptr;
-    float* pred = nullptr;
     float* eps = nullptr;
     int* t_dev = nullptr;
 };

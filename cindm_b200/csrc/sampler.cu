@@ -263,11 +263,9 @@ static int ensure_sample_buffers(cindm_engine* e, size_t elems) {
     CINDM_CHECK_CUDA(cudaDeviceSynchronize());
     graph_cache_clear(e);
     if (sb.x_alt) cudaFree(sb.x_alt);
-    if (sb.pred) cudaFree(sb.pred);
     if (sb.eps) cudaFree(sb.eps);
-    sb.x_alt = sb.pred = sb.eps = nullptr;
+    sb.x_alt = sb.eps = nullptr;
     CINDM_CHECK_CUDA(cudaMalloc(&sb.x_alt, elems * sizeof(float)));
-    CINDM_CHECK_CUDA(cudaMalloc(&sb.pred, elems * sizeof(float)));
     CINDM_CHECK_CUDA(cudaMalloc(&sb.eps, elems * sizeof(float)));
     sb.elems = elems;
     return 0;
