@@ -1,4 +1,5 @@
 // extern "C" boundary of libcindm_b200.so (declared in include/cindm_b200.h).
+#include <cstdlib>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -121,6 +122,9 @@ int cindm_create(const cindm_config* cfg, cindm_engine** out) {
     if (cfg->timesteps < 1 || cfg->timesteps > 65535) return fail(-2, "timesteps out of range");
     cindm_engine* e = new cindm_engine();
     e->cfg = *cfg;
+    // A/B switches for measurements (both default on)
+    if (const char* v = getenv("CINDM_TOEPLITZ")) e->use_toeplitz = v[0] != '0';
+    if (const char* v = getenv("CINDM_FUSED_ATTN")) e->use_fused_attn = v[0] != '0';
     *out = e;
     return 0;
     API_END

@@ -41,6 +41,10 @@ struct ResBlockW {               // ResidualTemporalBlock, reference model/diffu
 struct AttnW {                   // Residual(PreNorm(LayerNorm, LinearAttentionTemporal)) :272-291
     float* g = nullptr;          // [C]
     ConvW qkv, out;
+    // tcgen05 engine: to_qkv with the LayerNorm gain folded in, K-major [384][C] per 16-bit precision, and the row sums
+    // of that (rounded) operand: qkv = rstd * (W' x - mean * wsum)   (attn_tc.cu)
+    void* wln16[3] = {nullptr, nullptr, nullptr};
+    float* wsum[3] = {nullptr, nullptr, nullptr};
     std::string name;
 };
 
@@ -105,6 +109,7 @@ struct cindm_engine {
     cindm::SampleBuffers sb;
 
     bool use_toeplitz = true;              // H=3 convs as one dense block-Toeplitz GEMM (tcgen05 engine)
+    bool use_fused_attn = true;            // LayerNorm + to_qkv + attention core as one kernel (tcgen05 engine)
     bool taps_enabled = false;
     std::map<std::string, cindm::Tap> taps;
     std::vector<void*> tap_allocs;
@@ -138,6 +143,8 @@ int launch_gn_mish(const float* in, const NormW& gn, const float* add_vec, const
                    void* out, int64_t S, int H, int C, int out_prec, cudaStream_t st);
 int launch_layernorm(const void* in, const float* g, void* out, int64_t rows, int C, int prec, cudaStream_t st);
 int launch_attn_core(const void* qkv, void* out, int64_t S, int n, int prec, cudaStream_t st);
+// LayerNorm + to_qkv + attention core in one tcgen05 kernel: x [S][H][C] -> out [S][H][128] (attn_tc.cu)
+int launch_qkv_attn_tc(const AttnW& a, const void* x, void* out, int64_t S, int H, int C, int prec, cudaStream_t st);
 
 // fused first block (16-bit paths): see kernels_fused.cu
 struct StemLaunch {

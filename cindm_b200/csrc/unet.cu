@@ -142,6 +142,28 @@ struct Uploader {
         a.g = vec(prefix + ".fn.norm.g", c);
         conv(a.qkv, prefix + ".fn.fn.to_qkv", c, 384, 1, false);
         conv(a.out, prefix + ".fn.fn.to_out", 128, c, 1, true);
+        // folded operand of the fused tcgen05 attention kernel: W'[n][ci] = W[n][ci] * g[ci], and its row sums
+        const HostTensor* tg = find(prefix + ".fn.norm.g");
+        const HostTensor* tw = find(prefix + ".fn.fn.to_qkv.weight");
+        if (!tg || !tw || rc) return;
+        std::vector<__half> wh((size_t)384 * c);
+        std::vector<__nv_bfloat16> wb(wh.size());
+        std::vector<float> sh(384), sb(384);
+        for (int n = 0; n < 384; ++n) {
+            float ah = 0.f, ab = 0.f;
+            for (int ci = 0; ci < c; ++ci) {
+                const float v = tw->data[(size_t)n * c + ci] * tg->data[ci];
+                wh[(size_t)n * c + ci] = __float2half_rn(v);
+                wb[(size_t)n * c + ci] = __float2bfloat16_rn(v);
+                ah += __half2float(wh[(size_t)n * c + ci]);
+                ab += __bfloat162float(wb[(size_t)n * c + ci]);
+            }
+            sh[n] = ah; sb[n] = ab;
+        }
+        a.wln16[PREC_F16] = upload(wh.data(), wh.size() * sizeof(__half));
+        a.wln16[PREC_BF16] = upload(wb.data(), wb.size() * sizeof(__nv_bfloat16));
+        a.wsum[PREC_F16] = (float*)upload(sh.data(), sh.size() * sizeof(float));
+        a.wsum[PREC_BF16] = (float*)upload(sb.data(), sb.size() * sizeof(float));
     }
 };
 
@@ -320,6 +342,10 @@ struct Fwd {
 
     // x + to_out(linattn(LayerNorm(x)))
     int attention(const AttnW& a, const void* x, int C, int H, void* out) {
+        if (engine == CINDM_CONV_TCGEN05 && prec != PREC_F32 && e->use_fused_attn) {
+            CINDM_TRY(launch_qkv_attn_tc(a, x, e->ws.att, S, H, C, prec, st));
+            return conv_plain(a.out, e->ws.att, 128, nullptr, 0, prec, H, H, 1, 0, 0, x, out, prec);
+        }
         CINDM_TRY(launch_layernorm(x, a.g, e->ws.ln, S * H, C, prec, st));
         CINDM_TRY(conv_plain(a.qkv, e->ws.ln, C, nullptr, 0, prec, H, H, 1, 0, 0, nullptr, e->ws.qkv, prec));
         CINDM_TRY(launch_attn_core(e->ws.qkv, e->ws.att, S, H, prec, st));
