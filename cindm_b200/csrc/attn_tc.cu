@@ -8,11 +8,12 @@
 // * An M tile is 128/H whole slices.  The CTA that owns it runs the three 128-column passes (q | k | v) of the GEMM
 //   through a double-buffered TMEM accumulator; the epilogue warps normalise and park the 16-bit q|k|v rows in a
 //   shared-memory tile instead of HBM.
-// * After the third pass the same eight warps run the attention core on that tile, one (slice, head) task per warp
+// * After the third pass the same sixteen warps run the attention core on that tile, one (slice, head) task per warp
 //   with mma.sync (softmax over positions of k, ctx = k_s^T v, out = 32^-0.5 q ctx) while the MMA warp is already
 //   working on the next tile's q and k passes.  Only the [S][H][128] attention output goes to HBM; to_out + residual
 //   is the plain 1x1 tcgen05 conv that follows.
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-9 epilogue / attention.
+// Warp roles (576 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-17 epilogue / attention
+// (four warps per TMEM lane quarter, each owning 32 of a pass's 128 columns).
 #include "tc_common.cuh"
 
 namespace cindm {
@@ -22,7 +23,8 @@ namespace {
 constexpr int kAttnStages = 3;
 constexpr int kAttnStageBytes = kATileBytes + 128 * 128;      // A (128 rows) + B (128 weight rows), 64 channels each
 constexpr int kTileRow = 392;                                 // halves per row of the q|k|v tile (784 B: ldmatrix conflict-free)
-constexpr int kKsRow = 40;                                    // halves per row of a warp's softmax(k) scratch
+constexpr int kEpiWarps = 16;
+constexpr int kAttnThreads = 64 + 32 * kEpiWarps;
 
 struct AttnTcParams {
     const void* x;            // [S][H][C] 16-bit block input
@@ -55,16 +57,15 @@ __device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&d)[4], const uin
 }
 
 template <typename T16, int KS>      // KS = 16-position steps of the attention products (1: H <= 16, 2: H <= 32)
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(kAttnThreads, 1)
 qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const AttnTcParams p) {
     constexpr int ROWS = 16 * KS;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* tiles = smem;                                                             // kAttnStages x (A | B)
     T16* qkv = reinterpret_cast<T16*>(smem + kAttnStages * kAttnStageBytes);           // [128][kTileRow]
-    T16* ks_all = qkv + 128 * kTileRow;                                                // [8 warps][ROWS][kKsRow]
-    float* wsum = reinterpret_cast<float*>(ks_all + 8 * ROWS * kKsRow);                // [384]
-    float2* part = reinterpret_cast<float2*>(wsum + 384);                              // [2 halves][128 rows]
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(part + 256);
+    float* wsum = reinterpret_cast<float*>(qkv + 128 * kTileRow);                      // [384]
+    float2* part = reinterpret_cast<float2*>(wsum + 384);                              // [4 channel quarters][128 rows]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(part + 512);
     uint64_t* empty_bar = full_bar + kAttnStages;
     uint64_t* tmem_full = empty_bar + kAttnStages;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -73,7 +74,7 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kAttnStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiWarps); }
         fence_barrier_init();
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
@@ -136,36 +137,44 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
         __syncwarp();
     } else {
-        // =============================== epilogue + attention core (8 warps) ===============================
-        const int ew = warp - 2;                                  // 0..7
+        // =============================== epilogue + attention core (16 warps) ===============================
+        const int ew = warp - 2;                                  // 0..15
         const int q = warp & 3;                                   // TMEM lane quarter this warp may access
-        const int half = ew >> 2;                                 // which 64 of a pass's 128 columns this warp owns
+        const int cp = ew >> 2;                                   // which 32 of a pass's 128 columns (and channel quarter) this warp owns
         const int row = q * 32 + lane;                            // tile row == TMEM lane
         const int n = p.H, C = p.C;
         const T16* xin = reinterpret_cast<const T16*>(p.x);
         T16* out = reinterpret_cast<T16*>(p.out);
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
-        T16* sK = ks_all + ew * (ROWS * kKsRow);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cp * 32);
         const int g = lane >> 2, t4 = lane & 3;
+        // A 16-row fragment step of a task may reach past its slice into the next slice of the tile: those positions are
+        // cleared in the fragments (k index 16*ks + 2*t4 (+1) in the low registers, + 8 in the high ones)
+        uint32_t mlo[KS], mhi[KS];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const int j = 16 * ks + 2 * t4;
+            mlo[ks] = (j < p.H ? 0x0000FFFFu : 0u) | (j + 1 < p.H ? 0xFFFF0000u : 0u);
+            mhi[ks] = (j + 8 < p.H ? 0x0000FFFFu : 0u) | (j + 9 < p.H ? 0xFFFF0000u : 0u);
+        }
         const float inv_c = 1.0f / (float)C;
         int acc = 0; uint32_t acc_phase = 0;
         for (int m_tile = blockIdx.x; m_tile < p.m_tiles; m_tile += gridDim.x) {
             const long long s0 = (long long)m_tile * p.slices_per_tile;
             const bool valid = row < p.rows_used && (s0 + row / n) < p.S;
-            // ---- LayerNorm statistics of this thread's row (half of the channels each; shifted sums, fixed order) ----
+            // ---- LayerNorm statistics of this thread's row (a quarter of the channels each; shifted sums, fixed order) ----
             float mean = 0.f, rstd = 0.f;
             {
                 float s1 = 0.f, s2 = 0.f, x0 = 0.f;
                 if (valid) {
                     const T16* xr = xin + (s0 * n + row) * (long long)C;
                     x0 = (float)xr[0];
-                    const uint4* xp = reinterpret_cast<const uint4*>(xr + half * (C >> 1));
-                    for (int i = 0; i < (C >> 4); i += 4) {
-                        uint4 u[4];
+                    const uint4* xp = reinterpret_cast<const uint4*>(xr + cp * (C >> 2));
+                    for (int i = 0; i < (C >> 5); i += 2) {
+                        uint4 u[2];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) u[j] = xp[i + j];
+                        for (int j = 0; j < 2; ++j) u[j] = xp[i + j];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                        for (int j = 0; j < 2; ++j) {
                             const uint32_t w[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
@@ -177,10 +186,10 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         }
                     }
                 }
-                part[half * 128 + row] = make_float2(s1, s2);
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                const float2 o = part[(half ^ 1) * 128 + row];
-                const float a = half == 0 ? s1 + o.x : o.x + s1, b = half == 0 ? s2 + o.y : o.y + s2;
+                part[cp * 128 + row] = make_float2(s1, s2);
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+                const float2 p0 = part[row], p1 = part[128 + row], p2 = part[256 + row], p3 = part[384 + row];
+                const float a = (p0.x + p1.x) + (p2.x + p3.x), b = (p0.y + p1.y) + (p2.y + p3.y);
                 const float md = a * inv_c;
                 mean = x0 + md;
                 rstd = rsqrtf(fmaxf(b * inv_c - md * md, 0.f) + 1e-5f);
@@ -190,11 +199,10 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             for (int pass = 0; pass < 3; ++pass) {
                 mbar_wait_backoff(&tmem_full[acc], acc_phase);
                 tc_fence_after();
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
+                {
                     float v[32];
-                    tmem_ld32(lane_base + (uint32_t)(acc * 128 + cc * 32), v);
-                    const int col = pass * 128 + half * 64 + cc * 32;
+                    tmem_ld32(lane_base + (uint32_t)(acc * 128), v);
+                    const int col = pass * 128 + cp * 32;
                     const float4* ws4 = reinterpret_cast<const float4*>(wsum + col);
                     uint32_t packed[16];
 #pragma unroll
@@ -217,18 +225,18 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");             // the whole q|k|v tile is in shared memory
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");             // the whole q|k|v tile is in shared memory
             // ---- attention core: one (slice, head) task per warp ----
             const long long left = p.S - s0;
             const int slices_here = left < p.slices_per_tile ? (int)left : p.slices_per_tile;
-            for (int task = ew; task < slices_here * 4; task += 8) {
+            for (int task = ew; task < slices_here * 4; task += kEpiWarps) {
                 const int sl = task >> 2, h = task & 3, r0 = sl * n;
                 const T16* tq = qkv + h * 32;
-                // K: softmax over positions, one channel per lane
+                // K: softmax over positions, one channel per lane, written back in place
                 {
                     float kv[ROWS];
                     float m = -INFINITY;
-                    const T16* tk = tq + 128 + r0 * kTileRow + lane;
+                    T16* tk = qkv + h * 32 + 128 + r0 * kTileRow + lane;
 #pragma unroll
                     for (int j = 0; j < ROWS; ++j) {
                         kv[j] = j < n ? (float)tk[j * kTileRow] : -INFINITY;
@@ -239,11 +247,11 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     for (int j = 0; j < ROWS; ++j) { kv[j] = __expf(kv[j] - m); sum += kv[j]; }      // exp(-inf) = 0 pads rows >= n
                     const float inv = 1.0f / sum;
 #pragma unroll
-                    for (int j = 0; j < ROWS; ++j) sK[j * kKsRow + lane] = (T16)(kv[j] * inv);
+                    for (int j = 0; j < ROWS; ++j) if (j < n) tk[j * kTileRow] = (T16)(kv[j] * inv);
                 }
                 __syncwarp();
-                // ctx^T = V^T K_s : M = e (2 tiles of 16), N = d (4 tiles of 8), K = positions.  V rows beyond the slice belong
-                // to the next slice of the tile (finite) and meet zero rows of K_s; row indices are clamped to the tile.
+                // ctx^T = V^T K_s : M = e (2 tiles of 16), N = d (4 tiles of 8), K = positions.  Rows beyond the slice belong to the
+                // next slice of the tile: masked out of both operands, so no value of another slice can reach this one.
                 float ct[2][4][4];
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt)
@@ -256,14 +264,16 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     uint32_t bk[2][4];
 #pragma unroll
                     for (int np = 0; np < 2; ++np) {
-                        const int r = 16 * ks + (lane & 7) + ((lane >> 3) & 1) * 8, col = 16 * np + (lane >> 4) * 8;
-                        ldsm_x4_trans(smem_u32(sK + r * kKsRow + col), bk[np]);
+                        const int r = min(r0 + 16 * ks + (lane & 7) + ((lane >> 3) & 1) * 8, 127), col = 16 * np + (lane >> 4) * 8;
+                        ldsm_x4_trans(smem_u32(tq + 128 + r * kTileRow + col), bk[np]);
+                        bk[np][0] &= mlo[ks]; bk[np][1] &= mhi[ks]; bk[np][2] &= mlo[ks]; bk[np][3] &= mhi[ks];
                     }
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt) {
                         uint32_t av[4];
                         const int r = min(r0 + 16 * ks + (lane & 7) + (lane >> 4) * 8, 127), col = 16 * mt + ((lane >> 3) & 1) * 8;
                         ldsm_x4_trans(smem_u32(tq + 256 + r * kTileRow + col), av);
+                        av[0] &= mlo[ks]; av[1] &= mlo[ks]; av[2] &= mhi[ks]; av[3] &= mhi[ks];
 #pragma unroll
                         for (int nt = 0; nt < 4; ++nt) mma16816<T16>(ct[mt][nt], av, bk[nt >> 1][(nt & 1) * 2], bk[nt >> 1][(nt & 1) * 2 + 1]);
                     }
@@ -299,9 +309,8 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         if (j1 < n) *reinterpret_cast<uint32_t*>(dst + j1 * 128 + e) = pack2<T16>(oc[ne][2] * scale, oc[ne][3] * scale);
                     }
                 }
-                __syncwarp();                                          // this warp's scratch is rewritten by its next task
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");             // the tile is rewritten by the next M tile's q pass
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");             // the tile is rewritten by the next M tile's q pass
         }
     }
     tc_fence_before();
@@ -314,8 +323,7 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
 template <int KS>
 constexpr size_t attn_smem_bytes() {
-    return (size_t)kAttnStages * kAttnStageBytes + 128 * kTileRow * 2 + 8 * 16 * KS * kKsRow * 2 + 384 * 4 + 256 * 8 +
-           (2 * kAttnStages + 4) * 8 + 16;
+    return (size_t)kAttnStages * kAttnStageBytes + 128 * kTileRow * 2 + 384 * 4 + 512 * 8 + (2 * kAttnStages + 4) * 8 + 16;
 }
 
 template <typename T16, int KS>
@@ -328,7 +336,7 @@ int launch_instance(const CUtensorMap& ma, const CUtensorMap& mb, const AttnTcPa
         configured = true;
     }
     const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
-    kern<<<grid, 320, smem, st>>>(ma, mb, p);
+    kern<<<grid, kAttnThreads, smem, st>>>(ma, mb, p);
     CINDM_CHECK_LAUNCH();
     return 0;
 }
