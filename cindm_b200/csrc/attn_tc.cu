@@ -56,10 +56,11 @@ __device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&d)[4], const uin
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <typename T16, int KS>      // KS = 16-position steps of the attention products (1: H <= 16, 2: H <= 32)
+template <typename T16, int H>       // H = positions per slice at this level (3, 6, 12 or 24)
 __global__ void __launch_bounds__(kAttnThreads, 1)
 qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const AttnTcParams p) {
-    constexpr int ROWS = 16 * KS;
+    constexpr int KS = H <= 16 ? 1 : 2;                           // 16-position steps of the attention products
+    constexpr int n = H;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* tiles = smem;                                                             // kAttnStages x (A | B)
     T16* qkv = reinterpret_cast<T16*>(smem + kAttnStages * kAttnStageBytes);           // [128][kTileRow]
@@ -142,7 +143,7 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int q = warp & 3;                                   // TMEM lane quarter this warp may access
         const int cp = ew >> 2;                                   // which 32 of a pass's 128 columns (and channel quarter) this warp owns
         const int row = q * 32 + lane;                            // tile row == TMEM lane
-        const int n = p.H, C = p.C;
+        const int C = p.C;
         const T16* xin = reinterpret_cast<const T16*>(p.x);
         T16* out = reinterpret_cast<T16*>(p.out);
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cp * 32);
@@ -153,11 +154,25 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
             const int j = 16 * ks + 2 * t4;
-            mlo[ks] = (j < p.H ? 0x0000FFFFu : 0u) | (j + 1 < p.H ? 0xFFFF0000u : 0u);
-            mhi[ks] = (j + 8 < p.H ? 0x0000FFFFu : 0u) | (j + 9 < p.H ? 0xFFFF0000u : 0u);
+            mlo[ks] = (j < H ? 0x0000FFFFu : 0u) | (j + 1 < H ? 0xFFFF0000u : 0u);
+            mhi[ks] = (j + 8 < H ? 0x0000FFFFu : 0u) | (j + 9 < H ? 0xFFFF0000u : 0u);
         }
         const float inv_c = 1.0f / (float)C;
         int acc = 0; uint32_t acc_phase = 0;
+        // The first 32 bytes of this thread's channel quarter of its row (all of it at C = 64) are fetched one tile ahead,
+        // before the attention stage of the previous tile, so the statistics do not start on an exposed global load.
+        uint4 pre[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        T16 pre_x0 = (T16)0.f;
+        auto prefetch_row = [&](int mt) {
+            if (mt >= p.m_tiles) return;
+            const long long ps0 = (long long)mt * p.slices_per_tile;
+            if (row < p.rows_used && (ps0 + row / n) < p.S) {
+                const uint4* xp = reinterpret_cast<const uint4*>(xin + (ps0 * n + row) * (long long)C + cp * (C >> 2));
+                pre[0] = xp[0]; pre[1] = xp[1];
+                pre_x0 = xin[(ps0 * n + row) * (long long)C];
+            }
+        };
+        prefetch_row(blockIdx.x);
         for (int m_tile = blockIdx.x; m_tile < p.m_tiles; m_tile += gridDim.x) {
             const long long s0 = (long long)m_tile * p.slices_per_tile;
             const bool valid = row < p.rows_used && (s0 + row / n) < p.S;
@@ -167,12 +182,12 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 float s1 = 0.f, s2 = 0.f, x0 = 0.f;
                 if (valid) {
                     const T16* xr = xin + (s0 * n + row) * (long long)C;
-                    x0 = (float)xr[0];
+                    x0 = (float)pre_x0;
                     const uint4* xp = reinterpret_cast<const uint4*>(xr + cp * (C >> 2));
                     for (int i = 0; i < (C >> 5); i += 2) {
                         uint4 u[2];
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) u[j] = xp[i + j];
+                        if (i == 0) { u[0] = pre[0]; u[1] = pre[1]; }
+                        else { u[0] = xp[i]; u[1] = xp[i + 1]; }
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
                             const uint32_t w[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
@@ -194,8 +209,9 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 mean = x0 + md;
                 rstd = rsqrtf(fmaxf(b * inv_c - md * md, 0.f) + 1e-5f);
             }
-            const float sc = valid ? rstd : 0.f, nm = valid ? -mean * rstd : 0.f;
-            // ---- q | k | v passes: TMEM -> normalise -> 16-bit rows of the shared-memory tile ----
+            const float sc = rstd, nm = -mean * rstd;
+            // ---- q | k | v passes: TMEM -> normalise -> 16-bit rows of the shared-memory tile.  Rows beyond the tile's slices
+            //      carry stale operands; nothing reads them unmasked (see the fragment masks above) ----
             for (int pass = 0; pass < 3; ++pass) {
                 mbar_wait_backoff(&tmem_full[acc], acc_phase);
                 tc_fence_after();
@@ -208,11 +224,8 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
                         const float4 w4 = ws4[i >> 2];
-                        // rows beyond the tile's slices hold stale operands: force exact zeros (0 * finite; NaN-safe select)
-                        const float y0 = valid ? fmaf(v[i], sc, nm * w4.x) : 0.f;
-                        const float y1 = valid ? fmaf(v[i + 1], sc, nm * w4.y) : 0.f;
-                        const float y2 = valid ? fmaf(v[i + 2], sc, nm * w4.z) : 0.f;
-                        const float y3 = valid ? fmaf(v[i + 3], sc, nm * w4.w) : 0.f;
+                        const float y0 = fmaf(v[i], sc, nm * w4.x), y1 = fmaf(v[i + 1], sc, nm * w4.y);
+                        const float y2 = fmaf(v[i + 2], sc, nm * w4.z), y3 = fmaf(v[i + 3], sc, nm * w4.w);
                         packed[i >> 1] = pack2<T16>(y0, y1);
                         packed[(i >> 1) + 1] = pack2<T16>(y2, y3);
                     }
@@ -225,6 +238,7 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+            prefetch_row(m_tile + gridDim.x);
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");             // the whole q|k|v tile is in shared memory
             // ---- attention core: one (slice, head) task per warp ----
             const long long left = p.S - s0;
@@ -234,20 +248,20 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const T16* tq = qkv + h * 32;
                 // K: softmax over positions, one channel per lane, written back in place
                 {
-                    float kv[ROWS];
+                    float kv[H];
                     float m = -INFINITY;
                     T16* tk = qkv + h * 32 + 128 + r0 * kTileRow + lane;
 #pragma unroll
-                    for (int j = 0; j < ROWS; ++j) {
-                        kv[j] = j < n ? (float)tk[j * kTileRow] : -INFINITY;
+                    for (int j = 0; j < H; ++j) {
+                        kv[j] = (float)tk[j * kTileRow];
                         m = fmaxf(m, kv[j]);
                     }
                     float sum = 0.f;
 #pragma unroll
-                    for (int j = 0; j < ROWS; ++j) { kv[j] = __expf(kv[j] - m); sum += kv[j]; }      // exp(-inf) = 0 pads rows >= n
+                    for (int j = 0; j < H; ++j) { kv[j] = __expf(kv[j] - m); sum += kv[j]; }
                     const float inv = 1.0f / sum;
 #pragma unroll
-                    for (int j = 0; j < ROWS; ++j) if (j < n) tk[j * kTileRow] = (T16)(kv[j] * inv);
+                    for (int j = 0; j < H; ++j) tk[j * kTileRow] = (T16)(kv[j] * inv);
                 }
                 __syncwarp();
                 // ctx^T = V^T K_s : M = e (2 tiles of 16), N = d (4 tiles of 8), K = positions.  Rows beyond the slice belong to the
@@ -321,15 +335,14 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
 }
 
-template <int KS>
 constexpr size_t attn_smem_bytes() {
     return (size_t)kAttnStages * kAttnStageBytes + 128 * kTileRow * 2 + 384 * 4 + 512 * 8 + (2 * kAttnStages + 4) * 8 + 16;
 }
 
-template <typename T16, int KS>
+template <typename T16, int H>
 int launch_instance(const CUtensorMap& ma, const CUtensorMap& mb, const AttnTcParams& p, cudaStream_t st) {
-    auto kern = qkv_attn_kernel<T16, KS>;
-    constexpr size_t smem = attn_smem_bytes<KS>();
+    auto kern = qkv_attn_kernel<T16, H>;
+    constexpr size_t smem = attn_smem_bytes();
     static bool configured = false;
     if (!configured) {
         CINDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -345,12 +358,14 @@ int launch_instance(const CUtensorMap& ma, const CUtensorMap& mb, const AttnTcPa
 
 int launch_qkv_attn_tc(const AttnW& a, const void* x, void* out, int64_t S, int H, int C, int prec, cudaStream_t st) {
     if (prec != PREC_F16 && prec != PREC_BF16) return fail(-2, "attn_tc: 16-bit precisions only");
-    if (C % 64 || C > 512 || H < 1 || H > 32) return fail(-2, "attn_tc: unsupported block shape");
+    if (C % 64 || C > 512 || (H != 3 && H != 6 && H != 12 && H != 24)) return fail(-2, "attn_tc: unsupported block shape");
     if (!a.wln16[prec] || !a.wsum[prec]) return fail(-4, "attn_tc: folded LayerNorm operand missing");
     if (S == 0) return 0;
     AttnTcParams p;
     p.x = x; p.wsum = a.wsum[prec]; p.out = out; p.S = S; p.H = H; p.C = C;
-    p.slices_per_tile = 128 / H;
+    // whole slices per 128-row tile; at H <= 6 a multiple of 4, so that the (slice, head) tasks split evenly over the
+    // 16 warps (at H = 12 / 24 the extra tiles that would take cost more than the last, partly filled round of tasks)
+    p.slices_per_tile = H <= 6 ? (128 / H) / 4 * 4 : 128 / H;
     p.rows_used = p.slices_per_tile * H;
     p.m_tiles = (int)((S + p.slices_per_tile - 1) / p.slices_per_tile);
     p.k_chunks = C / kBlockK;
@@ -360,8 +375,16 @@ int launch_qkv_attn_tc(const AttnW& a, const void* x, void* out, int64_t S, int 
     CUtensorMap ma, mb;
     CINDM_TRY(encode_act_map(&ma, x, prec, S, H, C, p.slices_per_tile, H, 1));
     CINDM_TRY(encode_weight_map(&mb, a.wln16[prec], prec, 384, C, 128));
-    if (prec == PREC_F16) return H <= 16 ? launch_instance<__half, 1>(ma, mb, p, st) : launch_instance<__half, 2>(ma, mb, p, st);
-    return H <= 16 ? launch_instance<__nv_bfloat16, 1>(ma, mb, p, st) : launch_instance<__nv_bfloat16, 2>(ma, mb, p, st);
+    switch (H * 2 + (prec == PREC_F16 ? 0 : 1)) {
+        case 6: return launch_instance<__half, 3>(ma, mb, p, st);
+        case 7: return launch_instance<__nv_bfloat16, 3>(ma, mb, p, st);
+        case 12: return launch_instance<__half, 6>(ma, mb, p, st);
+        case 13: return launch_instance<__nv_bfloat16, 6>(ma, mb, p, st);
+        case 24: return launch_instance<__half, 12>(ma, mb, p, st);
+        case 25: return launch_instance<__nv_bfloat16, 12>(ma, mb, p, st);
+        case 48: return launch_instance<__half, 24>(ma, mb, p, st);
+        default: return launch_instance<__nv_bfloat16, 24>(ma, mb, p, st);
+    }
 }
 
 }  // namespace cindm

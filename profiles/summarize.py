@@ -14,6 +14,8 @@ def launches(path):
     rows = list(csv.DictReader(l for l in open(path) if not l.startswith("==")))
     agg = collections.OrderedDict()
     for r in rows:
+        if r.get("Metric Name", "gpu__time_duration.sum") != "gpu__time_duration.sum":
+            continue
         name = re.sub(r"<.*", "", r["Kernel Name"]).replace("void ", "").replace("unnamed>::", "")
         try:
             v = float(r["Metric Value"].replace(",", ""))
