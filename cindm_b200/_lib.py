@@ -64,6 +64,8 @@ _SIGNATURES = {
     "cindm_posterior_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                        c_int, c_int, c_int, c_int, POINTER(Objective), c_void_p]),
     "cindm_sample": (c_int, [c_void_p, POINTER(SampleConfig), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cindm_sample_ddim": (c_int, [c_void_p, POINTER(SampleConfig), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p]),
     "cindm_fill_initial_noise": (c_int, [c_void_p, c_int, c_int, c_int, c_uint64, c_int64, c_int, c_void_p]),
     "cindm_nbody_rollout": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "cindm_score_designs": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double, c_void_p]),

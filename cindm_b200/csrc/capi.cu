@@ -141,6 +141,9 @@ int cindm_destroy(cindm_engine* e) {
     if (e->sb.x_alt) cudaFree(e->sb.x_alt);
     if (e->sb.eps) cudaFree(e->sb.eps);
     if (e->sb.t_dev) cudaFree(e->sb.t_dev);
+    if (e->sb.step_dev) cudaFree(e->sb.step_dev);
+    if (e->sb.ddim_times) cudaFree(e->sb.ddim_times);
+    if (e->sb.ddim_coef) cudaFree(e->sb.ddim_coef);
     graph_cache_clear(e);
     if (e->sb.capture_stream) cudaStreamDestroy(e->sb.capture_stream);
     if (e->sb.ev_in) cudaEventDestroy(e->sb.ev_in);
@@ -356,6 +359,15 @@ int cindm_sample(cindm_engine* e, const cindm_sample_config* cfg, float* x, cons
     API_BEGIN
     if (!e || !cfg || !x) return fail(-2, "null argument");
     return sample_loop(e, *cfg, x, noise, x0_out, (cudaStream_t)stream);
+    API_END
+}
+
+int cindm_sample_ddim(cindm_engine* e, const cindm_sample_config* cfg, int n_pairs, const int32_t* times,
+                      const int32_t* times_next, const float* coef, float* x, const float* noise, float* x0_out,
+                      void* stream) {
+    API_BEGIN
+    if (!e || !cfg || !x) return fail(-2, "null argument");
+    return sample_ddim(e, *cfg, n_pairs, times, times_next, coef, x, noise, x0_out, (cudaStream_t)stream);
     API_END
 }
 

@@ -75,6 +75,11 @@ struct SampleBuffers {           // sized by cindm_sample on first use
     float* x_alt = nullptr;
     float* eps = nullptr;
     int* t_dev = nullptr;
+    // DDIM: per-step table {time} / {sqrt(alpha_next), c, sigma, last-step flag} and the device-resident step index
+    int* ddim_times = nullptr;
+    float* ddim_coef = nullptr;
+    int* step_dev = nullptr;
+    int ddim_capacity = 0;
 };
 
 struct Tap {
@@ -181,11 +186,17 @@ struct UpdateLaunch {
     const float* noise = nullptr; int t_start = 0, draws_per_step = 0, draw = 0;
     int use_philox = 0; uint64_t seed = 0; int64_t cand_off = 0;
     cindm_objective obj;
+    // DDIM outer update (reference ddim_sample :1781-1797) instead of the posterior sample: out = x0 * coef[0] +
+    // coef[1] * (eps + g) + coef[2] * noise, or x0 on the last step (coef[3] != 0); row = *step_dev of ddim_coef,
+    // which also replaces (t_start - t) as the row of the explicit noise tensor
+    int ddim = 0; const float* ddim_coef = nullptr; const int* step_dev = nullptr;
 };
 int launch_update(const UpdateLaunch& u, cudaStream_t st);
 int launch_fill_noise(float* x, int B, int T, int n, uint64_t seed, int64_t cand_off, int t, int draw,
                       cudaStream_t st);
 int launch_step_counter(int* t_dev, int delta, cudaStream_t st);
+int sample_ddim(cindm_engine* e, const cindm_sample_config& c, int n_pairs, const int32_t* times, const int32_t* times_next,
+                const float* coef3, float* x, const float* noise, float* x0_out, cudaStream_t caller);
 
 void graph_cache_clear(cindm_engine* e);
 int finalize_weights(cindm_engine* e, cudaStream_t st);

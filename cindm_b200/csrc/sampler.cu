@@ -68,6 +68,7 @@ int launch_fill_noise(float* x, int B, int T, int n, uint64_t seed, int64_t cand
 }
 
 __global__ void step_counter_kernel(int* t, int delta) { *t += delta; }
+__global__ void ddim_set_time_kernel(int* t, const int* times, const int* step) { *t = times[*step]; }
 int launch_step_counter(int* t_dev, int delta, cudaStream_t st) {
     step_counter_kernel<<<1, 1, 0, st>>>(t_dev, delta);
     CINDM_CHECK_LAUNCH();
@@ -143,6 +144,7 @@ struct UpdateParams {
     long long cand_off; unsigned long long seed;
     int B, T, n, timesteps, t_host, renoise, t_start, draws_per_step, draw, use_philox;
     cindm_objective obj;
+    int ddim; const float* ddim_coef; const int* step_dev;
 };
 
 __global__ void __launch_bounds__(256) ddpm_update_kernel(UpdateParams p) {
@@ -157,8 +159,17 @@ __global__ void __launch_bounds__(256) ddpm_update_kernel(UpdateParams p) {
     if (p.obj.guidance == CINDM_GUIDE_STANDARD) gscale = 1.f;
     else if (p.obj.guidance == CINDM_GUIDE_STANDARD_ALPHA)
         gscale = __fdiv_rn(p.sched[TAB_BETAS * TS + t], __fsqrt_rn(p.sched[TAB_ACP_PREV * TS + t]));
+    const int step = p.step_dev ? *p.step_dev : p.t_start - t;      // sampling step index (row of the explicit noise tensor)
     float na, nb;   // out = na * pred + nb * noise
-    if (p.renoise) {
+    float d_san = 0.f, d_c = 0.f;
+    bool d_last = false;
+    if (p.ddim) {
+        const float* cf = p.ddim_coef + 4 * step;
+        d_san = cf[0]; d_c = cf[1];
+        d_last = cf[3] != 0.f;
+        na = 1.0f;
+        nb = d_last ? 0.f : cf[2];                                      // sigma (0 when eta == 0; NaN on the last pair, unused there)
+    } else if (p.renoise) {
         float ratio = __fdiv_rn(p.sched[TAB_ACP * TS + t], p.sched[TAB_ACP_PREV * TS + t]);   // fp32 ratio (:1366)
         na = __fsqrt_rn(ratio);
         nb = __fsqrt_rn(__fsub_rn(1.0f, ratio));
@@ -170,7 +181,7 @@ __global__ void __launch_bounds__(256) ddpm_update_kernel(UpdateParams p) {
     const float4* noise = nullptr;
     if (p.noise)
         noise = reinterpret_cast<const float4*>(
-            p.noise + ((long long)(p.t_start - t) * p.draws_per_step + p.draw) * ((long long)p.B * p.T * p.n * 4));
+            p.noise + ((long long)step * p.draws_per_step + p.draw) * ((long long)p.B * p.T * p.n * 4));
 
     const long long total = (long long)p.B * p.T * p.n;
     const int F = 4 * p.n;
@@ -200,7 +211,15 @@ __global__ void __launch_bounds__(256) ddpm_update_kernel(UpdateParams p) {
             x0[q] = v;
             float mu = __fadd_rn(__fmul_rn(c1, v), __fmul_rn(c2, xs[q]));                   // (:943-946)
             pr[q] = __fsub_rn(mu, g[q]);                                                    // (:1349)
-            out[q] = have_noise ? __fadd_rn(__fmul_rn(na, pr[q]), __fmul_rn(nb, ns[q])) : __fmul_rn(na, pr[q]);
+            if (p.ddim) {
+                // pred_noise + grad_design_final (:1375), then img = x_start * sqrt(alpha_next) + c * pred_noise + sigma * noise (:1786-1788)
+                const float pn = __fadd_rn(es[q], g[q]);
+                float o = __fadd_rn(__fmul_rn(v, d_san), __fmul_rn(d_c, pn));
+                if (have_noise) o = __fadd_rn(o, __fmul_rn(nb, ns[q]));
+                out[q] = d_last ? v : o;                                                    // time_next < 0: img = x_start (:1789-1793)
+            } else {
+                out[q] = have_noise ? __fadd_rn(__fmul_rn(na, pr[q]), __fmul_rn(nb, ns[q])) : __fmul_rn(na, pr[q]);
+            }
         }
         reinterpret_cast<float4*>(p.x_out)[i] = make_float4(out[0], out[1], out[2], out[3]);
         if (p.pred_out) reinterpret_cast<float4*>(p.pred_out)[i] = make_float4(pr[0], pr[1], pr[2], pr[3]);
@@ -217,6 +236,8 @@ int launch_update(const UpdateLaunch& u, cudaStream_t st) {
     p.B = u.B; p.T = u.T; p.n = u.n; p.timesteps = u.timesteps; p.t_host = u.t_host; p.renoise = u.renoise;
     p.t_start = u.t_start; p.draws_per_step = u.draws_per_step; p.draw = u.draw; p.use_philox = u.use_philox;
     p.obj = u.obj;
+    p.ddim = u.ddim; p.ddim_coef = u.ddim_coef; p.step_dev = u.step_dev;
+    if (u.ddim && (!u.ddim_coef || !u.step_dev)) return fail(-2, "DDIM update needs the coefficient table and the step counter");
     long long total = (long long)u.B * u.T * u.n;
     if (total == 0) return 0;
     KernelTimer kt("ddpm_update", st, (double)total * 16.0 * (u.noise ? 4.0 : 3.0));
@@ -271,12 +292,20 @@ static int ensure_sample_buffers(cindm_engine* e, size_t elems) {
     return 0;
 }
 
-// Issue the kernels of ONE DDPM step.  x lives in bufs[cur]; returns (through cur) where the result is.
+// Issue the kernels of ONE sampling step.  x lives in bufs[cur]; returns (through cur) where the result is.
+// ddim: the step is one (time, time_next) pair of ddim_sample (:1751-1797): the timestep comes from the device table
+// indexed by the device step counter, the recurrence runs as in the DDPM step, and the last evaluation feeds the DDIM
+// update.  Random draws per step, in the reference's order: R re-noise draws, the (unused) posterior noise, the DDIM noise.
 static int issue_step(cindm_engine* e, const cindm_sample_config& c, float* bufs[2], int& cur, const float* noise,
-                      float* x0_out, int t, const int* t_dev, cudaStream_t st) {
+                      float* x0_out, int t, const int* t_dev, cudaStream_t st, bool ddim = false) {
     const int T = e->cfg.horizon + c.n_composed * c.compose_start_step;
-    const int iters = c.recurrence > 0 ? c.recurrence : 1;
-    const int draws = c.recurrence > 0 ? c.recurrence + 1 : 1;
+    const bool guided = c.objective.guidance != CINDM_GUIDE_NONE;
+    const int iters = ddim ? (guided ? c.recurrence : 1) : (c.recurrence > 0 ? c.recurrence : 1);
+    const int draws = ddim ? (guided ? c.recurrence + 2 : 1) : (c.recurrence > 0 ? c.recurrence + 1 : 1);
+    if (ddim) {
+        ddim_set_time_kernel<<<1, 1, 0, st>>>(e->sb.t_dev, e->sb.ddim_times, e->sb.step_dev);
+        CINDM_CHECK_LAUNCH();
+    }
     for (int r = 0; r < iters; ++r) {
         CINDM_TRY(composed_eps(e, bufs[cur], e->sb.eps, c.batch, c.n_bodies, c.n_composed, c.compose_start_step,
                                c.compose_mode, t, t_dev, c.precision, c.conv_engine, st));
@@ -293,9 +322,15 @@ static int issue_step(cindm_engine* e, const cindm_sample_config& c, float* bufs
         // the last evaluation goes straight to the final posterior noise (draw id R)
         u.renoise = (c.recurrence > 0 && !last) ? 1 : 0;
         u.draw = (c.recurrence > 0 && last) ? c.recurrence : r;
+        if (ddim) {
+            u.step_dev = e->sb.step_dev;
+            if (last) { u.ddim = 1; u.ddim_coef = e->sb.ddim_coef; u.renoise = 0; u.draw = guided ? c.recurrence + 1 : 0; }
+            else { u.renoise = 1; u.draw = r; }
+        }
         CINDM_TRY(launch_update(u, st));
         cur ^= 1;
     }
+    if (ddim) CINDM_TRY(launch_step_counter(e->sb.step_dev, 1, st));
     return 0;
 }
 
@@ -386,6 +421,110 @@ static int sample_loop_on(cindm_engine* e, const cindm_sample_config& c, float* 
     }
     if (cur != 0) CINDM_CHECK_CUDA(cudaMemcpyAsync(x, e->sb.x_alt, elems * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return 0;
+}
+
+// ---------------------------------------------------------------- DDIM loop (sampling_timesteps < timesteps)
+static int sample_ddim_on(cindm_engine* e, const cindm_sample_config& c, int n_pairs, const int32_t* times,
+                          const int32_t* times_next, const float* coef3, float* x, const float* noise, float* x0_out,
+                          cudaStream_t st) {
+    if (!e->finalized) return fail(-4, "weights not finalized");
+    if (!e->sched_dev) return fail(-4, "schedule tables not set (cindm_set_schedule)");
+    if (n_pairs <= 0 || !times || !times_next || !coef3) return fail(-2, "DDIM needs the (time, time_next) pairs and their coefficients");
+    if (c.compose_start_step >= e->cfg.horizon) return fail(-2, "compose_start_step must be < horizon");
+    if (c.batch <= 0) return fail(-2, "batch must be positive");
+    const bool guided = c.objective.guidance != CINDM_GUIDE_NONE;
+    // only the recurrence branch of p_sample_compose_inside returns (pred_noise + grad, x_start) (:1372-1376); the
+    // single-pass "standard" branch hands ddim_sample the posterior sample in place of epsilon (:1283)
+    if (guided && c.recurrence <= 0)
+        return fail(-5, "DDIM sampling with guidance needs a '-recurrence-K' design_guidance (reference :1283 vs :1372-1376)");
+    for (int i = 0; i < n_pairs; ++i)
+        if (times[i] < 0 || times[i] >= e->cfg.timesteps) return fail(-2, "DDIM timestep out of range");
+    const int T = e->cfg.horizon + c.n_composed * c.compose_start_step;
+    const size_t elems = (size_t)c.batch * T * c.n_bodies * 4;
+    const int64_t S = (int64_t)(c.n_composed + 1) * (c.n_bodies * (c.n_bodies - 1) / 2) * c.batch;
+    CINDM_TRY(reserve_workspace(e, S > e->ws.max_slices ? S : e->ws.max_slices, c.precision));
+    CINDM_TRY(ensure_sample_buffers(e, elems));
+    SampleBuffers& sb = e->sb;
+    if (!sb.step_dev) CINDM_CHECK_CUDA(cudaMalloc(&sb.step_dev, sizeof(int)));
+    if (sb.ddim_capacity < n_pairs) {
+        CINDM_CHECK_CUDA(cudaStreamSynchronize(st));
+        graph_cache_clear(e);
+        if (sb.ddim_times) cudaFree(sb.ddim_times);
+        if (sb.ddim_coef) cudaFree(sb.ddim_coef);
+        sb.ddim_times = nullptr; sb.ddim_coef = nullptr; sb.ddim_capacity = 0;
+        CINDM_CHECK_CUDA(cudaMalloc(&sb.ddim_times, (size_t)n_pairs * sizeof(int)));
+        CINDM_CHECK_CUDA(cudaMalloc(&sb.ddim_coef, (size_t)n_pairs * 4 * sizeof(float)));
+        sb.ddim_capacity = n_pairs;
+    }
+    std::vector<float> coef4((size_t)n_pairs * 4);
+    for (int i = 0; i < n_pairs; ++i) {
+        coef4[4 * i] = coef3[3 * i]; coef4[4 * i + 1] = coef3[3 * i + 1]; coef4[4 * i + 2] = coef3[3 * i + 2];
+        coef4[4 * i + 3] = times_next[i] < 0 ? 1.f : 0.f;
+    }
+    const int zero = 0;
+    // pageable sources: these copies return once the host buffers have been staged
+    CINDM_CHECK_CUDA(cudaMemcpyAsync(sb.ddim_times, times, (size_t)n_pairs * sizeof(int), cudaMemcpyHostToDevice, st));
+    CINDM_CHECK_CUDA(cudaMemcpyAsync(sb.ddim_coef, coef4.data(), coef4.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    CINDM_CHECK_CUDA(cudaMemcpyAsync(sb.step_dev, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+    CINDM_CHECK_CUDA(cudaStreamSynchronize(st));
+
+    float* bufs[2] = {x, sb.x_alt};
+    int cur = 0;
+    const int iters = guided ? c.recurrence : 1;
+    if (!c.use_graph) {
+        for (int i = 0; i < n_pairs; ++i) CINDM_TRY(issue_step(e, c, bufs, cur, noise, x0_out, 0, sb.t_dev, st, true));
+    } else {
+        const int steps_per_graph = (iters % 2) ? 2 : 1;
+        cindm_sample_config kc = c;
+        kc.t_start = -1; kc.t_end = -1;                              // marks a DDIM graph; the pairs live in device tables
+        std::string key(reinterpret_cast<const char*>(&kc), sizeof(kc));
+        const void* ptrs[4] = {x, noise, x0_out, (const void*)st};
+        key.append(reinterpret_cast<const char*>(ptrs), sizeof(ptrs));
+        if (!sb.graph_exec || sb.graph_key != key) {
+            graph_cache_clear(e);
+            cudaGraph_t graph = nullptr;
+            CINDM_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const long long before = launch_count();
+            int rc = 0, gcur = 0;
+            for (int k = 0; k < steps_per_graph && rc == 0; ++k) rc = issue_step(e, c, bufs, gcur, noise, x0_out, 0, sb.t_dev, st, true);
+            const long long nodes = launch_count() - before;
+            add_launches(-nodes);
+            cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) return fail(-100, std::string("graph capture: ") + cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&sb.graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) { sb.graph_exec = nullptr; return fail(-100, std::string("graph instantiate: ") + cudaGetErrorString(ce)); }
+            sb.graph_key = key;
+            sb.graph_nodes = nodes;
+        }
+        int done = 0;
+        for (; done + steps_per_graph <= n_pairs; done += steps_per_graph) {
+            CINDM_CHECK_CUDA(cudaGraphLaunch(sb.graph_exec, st));
+            add_launches(sb.graph_nodes);
+        }
+        for (; done < n_pairs; ++done) CINDM_TRY(issue_step(e, c, bufs, cur, noise, x0_out, 0, sb.t_dev, st, true));
+    }
+    if (cur != 0) CINDM_CHECK_CUDA(cudaMemcpyAsync(x, sb.x_alt, elems * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int sample_ddim(cindm_engine* e, const cindm_sample_config& c, int n_pairs, const int32_t* times, const int32_t* times_next,
+                const float* coef3, float* x, const float* noise, float* x0_out, cudaStream_t caller) {
+    const bool special = caller == nullptr || caller == cudaStreamLegacy || caller == cudaStreamPerThread;
+    if (!c.use_graph || !special) return sample_ddim_on(e, c, n_pairs, times, times_next, coef3, x, noise, x0_out, caller);
+    SampleBuffers& sb = e->sb;
+    if (!sb.capture_stream) {
+        CINDM_CHECK_CUDA(cudaStreamCreateWithFlags(&sb.capture_stream, cudaStreamNonBlocking));
+        CINDM_CHECK_CUDA(cudaEventCreateWithFlags(&sb.ev_in, cudaEventDisableTiming));
+        CINDM_CHECK_CUDA(cudaEventCreateWithFlags(&sb.ev_out, cudaEventDisableTiming));
+    }
+    CINDM_CHECK_CUDA(cudaEventRecord(sb.ev_in, caller));
+    CINDM_CHECK_CUDA(cudaStreamWaitEvent(sb.capture_stream, sb.ev_in, 0));
+    int rc = sample_ddim_on(e, c, n_pairs, times, times_next, coef3, x, noise, x0_out, sb.capture_stream);
+    CINDM_CHECK_CUDA(cudaEventRecord(sb.ev_out, sb.capture_stream));
+    CINDM_CHECK_CUDA(cudaStreamWaitEvent(caller, sb.ev_out, 0));
+    return rc;
 }
 
 }  // namespace cindm

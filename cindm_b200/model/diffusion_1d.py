@@ -8,7 +8,7 @@ include/cindm_b200.h (hand-written sm_100a CUDA).  PyTorch only owns device memo
 
 Fast-path subset (anything else raises NotImplementedError — there is no silent fallback):
 objective 'pred_noise', conditioned_steps 0, cond None, compose_mode in {mean-inside, sum-inside},
-design_guidance in {standard, standard-alpha}[-recurrence-K], sampling_timesteps == timesteps,
+design_guidance in {standard, standard-alpha}[-recurrence-K], DDPM (sampling_timesteps == timesteps) or DDIM,
 horizon 24, dim 64, attention=True.
 """
 import ctypes
@@ -465,11 +465,82 @@ class GaussianDiffusion1D:
         self.last_x_start = x0
         return img
 
+    def ddim_schedule(self, pairs=None):
+        """The (time, time_next) pairs of ddim_sample (reference :1741-1743) and, per pair, the fp32 coefficients
+        [sqrt(alpha_next), c, sigma] formed with the same tensor expressions as :1778-1782 (so the last pair, whose
+        time_next = -1 indexes alphas_cumprod[-1], carries the same NaNs the reference computes and then discards).
+        `pairs` overrides the reference's linspace grid (parity tests step through chosen timesteps)."""
+        if pairs is None:
+            times = torch.linspace(-1, self.num_timesteps - 1, steps=self.sampling_timesteps + 1)
+            times = list(reversed(times.int().tolist()))
+            pairs = list(zip(times[:-1], times[1:]))
+        acp = self.alphas_cumprod.detach().to("cpu", torch.float32)
+        eta = self.ddim_sampling_eta
+        coef = torch.empty((len(pairs), 3), dtype=torch.float32)
+        for i, (time, time_next) in enumerate(pairs):
+            alpha = acp[time]
+            alpha_next = acp[time_next]
+            sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+            c = (1 - alpha_next - sigma ** 2).sqrt()
+            coef[i, 0] = alpha_next.sqrt()
+            coef[i, 1] = c
+            coef[i, 2] = sigma
+        return pairs, coef
+
+    def ddim_sample(self, shape, cond, n_composed=None, clip_denoised=True, compose_start_step=4, compose_n_bodies=2,
+                    compose_mode="mean", design_fn=None, design_guidance="standard", initial_state_overwrite=None,
+                    initialization_mode=0, initialization_img=None, noise=None, img=None, pairs=None):
+        """DDIM sampling (reference :1723-1804).  The reference draws img = randn(shape) with shape = (B, image_size,
+        channels), so at HEAD it only runs for n_composed = 0, compose_n_bodies = 2; here the same loop runs on the
+        composed shape [B, image_size + n_composed * compose_start_step, 4 * compose_n_bodies] and is identical on the
+        reference's subset.  Like the reference it ignores initialization_mode / initialization_img.  `img` / `noise`
+        (optional) replace the Philox draws for parity runs: noise is [pairs, draws, B, T, F] with draws = R + 2
+        (R re-noise draws, the unused posterior draw, the DDIM draw) with guidance, 1 without."""
+        if cond is not None or initial_state_overwrite is not None or not clip_denoised:
+            raise NotImplementedError("cond / initial_state_overwrite / clip_denoised=False are not on the CUDA fast path")
+        n_composed = 0 if n_composed is None else n_composed
+        if "inside" not in compose_mode:
+            if design_fn is None and n_composed == 0 and compose_n_bodies == 2:
+                compose_mode = "mean-inside"      # model_predictions without composition == the 1-window, 1-pair operator
+            else:
+                raise NotImplementedError(f"compose_mode {compose_mode!r}: only the *-inside operators are on the CUDA fast path")
+        eng = self.model.engine()
+        b = shape[0]
+        t_total = shape[1] + n_composed * compose_start_step
+        f = compose_n_bodies * 4
+        pairs, coef = self.ddim_schedule(pairs)
+        times = torch.tensor([p[0] for p in pairs], dtype=torch.int32)
+        times_next = torch.tensor([p[1] for p in pairs], dtype=torch.int32)
+        L = _lib.lib()
+        with torch.cuda.device(self.device):
+            if img is None:
+                x = torch.empty((b, t_total, f), device=self.device, dtype=torch.float32)
+                _lib.check(L.cindm_fill_initial_noise(_lib.ptr(x), b, t_total, compose_n_bodies, self.seed,
+                                                      self.candidate_offset, self.num_timesteps, _lib.stream_ptr(self.device)))
+            else:
+                x = img.to(self.device, torch.float32).reshape(b, t_total, f).contiguous().clone()
+            cfg = self._sample_config(b, n_composed, compose_start_step, compose_n_bodies, compose_mode, design_fn,
+                                      design_guidance, 0, 0, self.use_cuda_graph)
+            if noise is not None:
+                draws = cfg.recurrence + 2 if design_fn is not None else 1
+                noise = noise.to(self.device, torch.float32).contiguous()
+                assert tuple(noise.shape) == (len(pairs), draws, b, t_total, f)
+            x0 = torch.empty_like(x)
+            _lib.check(L.cindm_sample_ddim(eng.handle, ctypes.byref(cfg), len(pairs), times.data_ptr(), times_next.data_ptr(),
+                                           coef.data_ptr(), _lib.ptr(x), _lib.ptr(noise) if noise is not None else None,
+                                           _lib.ptr(x0), _lib.stream_ptr(self.device)))
+        self.last_x_start = x0
+        return x
+
     def sample(self, batch_size=16, cond=None, is_composing_time=False, n_composed=2, compose_start_step=4,
                compose_n_bodies=2, compose_mode="mean", design_fn=None, design_guidance="standard",
                initial_state_overwrite=None, initialization_mode=0, initialization_img=None):
-        if self.sampling_timesteps < self.num_timesteps:
-            raise NotImplementedError("sampling_timesteps < timesteps (ddim_sample) is a 'next' row, not built yet")
+        if self.sampling_timesteps < self.num_timesteps:              # reference :2347-2362
+            return self.ddim_sample((batch_size, self.image_size, self.channels), cond=cond, n_composed=n_composed,
+                                    compose_start_step=compose_start_step, compose_n_bodies=compose_n_bodies,
+                                    compose_mode=compose_mode, design_fn=design_fn, design_guidance=design_guidance,
+                                    initial_state_overwrite=initial_state_overwrite,
+                                    initialization_mode=initialization_mode, initialization_img=initialization_img)
         return self.p_sample_loop((batch_size, self.image_size, self.channels), cond=cond, n_composed=n_composed,
                                   compose_start_step=compose_start_step, compose_n_bodies=compose_n_bodies,
                                   compose_mode=compose_mode, design_fn=design_fn, design_guidance=design_guidance,

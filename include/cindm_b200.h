@@ -156,6 +156,19 @@ int cindm_posterior_update(cindm_engine* e, const float* x_dev, const float* eps
  * consumes torch.randn_like.  x0_out_dev (optional) receives the last x_start. */
 int cindm_sample(cindm_engine* e, const cindm_sample_config* cfg, float* x_dev, const float* noise_dev,
                  float* x0_out_dev, void* stream);
+/* DDIM sampling, `sampling_timesteps < timesteps`: replaces ddim_sample (model/diffusion_1d.py:1723-1804) with the
+ * guidance / composition of p_sample_compose_inside in its epsilon-returning mode (:1372-1376).  The host passes the
+ * reference's schedule for the run: n_pairs (time, time_next) pairs (:1741-1743; time_next = -1 on the last one) and,
+ * per pair, coef[3] = { sqrt(alpha_next), c, sigma } evaluated in fp32 as :1778-1782 does (eta = ddim_sampling_eta).
+ * Per pair: with guidance, cfg->recurrence evaluations {compose, posterior mean - g, re-noise} at `time`, then
+ * x <- x_start * coef[0] + coef[1] * (eps + g) + coef[2] * noise (x <- x_start on the last pair); without guidance one
+ * evaluation (model_predictions :1755).  cfg->t_start / t_end are ignored.  Guidance without recurrence is refused
+ * (-5): that branch of the reference returns the posterior sample where ddim_sample expects epsilon (:1283).
+ * noise_dev (optional) is [pair][draw][B][T][4n] with draws = R re-noise draws, the unused posterior draw, the DDIM draw
+ * (R + 2 per pair; 1 per pair without guidance); NULL = Philox keyed by (seed, candidate, time, draw). */
+int cindm_sample_ddim(cindm_engine* e, const cindm_sample_config* cfg, int n_pairs, const int32_t* times_host,
+                      const int32_t* times_next_host, const float* coef_host, float* x_dev, const float* noise_dev,
+                      float* x0_out_dev, void* stream);
 /* fill x with the Philox N(0,1) stream used for the initial img (draw id 0xFFFF, t = timesteps) */
 int cindm_fill_initial_noise(float* x_dev, int batch, int t_total, int n_bodies, uint64_t seed,
                              int64_t candidate_offset, int timesteps, void* stream);

@@ -258,7 +258,66 @@ def gen_trajectories(m, dif, ns):
     np.savez_compressed(os.path.join(GOLDEN, "trajectories.npz"), **out)
 
 
+# name: (n_bodies, guidance or None, compose_mode, coef, cc, B, sampling_timesteps, eta)
+# (the reference's ddim_sample draws img = randn(B, image_size, channels): 2 bodies, no extra windows)
+DDIM_CASES = {
+    "plain_s4": (2, None, "mean-inside", 0.0, 0.0, 2, 4, 0.0),
+    "rec2_s3": (2, "standard-recurrence-2", "mean-inside", 0.2, 0.2, 2, 3, 0.0),
+    "alpha_rec1_s3_eta": (2, "standard-alpha-recurrence-1", "mean-inside", 0.4, 0.1, 2, 3, 0.5),
+}
+
+
+def gen_ddim(m, dif, ns):
+    """Whole ddim_sample runs of the unmodified reference with every random draw recorded in order."""
+    out = {}
+    real_randn_like, real_randn = torch.randn_like, torch.randn
+    keep = (dif.sampling_timesteps, dif.ddim_sampling_eta)
+    for name, (n, guidance, mode, coef, cc, b, s_steps, eta) in DDIM_CASES.items():
+        fn = None
+        if guidance is not None:
+            target = torch.tensor([0.5, 0.5], dtype=float)
+            fn = ns["get_design_fn"](target, last_n_step=1, coef=coef, time_consistency_coef=cc, design_fn_mode="L2")
+        draws = []
+        gen = torch.Generator().manual_seed(777 + s_steps)
+
+        def logged_randn_like(t, **kw):
+            z = real_randn(t.shape, generator=gen, dtype=t.dtype)
+            draws.append(z)
+            return z
+
+        def logged_randn(shape, **kw):
+            z = real_randn(tuple(shape), generator=gen)
+            draws.append(z)
+            return z
+
+        torch.randn_like, torch.randn = logged_randn_like, logged_randn
+        dif.sampling_timesteps, dif.ddim_sampling_eta = s_steps, eta
+        try:
+            m.grad_mean_list.clear()
+            img = dif.ddim_sample((b, HORIZON, 4 * n), None, n_composed=0, compose_start_step=10, compose_n_bodies=n,
+                                  compose_mode=mode, design_fn=fn, design_guidance=guidance or "standard")
+        finally:
+            torch.randn_like, torch.randn = real_randn_like, real_randn
+            dif.sampling_timesteps, dif.ddim_sampling_eta = keep
+        out[name + ":x_init"] = draws[0].numpy()
+        out[name + ":noise"] = torch.stack(draws[1:]).numpy()
+        out[name + ":img"] = img.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "ddim.npz"), **out)
+    return {k: list(v) for k, v in DDIM_CASES.items()}
+
+
 def main():
+    if "--only-ddim" in sys.argv:
+        # add the DDIM vectors without regenerating the other files
+        torch.set_num_threads(os.cpu_count())
+        sd = init_unet_params(seed=0, randomize_affine=True)
+        m, net, dif = build_reference(sd)
+        cases = gen_ddim(m, dif, reference_objective_namespace())
+        meta = json.load(open(os.path.join(GOLDEN, "meta.json")))
+        meta["ddim_cases"] = cases
+        json.dump(meta, open(os.path.join(GOLDEN, "meta.json"), "w"), indent=1)
+        print("ddim.npz", os.path.getsize(os.path.join(GOLDEN, "ddim.npz")))
+        return
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     sd = init_unet_params(seed=0, randomize_affine=True)
@@ -270,7 +329,9 @@ def main():
     gen_index_maps(m, dif)
     gen_design_grad(ns)
     gen_trajectories(m, dif, ns)
+    ddim_cases = gen_ddim(m, dif, ns)
     meta = {
+        "ddim_cases": ddim_cases,
         "weights": "cindm_b200.model.params.init_unet_params(seed=0, randomize_affine=True)",
         "torch": torch.__version__,
         "compose_cases": {k: list(v) for k, v in COMPOSE_CASES.items()},

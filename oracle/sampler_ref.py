@@ -7,7 +7,8 @@ the composition operator of `model_predictions` (:959-1001) in its original
 one-forward-per-(window, pair) form, x0 / posterior (:914-918, :938-949, :1033-1044),
 the design-objective guidance through `torch.autograd.grad` (:1314-1349) with the
 driver's objective (/root/reference/inference/inverse_design_diffusion_1d.py:211-258),
-the recurrence / re-noise update (:1284-1376) and the 1000-step loop (:1655-1720).
+the recurrence / re-noise update (:1284-1376), the 1000-step loop (:1655-1720) and the DDIM
+loop (:1723-1804) with the epsilon-returning mode of the recurrence branch (:1372-1376).
 
 Noise is ALWAYS supplied by the caller (a callable returning a tensor per draw) so the
 same tensors can be fed to the CUDA path.  Pinned against the live reference and the
@@ -222,4 +223,68 @@ def p_sample_loop(sd, tables, img, noise_fn, *, steps=None, **kw):
     x0 = None
     for t in steps:
         img, x0 = p_sample_step(sd, tables, img, t, noise_fn, **kw)
+    return img, x0
+
+
+# ---------------------------------------------------------------------------------------------
+# DDIM (sampling_timesteps < timesteps)
+# ---------------------------------------------------------------------------------------------
+def ddim_time_pairs(total_timesteps, sampling_timesteps):
+    """[(time, time_next)] as ddim_sample builds them (:1741-1743); the last pair has time_next = -1."""
+    times = torch.linspace(-1, total_timesteps - 1, steps=sampling_timesteps + 1)
+    times = list(reversed(times.int().tolist()))
+    return list(zip(times[:-1], times[1:]))
+
+
+def eps_step_recurrence(sd, tables, x, t, noise_fn, *, n_composed, compose_start_step, compose_n_bodies,
+                        compose_mode, design_fn, design_guidance, horizon=24, eps_model=None):
+    """The recurrence branch of p_sample_compose_inside when sampling_timesteps != 1000 (:1284-1376):
+    same R iterations and random draws as the DDPM step, but returns (pred_noise + grad_design_final,
+    x_start) of the LAST iteration (:1372-1376); the posterior noise is drawn and dropped."""
+    use_alpha = design_guidance.startswith("standard-alpha")
+    reps = recurrence_count(design_guidance)
+    if reps is None or design_guidance.split("-recurrence")[0] not in ("standard", "standard-alpha"):
+        raise NotImplementedError(design_guidance)
+    ratio = tables["alphas_cumprod"][t] / tables["alphas_cumprod_prev"][t]
+    for _ in range(reps):
+        eps = composed_eps(sd, x, t, n_composed, compose_start_step, compose_n_bodies, compose_mode, horizon, eps_model)
+        x0 = (tables["sqrt_recip_alphas_cumprod"][t] * x - tables["sqrt_recipm1_alphas_cumprod"][t] * eps).clamp(-1.0, 1.0)
+        mean = tables["posterior_mean_coef1"][t] * x0 + tables["posterior_mean_coef2"][t] * x
+        g = design_grad_autograd(design_fn, x)
+        if use_alpha:
+            g = (tables["betas"][t] / torch.sqrt(tables["alphas_cumprod_prev"][t])) * g
+        pred = mean - g
+        x = torch.sqrt(ratio) * pred + torch.sqrt(1 - ratio) * noise_fn(pred.shape)
+    if t > 0:
+        noise_fn(pred.shape)
+    return eps + g, x0
+
+
+def ddim_sample(sd, tables, img, noise_fn, *, sampling_timesteps, eta=0.0, n_composed=0, compose_start_step=4,
+                compose_n_bodies=2, compose_mode="mean-inside", design_fn=None, design_guidance="standard",
+                horizon=24, eps_model=None, pairs=None):
+    """ddim_sample (:1723-1804) from a given initial img, cond=None (`pairs` overrides the linspace time grid).  Without design_fn each step is one
+    model_predictions call (:1755, clip_x_start=True); with it, eps_step_recurrence.  One more draw per step
+    feeds sigma * noise (:1784)."""
+    acp = tables["alphas_cumprod"]
+    x0 = None
+    for time, time_next in (pairs or ddim_time_pairs(len(tables["betas"]), sampling_timesteps)):
+        if design_fn is None:
+            pred_noise = composed_eps(sd, img, time, n_composed, compose_start_step, compose_n_bodies, compose_mode,
+                                      horizon, eps_model)
+            x0 = (tables["sqrt_recip_alphas_cumprod"][time] * img
+                  - tables["sqrt_recipm1_alphas_cumprod"][time] * pred_noise).clamp(-1.0, 1.0)
+        else:
+            pred_noise, x0 = eps_step_recurrence(
+                sd, tables, img, time, noise_fn, n_composed=n_composed, compose_start_step=compose_start_step,
+                compose_n_bodies=compose_n_bodies, compose_mode=compose_mode, design_fn=design_fn,
+                design_guidance=design_guidance, horizon=horizon, eps_model=eps_model)
+        alpha = acp[time]
+        alpha_next = acp[time_next]
+        sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+        c = (1 - alpha_next - sigma ** 2).sqrt()
+        noise = noise_fn(img.shape)
+        img = x0 * alpha_next.sqrt() + c * pred_noise + sigma * noise
+        if time_next < 0:
+            img = x0
     return img, x0

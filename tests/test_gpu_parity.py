@@ -439,3 +439,141 @@ def test_initialization_modes(diffusion):
         assert not torch.equal(a, b) and not torch.equal(b, c)
     finally:
         diffusion.num_timesteps = steps
+
+
+# ---------------------------------------------------------------------------------------------
+# DDIM (sampling_timesteps < timesteps): reference ddim_sample :1723-1804
+# ---------------------------------------------------------------------------------------------
+def _ddim_setup(diffusion, s_steps, eta):
+    keep = (diffusion.sampling_timesteps, diffusion.ddim_sampling_eta)
+    diffusion.sampling_timesteps, diffusion.ddim_sampling_eta = s_steps, eta
+    return keep
+
+
+@pytest.mark.parametrize("case", sorted(META.get("ddim_cases", {})))
+def test_ddim_sample_fp32_vs_reference(diffusion, golden, case):
+    """Whole ddim_sample runs of the unmodified reference, its recorded random draws fed to the CUDA path."""
+    from cindm_b200.model.diffusion_1d import get_design_fn, parse_design_guidance
+    set_precision(diffusion, "fp32")
+    n, guidance, mode, coef, cc, b, s_steps, eta = META["ddim_cases"][case]
+    g = golden("ddim.npz")
+    fn = None
+    draws = 1
+    if guidance is not None:
+        fn = get_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, coef=coef, time_consistency_coef=cc)
+        draws = parse_design_guidance(guidance)[1] + 2
+    x_init = torch.from_numpy(g[case + ":x_init"])
+    noise = torch.from_numpy(g[case + ":noise"]).reshape(s_steps, draws, *x_init.shape)
+    keep = _ddim_setup(diffusion, s_steps, eta)
+    try:
+        pairs, coefs = diffusion.ddim_schedule()
+        assert len(pairs) == s_steps and pairs[-1][1] == -1
+        for use_graph in (False, True):
+            diffusion.use_cuda_graph = use_graph
+            out = diffusion.ddim_sample((b, 24, 8), None, n_composed=0, compose_start_step=10, compose_n_bodies=n,
+                                        compose_mode=mode, design_fn=fn, design_guidance=guidance or "standard",
+                                        noise=noise, img=x_init)
+            # The reference's grid starts at t = 999, where x_start = A_t x - B_t eps multiplies the fp32 rounding
+            # differences of eps by A_999 = 2e4 before the clamp, and DDIM carries x_start straight into the next img
+            # (x sqrt(alpha_next) ~ 0.15): 1e-6 in eps is ~3e-3 here.  The tight per-step bar is the next test.
+            assert rel_l2(out, g[case + ":img"]) < 1e-2, use_graph
+    finally:
+        diffusion.use_cuda_graph = True
+        diffusion.sampling_timesteps, diffusion.ddim_sampling_eta = keep
+
+
+@pytest.mark.parametrize("guided", [False, True])
+def test_ddim_steps_fp32_tight(diffusion, test_weights, guided):
+    """DDIM pairs at moderate timesteps (no x_start amplification) against the oracle, at the fp32 bar."""
+    from oracle import sampler_ref
+    from cindm_b200.model.diffusion_1d import get_design_fn
+    set_precision(diffusion, "fp32")
+    pairs = [(600, 420), (420, 180), (180, -1)]
+    b, R = 3, 2
+    gen = torch.Generator().manual_seed(5)
+    x_init = torch.randn(b, 24, 8, generator=gen)
+    draws = R + 2 if guided else 1
+    noise = torch.randn(len(pairs), draws, b, 24, 8, generator=gen)
+    tabs = sampler_ref.cosine_schedule_tables()
+    ofn = sampler_ref.make_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, 0.4, 0.2, "L2") if guided else None
+    fn = get_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, coef=0.4, time_consistency_coef=0.2) if guided else None
+    guidance = f"standard-alpha-recurrence-{R}"
+    flat = list(noise.reshape(-1, b, 24, 8))
+    ref, ref_x0 = sampler_ref.ddim_sample(test_weights, tabs, x_init, lambda shape: flat.pop(0), sampling_timesteps=3, eta=0.7,
+                                          compose_start_step=10, design_fn=ofn, design_guidance=guidance, pairs=pairs)
+    assert not flat
+    keep = _ddim_setup(diffusion, 3, 0.7)
+    try:
+        out = diffusion.ddim_sample((b, 24, 8), None, n_composed=0, compose_start_step=10, compose_n_bodies=2,
+                                    compose_mode="mean-inside", design_fn=fn, design_guidance=guidance, noise=noise,
+                                    img=x_init, pairs=pairs)
+        assert rel_l2(out, ref) < 2 * FP32_TOL
+        assert rel_l2(diffusion.last_x_start, ref_x0) < 2 * FP32_TOL
+    finally:
+        diffusion.sampling_timesteps, diffusion.ddim_sampling_eta = keep
+
+
+@pytest.mark.parametrize("precision,engine", [("fp16", "simt"), ("fp16", "tcgen05"), ("bf16", "tcgen05")])
+def test_ddim_composed_16bit_vs_oracle(diffusion, test_weights, precision, engine):
+    """4-body, two windows (a shape the reference's ddim_sample cannot draw, see ddim_sample's docstring) against the
+    oracle, on a grid of moderate timesteps (the reference's grid starts at t = 999, see the test above)."""
+    from oracle import sampler_ref
+    from cindm_b200.model.diffusion_1d import get_design_fn
+    n, nc, start, b, R = 4, 1, 10, 2, 2
+    pairs = [(700, 450), (450, 200), (200, -1)]
+    guidance = f"standard-recurrence-{R}"
+    gen = torch.Generator().manual_seed(99)
+    x_init = torch.randn(b, 34, 16, generator=gen)
+    noise = torch.randn(len(pairs), R + 2, b, 34, 16, generator=gen)
+    tabs = sampler_ref.cosine_schedule_tables()
+    ofn = sampler_ref.make_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, 0.2, 0.2, "L2")
+    flat = list(noise.reshape(-1, b, 34, 16))
+    ref, _ = sampler_ref.ddim_sample(test_weights, tabs, x_init, lambda shape: flat.pop(0), sampling_timesteps=3,
+                                     eta=0.3, n_composed=nc, compose_start_step=start, compose_n_bodies=n,
+                                     compose_mode="mean-inside", design_fn=ofn, design_guidance=guidance, pairs=pairs)
+    assert not flat
+    fn = get_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, coef=0.2, time_consistency_coef=0.2)
+    keep = _ddim_setup(diffusion, 3, 0.3)
+    kw = dict(n_composed=nc, compose_start_step=start, compose_n_bodies=n, compose_mode="mean-inside", design_fn=fn,
+              design_guidance=guidance, noise=noise, img=x_init, pairs=pairs)
+    try:
+        set_precision(diffusion, "fp32")
+        assert rel_l2(diffusion.ddim_sample((b, 24, 8), None, **kw), ref) < 2 * FP32_TOL
+        set_precision(diffusion, precision, engine)
+        assert rel_l2(diffusion.ddim_sample((b, 24, 8), None, **kw), ref) < (HALF_TOL if precision == "fp16" else 5 * HALF_TOL)
+    finally:
+        set_precision(diffusion, "fp32")
+        diffusion.sampling_timesteps, diffusion.ddim_sampling_eta = keep
+
+
+def test_ddim_dispatch_philox_and_errors(diffusion):
+    """sample() routes to DDIM when sampling_timesteps < timesteps (reference :2347-2362); Philox draws are
+    sharding-invariant; guidance without recurrence is refused (the reference returns the wrong quantity there)."""
+    from cindm_b200 import _lib
+    from cindm_b200.model.diffusion_1d import get_design_fn
+    set_precision(diffusion, "fp16", "tcgen05")
+    fn = get_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, coef=0.2, time_consistency_coef=0.2)
+    kw = dict(n_composed=1, compose_start_step=10, compose_n_bodies=4, compose_mode="mean-inside", design_fn=fn,
+              design_guidance="standard-recurrence-3")
+    keep = _ddim_setup(diffusion, 5, 1.0)
+    try:
+        diffusion.seed, diffusion.candidate_offset = 11, 0
+        full = diffusion.sample(batch_size=4, **kw).cpu()
+        assert full.shape == (4, 34, 16) and torch.isfinite(full).all() and full.abs().max() <= 1.0
+        lo = diffusion.sample(batch_size=2, **kw).cpu()
+        diffusion.candidate_offset = 2
+        hi = diffusion.sample(batch_size=2, **kw).cpu()
+        assert torch.equal(full, torch.cat([lo, hi]))
+        diffusion.candidate_offset = 0
+        diffusion.use_cuda_graph = False
+        direct = diffusion.sample(batch_size=4, **kw).cpu()
+        assert torch.equal(full, direct)
+        with pytest.raises(_lib.CindmError, match="recurrence"):
+            diffusion.sample(batch_size=2, **dict(kw, design_guidance="standard"))
+        plain = diffusion.sample(batch_size=3, n_composed=0, compose_start_step=10, compose_n_bodies=2, compose_mode="mean-inside")
+        assert plain.shape == (3, 24, 8) and torch.isfinite(plain).all()
+    finally:
+        diffusion.use_cuda_graph = True
+        diffusion.candidate_offset = 0
+        set_precision(diffusion, "fp32")
+        diffusion.sampling_timesteps, diffusion.ddim_sampling_eta = keep

@@ -108,3 +108,22 @@ def test_teacher_forced_steps_match_reference(golden, test_weights, case):
         assert rel_l2(img, g[f"{case}:img_after_{si}"]) < 1e-5, (si, t)
         img = torch.from_numpy(g[f"{case}:img_after_{si}"])      # teacher forcing
     assert not noise
+
+
+@pytest.mark.parametrize("case", sorted(META.get("ddim_cases", {})))
+def test_ddim_sample_matches_reference(golden, test_weights, case):
+    """Whole ddim_sample runs of the unmodified reference (sampling_timesteps 3-4), every draw replayed in order."""
+    n, guidance, mode, coef, cc, b, s_steps, eta = META["ddim_cases"][case]
+    g = golden("ddim.npz")
+    tabs = sampler_ref.cosine_schedule_tables()
+    fn = None
+    if guidance is not None:
+        fn = sampler_ref.make_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, coef, cc, "L2")
+    noise = list(torch.from_numpy(g[case + ":noise"]))
+    img, _ = sampler_ref.ddim_sample(
+        test_weights, tabs, torch.from_numpy(g[case + ":x_init"]), lambda shape: noise.pop(0),
+        sampling_timesteps=s_steps, eta=eta, n_composed=0, compose_start_step=10, compose_n_bodies=n,
+        compose_mode=mode, design_fn=fn, design_guidance=guidance or "standard")
+    assert not noise                                   # same number of random draws as the reference
+    assert rel_l2(img, g[case + ":img"]) < 1e-5
+    assert sampler_ref.ddim_time_pairs(1000, 4) == [(999, 749), (749, 499), (499, 249), (249, -1)]
