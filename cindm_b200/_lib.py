@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libcindm_b200.so")
 
 PREC_F32, PREC_F16, PREC_BF16 = 0, 1, 2
 CONV_SIMT, CONV_TCGEN05 = 0, 1
-COMPOSE_MEAN_INSIDE, COMPOSE_SUM_INSIDE = 0, 1
+COMPOSE_MEAN_INSIDE, COMPOSE_SUM_INSIDE, COMPOSE_MEAN_OUTSIDE, COMPOSE_NOISE_SUM = 0, 1, 2, 3
 OBJ_L2, OBJ_L2SQUARE = 0, 1
 GUIDE_NONE, GUIDE_STANDARD, GUIDE_STANDARD_ALPHA = 0, 1, 2
 
@@ -64,6 +64,8 @@ _SIGNATURES = {
     "cindm_posterior_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                        c_int, c_int, c_int, c_int, POINTER(Objective), c_void_p]),
     "cindm_sample": (c_int, [c_void_p, POINTER(SampleConfig), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cindm_composed_posterior": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                         c_int, c_void_p]),
     "cindm_sample_ddim": (c_int, [c_void_p, POINTER(SampleConfig), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
     "cindm_fill_initial_noise": (c_int, [c_void_p, c_int, c_int, c_int, c_uint64, c_int64, c_int, c_void_p]),

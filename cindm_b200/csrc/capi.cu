@@ -140,6 +140,7 @@ int cindm_destroy(cindm_engine* e) {
     if (e->sched_dev) cudaFree(e->sched_dev);
     if (e->sb.x_alt) cudaFree(e->sb.x_alt);
     if (e->sb.eps) cudaFree(e->sb.eps);
+    if (e->sb.x0c) cudaFree(e->sb.x0c);
     if (e->sb.t_dev) cudaFree(e->sb.t_dev);
     if (e->sb.step_dev) cudaFree(e->sb.step_dev);
     if (e->sb.ddim_times) cudaFree(e->sb.ddim_times);
@@ -335,6 +336,19 @@ int cindm_design_grad(const float* x, float* g, int B, int T, int n, const cindm
     if (!obj) return fail(-2, "null objective");
     if (T < 2) return fail(-2, "need at least two time steps");
     return launch_design_grad(x, g, B, T, n, *obj, (cudaStream_t)stream);
+    API_END
+}
+
+int cindm_composed_posterior(cindm_engine* e, const float* x, float* mean_out, float* x0_out, int B, int n, int nc,
+                             int start, int t, int precision, int conv_engine, void* stream) {
+    API_BEGIN
+    if (!e || !x || !mean_out || !x0_out) return fail(-2, "null argument");
+    if (!e->finalized) return fail(-4, "weights not finalized");
+    if (t < 0 || t >= e->cfg.timesteps) return fail(-2, "timestep out of range");
+    const int64_t S = (int64_t)(nc + 1) * (n * (n - 1) / 2) * B;
+    CINDM_TRY(reserve_workspace(e, S > e->ws.max_slices ? S : e->ws.max_slices, precision));
+    return composed_eps(e, x, mean_out, B, n, nc, start, CINDM_COMPOSE_MEAN_OUTSIDE, t, nullptr, precision, conv_engine,
+                        (cudaStream_t)stream, x0_out);
     API_END
 }
 

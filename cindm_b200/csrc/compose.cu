@@ -76,6 +76,75 @@ __global__ void __launch_bounds__(256) compose_scatter_kernel(const float4* __re
     }
 }
 
+// compose_mode "mean" of p_sample_compose_outside (reference :1414-1451): each (window, pair) slice has its own
+// x_start = clamp(A_t x - B_t eps) and posterior mean c1 x_start + c2 x (p_mean_variance on the slice, :1427-1433);
+// both are summed over senders, / (n-1), summed over covering windows, / cover.
+__global__ void __launch_bounds__(256) compose_scatter_posterior_kernel(
+    const float4* __restrict__ eps_pair, const float4* __restrict__ x, float4* __restrict__ mean_out,
+    float4* __restrict__ x0_out, int B, int n, int W, int start, int H, int T, const float* __restrict__ sched, int TS,
+    int t_host, const int* __restrict__ t_dev) {
+    const int tt = t_dev ? *t_dev : t_host;
+    const float A = sched[TAB_SQRT_RECIP_ACP * TS + tt], Bc = sched[TAB_SQRT_RECIPM1_ACP * TS + tt];
+    const float c1 = sched[TAB_POST_C1 * TS + tt], c2 = sched[TAB_POST_C2 * TS + tt];
+    const int P = n * (n - 1) / 2;
+    const long long total = (long long)B * T * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int r = (int)(i % n);
+        long long bt = i / n;
+        int t = (int)(bt % T);
+        int b = (int)(bt / T);
+        const float4 xv4 = x[i];
+        const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
+        float am[4] = {0.f, 0.f, 0.f, 0.f}, a0[4] = {0.f, 0.f, 0.f, 0.f};
+        int cover = 0;
+        for (int kk = 0; kk < W; ++kk) {
+            int h = t - kk * start;
+            if (h < 0 || h >= H) continue;
+            ++cover;
+            float wm[4] = {0.f, 0.f, 0.f, 0.f}, w0[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int s = 0; s < n; ++s) {
+                if (s == r) continue;
+                int ii = r < s ? r : s, jj = r < s ? s : r;
+                int p = pair_index(ii, jj, n);
+                int half = (r == ii) ? 0 : 1;
+                long long slice = ((long long)kk * P + p) * B + b;
+                const float4 e4 = eps_pair[(slice * H + h) * 2 + half];
+                const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float v = __fsub_rn(__fmul_rn(A, xv[q]), __fmul_rn(Bc, ev[q]));
+                    v = fminf(fmaxf(v, -1.0f), 1.0f);
+                    w0[q] += v;
+                    wm[q] += __fadd_rn(__fmul_rn(c1, v), __fmul_rn(c2, xv[q]));
+                }
+            }
+            const float d = (float)(n - 1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { am[q] += wm[q] / d; a0[q] += w0[q] / d; }
+        }
+        const float div = (float)cover;
+        mean_out[i] = make_float4(am[0] / div, am[1] / div, am[2] / div, am[3] / div);
+        x0_out[i] = make_float4(a0[0] / div, a0[1] / div, a0[2] / div, a0[3] / div);
+    }
+}
+
+int launch_compose_scatter_posterior(const float* eps_pair, const float* x, float* mean_out, float* x0_out, int B, int n,
+                                     int nc, int start, int H, const float* sched, int timesteps, int t, const int* t_dev,
+                                     cudaStream_t st) {
+    if (!sched) return fail(-4, "schedule tables not set (cindm_set_schedule)");
+    const int W = nc + 1, T = H + nc * start;
+    long long total = (long long)B * T * n;
+    if (total == 0) return 0;
+    KernelTimer kt("compose_scatter", st, (double)total * 48.0 + (double)W * (n * (n - 1) / 2) * B * H * 32.0);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    compose_scatter_posterior_kernel<<<blocks, 256, 0, st>>>((const float4*)eps_pair, (const float4*)x, (float4*)mean_out,
+                                                             (float4*)x0_out, B, n, W, start, H, T, sched, timesteps, t, t_dev);
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
 int launch_compose_gather(const float* x, float* slices, int B, int n, int nc, int start, int H, cudaStream_t st) {
     const int W = nc + 1, T = H + nc * start, P = n * (n - 1) / 2;
     long long total = (long long)W * P * B * H * 2;

@@ -74,6 +74,7 @@ struct SampleBuffers {           // sized by cindm_sample on first use
     long long graph_nodes = 0;
     float* x_alt = nullptr;
     float* eps = nullptr;
+    float* x0c = nullptr;          // composed x_start of the "mean" (outside) composition
     int* t_dev = nullptr;
     // DDIM: per-step table {time} / {sqrt(alpha_next), c, sigma, last-step flag} and the device-resident step index
     int* ddim_times = nullptr;
@@ -171,6 +172,10 @@ int unet_forward(cindm_engine* e, const float* slices, int64_t S, int t, const i
                  int precision, int conv_engine, cudaStream_t st, const GatherSpec* gather = nullptr);
 
 int launch_compose_gather(const float* x, float* slices, int B, int n, int nc, int start, int H, cudaStream_t st);
+// "mean" composition of p_sample_compose_outside: per-slice clamped x_start and posterior mean, averaged (compose.cu)
+int launch_compose_scatter_posterior(const float* eps_pair, const float* x, float* mean_out, float* x0_out, int B, int n,
+                                     int nc, int start, int H, const float* sched, int timesteps, int t, const int* t_dev,
+                                     cudaStream_t st);
 int launch_compose_scatter(const float* eps_pair, float* eps, int B, int n, int nc, int start, int H, int mode,
                            cudaStream_t st);
 int launch_design_grad(const float* x, float* g, int B, int T, int n, const cindm_objective& obj, cudaStream_t st);
@@ -190,6 +195,8 @@ struct UpdateLaunch {
     // coef[1] * (eps + g) + coef[2] * noise, or x0 on the last step (coef[3] != 0); row = *step_dev of ddim_coef,
     // which also replaces (t_start - t) as the row of the explicit noise tensor
     int ddim = 0; const float* ddim_coef = nullptr; const int* step_dev = nullptr;
+    // "mean" (outside) composition: the posterior mean and x_start are inputs (eps is not read)
+    const float* mean_in = nullptr; const float* x0_in = nullptr;
 };
 int launch_update(const UpdateLaunch& u, cudaStream_t st);
 int launch_fill_noise(float* x, int B, int T, int n, uint64_t seed, int64_t cand_off, int t, int draw,
@@ -202,8 +209,9 @@ void graph_cache_clear(cindm_engine* e);
 int finalize_weights(cindm_engine* e, cudaStream_t st);
 int reserve_workspace(cindm_engine* e, int64_t S, int prec);
 int64_t workspace_bytes(int64_t S, int prec, int horizon);
+// x0_composed: required for (and only used by) CINDM_COMPOSE_MEAN_OUTSIDE, where `eps` receives the composed posterior mean
 int composed_eps(cindm_engine* e, const float* x, float* eps, int B, int n, int nc, int start, int mode, int t,
-                 const int* t_dev, int prec, int conv_engine, cudaStream_t st);
+                 const int* t_dev, int prec, int conv_engine, cudaStream_t st, float* x0_composed = nullptr);
 int sample_loop(cindm_engine* e, const cindm_sample_config& cfg, float* x, const float* noise, float* x0_out,
                 cudaStream_t st);
 

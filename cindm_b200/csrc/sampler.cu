@@ -145,6 +145,7 @@ struct UpdateParams {
     int B, T, n, timesteps, t_host, renoise, t_start, draws_per_step, draw, use_philox;
     cindm_objective obj;
     int ddim; const float* ddim_coef; const int* step_dev;
+    const float* mean_in; const float* x0_in;
 };
 
 __global__ void __launch_bounds__(256) ddpm_update_kernel(UpdateParams p) {
@@ -192,8 +193,14 @@ __global__ void __launch_bounds__(256) ddpm_update_kernel(UpdateParams p) {
         int tt = (int)(bt % p.T);
         long long b = bt / p.T;
         float4 xv = reinterpret_cast<const float4*>(p.x)[i];
-        float4 ev = reinterpret_cast<const float4*>(p.eps)[i];
+        float4 ev = p.mean_in ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<const float4*>(p.eps)[i];
         float xs[4] = {xv.x, xv.y, xv.z, xv.w}, es[4] = {ev.x, ev.y, ev.z, ev.w};
+        float mi[4] = {0.f, 0.f, 0.f, 0.f}, x0i[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.mean_in) {                                      // "mean" (outside) composition: posterior already composed
+            const float4 m4 = reinterpret_cast<const float4*>(p.mean_in)[i], z4 = reinterpret_cast<const float4*>(p.x0_in)[i];
+            mi[0] = m4.x; mi[1] = m4.y; mi[2] = m4.z; mi[3] = m4.w;
+            x0i[0] = z4.x; x0i[1] = z4.y; x0i[2] = z4.z; x0i[3] = z4.w;
+        }
         float g[4] = {0.f, 0.f, 0.f, 0.f};
         if (gscale != 0.f) {
             float2 gr = objective_grad(p.x, bt * F, tt, p.T, F, j, xv.x, xv.y, p.obj);
@@ -208,8 +215,9 @@ __global__ void __launch_bounds__(256) ddpm_update_kernel(UpdateParams p) {
         for (int q = 0; q < 4; ++q) {
             float v = __fsub_rn(__fmul_rn(A, xs[q]), __fmul_rn(Bc, es[q]));                 // (:914-918)
             v = fminf(fmaxf(v, -1.0f), 1.0f);                                               // clamp_(-1, 1) (:1039)
-            x0[q] = v;
             float mu = __fadd_rn(__fmul_rn(c1, v), __fmul_rn(c2, xs[q]));                   // (:943-946)
+            if (p.mean_in) { v = x0i[q]; mu = mi[q]; }
+            x0[q] = v;
             pr[q] = __fsub_rn(mu, g[q]);                                                    // (:1349)
             if (p.ddim) {
                 // pred_noise + grad_design_final (:1375), then img = x_start * sqrt(alpha_next) + c * pred_noise + sigma * noise (:1786-1788)
@@ -237,6 +245,9 @@ int launch_update(const UpdateLaunch& u, cudaStream_t st) {
     p.t_start = u.t_start; p.draws_per_step = u.draws_per_step; p.draw = u.draw; p.use_philox = u.use_philox;
     p.obj = u.obj;
     p.ddim = u.ddim; p.ddim_coef = u.ddim_coef; p.step_dev = u.step_dev;
+    p.mean_in = u.mean_in; p.x0_in = u.x0_in;
+    if ((u.mean_in == nullptr) != (u.x0_in == nullptr)) return fail(-2, "composed posterior mean and x_start come together");
+    if (u.mean_in && u.ddim) return fail(-5, "DDIM runs on the *-inside composition only (reference ddim_sample :1758-1771)");
     if (u.ddim && (!u.ddim_coef || !u.step_dev)) return fail(-2, "DDIM update needs the coefficient table and the step counter");
     long long total = (long long)u.B * u.T * u.n;
     if (total == 0) return 0;
@@ -250,8 +261,12 @@ int launch_update(const UpdateLaunch& u, cudaStream_t st) {
 
 // ---------------------------------------------------------------- composed epsilon + loop
 int composed_eps(cindm_engine* e, const float* x, float* eps, int B, int n, int nc, int start, int mode, int t,
-                 const int* t_dev, int prec, int conv_engine, cudaStream_t st) {
+                 const int* t_dev, int prec, int conv_engine, cudaStream_t st, float* x0_composed) {
     const int H = e->cfg.horizon;
+    if (mode == CINDM_COMPOSE_NOISE_SUM) mode = CINDM_COMPOSE_SUM_INSIDE;      // same operator (:1452-1457 vs :997-999)
+    if (mode == CINDM_COMPOSE_MEAN_OUTSIDE && !x0_composed)
+        return fail(-5, "compose_mode 'mean' composes the posterior, not epsilon: there is no composed epsilon to return");
+    if (mode < 0 || mode > CINDM_COMPOSE_NOISE_SUM) return fail(-2, "bad compose_mode");
     if (n < 2) return fail(-2, "compose_n_bodies must be at least 2");
     if (nc < 0 || start <= 0) return fail(-2, "bad composition window parameters");
     const int64_t S = (int64_t)(nc + 1) * (n * (n - 1) / 2) * B;
@@ -264,6 +279,9 @@ int composed_eps(cindm_engine* e, const float* x, float* eps, int B, int n, int 
         GatherSpec gs{x, B, n, nc, start};          // the stem kernel gathers straight from x
         CINDM_TRY(unet_forward(e, nullptr, S, t, t_dev, e->ws.eps_pair, prec, conv_engine, st, &gs));
     }
+    if (mode == CINDM_COMPOSE_MEAN_OUTSIDE)      // `eps` receives the composed posterior mean, x0_composed the composed x_start
+        return launch_compose_scatter_posterior(e->ws.eps_pair, x, eps, x0_composed, B, n, nc, start, H, e->sched_dev,
+                                                e->cfg.timesteps, t, t_dev, st);
     return launch_compose_scatter(e->ws.eps_pair, eps, B, n, nc, start, H, mode, st);
 }
 
@@ -285,9 +303,11 @@ static int ensure_sample_buffers(cindm_engine* e, size_t elems) {
     graph_cache_clear(e);
     if (sb.x_alt) cudaFree(sb.x_alt);
     if (sb.eps) cudaFree(sb.eps);
-    sb.x_alt = sb.eps = nullptr;
+    if (sb.x0c) cudaFree(sb.x0c);
+    sb.x_alt = sb.eps = sb.x0c = nullptr;
     CINDM_CHECK_CUDA(cudaMalloc(&sb.x_alt, elems * sizeof(float)));
     CINDM_CHECK_CUDA(cudaMalloc(&sb.eps, elems * sizeof(float)));
+    CINDM_CHECK_CUDA(cudaMalloc(&sb.x0c, elems * sizeof(float)));
     sb.elems = elems;
     return 0;
 }
@@ -307,11 +327,13 @@ static int issue_step(cindm_engine* e, const cindm_sample_config& c, float* bufs
         CINDM_CHECK_LAUNCH();
     }
     for (int r = 0; r < iters; ++r) {
+        const bool outside = c.compose_mode == CINDM_COMPOSE_MEAN_OUTSIDE;
         CINDM_TRY(composed_eps(e, bufs[cur], e->sb.eps, c.batch, c.n_bodies, c.n_composed, c.compose_start_step,
-                               c.compose_mode, t, t_dev, c.precision, c.conv_engine, st));
+                               c.compose_mode, t, t_dev, c.precision, c.conv_engine, st, outside ? e->sb.x0c : nullptr));
         const bool last = r == iters - 1;
         UpdateLaunch u;
         u.x = bufs[cur]; u.eps = e->sb.eps; u.x_out = bufs[cur ^ 1];
+        if (outside) { u.mean_in = e->sb.eps; u.x0_in = e->sb.x0c; }
         u.pred_out = nullptr; u.x0_out = last ? x0_out : nullptr;
         u.B = c.batch; u.T = T; u.n = c.n_bodies; u.sched = e->sched_dev; u.timesteps = e->cfg.timesteps;
         u.t_dev = t_dev; u.t_host = t;
@@ -435,6 +457,8 @@ static int sample_ddim_on(cindm_engine* e, const cindm_sample_config& c, int n_p
     const bool guided = c.objective.guidance != CINDM_GUIDE_NONE;
     // only the recurrence branch of p_sample_compose_inside returns (pred_noise + grad, x_start) (:1372-1376); the
     // single-pass "standard" branch hands ddim_sample the posterior sample in place of epsilon (:1283)
+    if (c.compose_mode != CINDM_COMPOSE_MEAN_INSIDE && c.compose_mode != CINDM_COMPOSE_SUM_INSIDE)
+        return fail(-5, "DDIM runs on the *-inside composition only (reference ddim_sample :1758-1771)");
     if (guided && c.recurrence <= 0)
         return fail(-5, "DDIM sampling with guidance needs a '-recurrence-K' design_guidance (reference :1283 vs :1372-1376)");
     for (int i = 0; i < n_pairs; ++i)

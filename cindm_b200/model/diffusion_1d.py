@@ -129,7 +129,11 @@ def _compose_mode(compose_mode):
         return _lib.COMPOSE_MEAN_INSIDE
     if compose_mode == "sum-inside":
         return _lib.COMPOSE_SUM_INSIDE
-    raise NotImplementedError(f"compose_mode {compose_mode!r}: only mean-inside / sum-inside are on the CUDA fast path")
+    if compose_mode == "mean":                    # p_sample_compose_outside (reference :1414-1451), the API default
+        return _lib.COMPOSE_MEAN_OUTSIDE
+    if compose_mode == "noise_sum":               # (:1452-1461)
+        return _lib.COMPOSE_NOISE_SUM
+    raise NotImplementedError(f"compose_mode {compose_mode!r}: mean-inside / sum-inside / mean / noise_sum are built")
 
 
 class _Engine:
@@ -431,14 +435,36 @@ class GaussianDiffusion1D:
                                                _lib.stream_ptr(self.device)))
         return x, x0
 
+    def p_sample_compose_outside(self, x, cond, t, x_self_cond=None, clip_denoised=True, design_fn=None,
+                                 design_guidance="standard", compose_mode="mean", n_composed=0, compose_start_step=4,
+                                 single_model_step=-1, compose_n_bodies=2, initial_state_overwrite=None, noise=None):
+        """One reverse step t -> t-1 with compose_mode 'mean' / 'noise_sum' (reference :1379-1652); same step kernel
+        sequence as p_sample_compose_inside with the posterior composed per slice ('mean') or the summed epsilon."""
+        if compose_mode not in ("mean", "noise_sum"):
+            raise ValueError(f"p_sample_compose_outside: compose_mode {compose_mode!r}")      # the reference's bare `raise`
+        return self.p_sample_compose_inside(x, cond, t, x_self_cond, clip_denoised, design_fn, design_guidance,
+                                            initial_state_overwrite, compose_mode, n_composed, compose_start_step,
+                                            single_model_step, compose_n_bodies, noise)
+
+    def composed_posterior(self, x, t, n_composed, compose_start_step, compose_n_bodies):
+        """compose_mode 'mean' (reference :1414-1451): x [B,T,4n] -> (model_mean, x_start), each [B,T,4n]."""
+        eng = self.model.engine()
+        x = x.to(self.device, torch.float32).contiguous()
+        b, t_total, f = x.shape
+        assert f == 4 * compose_n_bodies and t_total == self.image_size + n_composed * compose_start_step
+        mean, x0 = torch.empty_like(x), torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cindm_composed_posterior(
+                eng.handle, _lib.ptr(x), _lib.ptr(mean), _lib.ptr(x0), b, compose_n_bodies, n_composed, compose_start_step,
+                int(t), self._prec(), self._conv(), _lib.stream_ptr(self.device)))
+        return mean, x0
+
     # --- the reference's public sampling API -------------------------------------------------
     def p_sample_loop(self, shape, cond, n_composed=0, compose_start_step=4, compose_n_bodies=2, compose_mode="mean",
                       design_fn=None, design_guidance="standard", initial_state_overwrite=None, initialization_mode=0,
                       initialization_img=None):
         if cond is not None or initial_state_overwrite is not None:
             raise NotImplementedError("cond / initial_state_overwrite are not on the CUDA fast path")
-        if "inside" not in compose_mode:
-            raise NotImplementedError(f"compose_mode {compose_mode!r}: only the *-inside operators are on the CUDA fast path")
         assert compose_start_step < shape[1]                                   # reference :1679
         eng = self.model.engine()
         b = shape[0]

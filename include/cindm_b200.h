@@ -33,7 +33,12 @@ enum { CINDM_PREC_F32 = 0, CINDM_PREC_F16 = 1, CINDM_PREC_BF16 = 2 };
 /* conv engine: SIMT FMA kernels, or tcgen05 tensor-core kernels (16-bit precisions only) */
 enum { CINDM_CONV_SIMT = 0, CINDM_CONV_TCGEN05 = 1 };
 /* composition reduce: "mean-inside" / "sum-inside" (model/diffusion_1d.py:994-999) */
-enum { CINDM_COMPOSE_MEAN_INSIDE = 0, CINDM_COMPOSE_SUM_INSIDE = 1 };
+/* compose_mode of sample() / p_sample_loop (model/diffusion_1d.py:1683-1715):
+ *   "mean-inside" / "sum-inside": composed epsilon inside model_predictions (:959-1001), then one posterior;
+ *   "mean" (the API default): p_sample_compose_outside (:1379-1652) - every (window, pair) slice gets its own clamped
+ *       x_start and posterior mean, and THOSE are averaged over senders and covering windows (:1446-1451);
+ *   "noise_sum": the summed epsilon of :1452-1461, which is the sum-inside operator followed by the same posterior. */
+enum { CINDM_COMPOSE_MEAN_INSIDE = 0, CINDM_COMPOSE_SUM_INSIDE = 1, CINDM_COMPOSE_MEAN_OUTSIDE = 2, CINDM_COMPOSE_NOISE_SUM = 3 };
 /* design objective: get_design_fn design_fn_mode (inference/inverse_design_diffusion_1d.py:215-222) */
 enum { CINDM_OBJ_L2 = 0, CINDM_OBJ_L2SQUARE = 1 };
 /* guidance scaling: "standard*" (g) or "standard-alpha*" (beta_t/sqrt(abar_prev_t) * g) (:1321-1324) */
@@ -133,6 +138,11 @@ int cindm_unet_enable_taps(cindm_engine* e, int enable);
 int cindm_composed_eps(cindm_engine* e, const float* x_dev, float* eps_dev, int batch, int n_bodies,
                        int n_composed, int compose_start_step, int compose_mode, int t, int precision,
                        int conv_engine, void* stream);
+/* compose_mode "mean" of p_sample_compose_outside (:1414-1451): gather -> U-Net -> per-slice clamped x_start and
+ * posterior mean (p_mean_variance on every (window, pair) slice, :1427-1433) -> mean over senders and covering
+ * windows.  Outputs the composed posterior mean and x_start, both [B][T][4n]. */
+int cindm_composed_posterior(cindm_engine* e, const float* x_dev, float* mean_dev, float* x0_dev, int batch, int n_bodies,
+                             int n_composed, int compose_start_step, int t, int precision, int conv_engine, void* stream);
 
 /* ---- guidance gradient: replaces torch.autograd.grad(design_fn(x), x) (:1316-1320) with the
  *      closed form of get_design_fn (inference/inverse_design_diffusion_1d.py:211-229) --------- */

@@ -267,6 +267,48 @@ DDIM_CASES = {
 }
 
 
+# p_sample_compose_outside: name -> (n_bodies, n_composed, start, guidance, compose_mode, coef, cc, B, steps)
+OUTSIDE_CASES = {
+    "mean_std_4body_w2": (4, 1, 10, "standard", "mean", 0.2, 0.2, 2, (500, 499, 0)),
+    "mean_rec2_2body_w3": (2, 2, 10, "standard-recurrence-2", "mean", 0.4, 0.1, 2, (300, 299)),
+    "noise_sum_alpha_4body": (4, 1, 10, "standard-alpha", "noise_sum", 0.2, 0.2, 2, (700, 1)),
+    "noise_sum_rec2_3body": (3, 0, 10, "standard-alpha-recurrence-2", "noise_sum", 0.2, 0.2, 2, (400, 399)),
+}
+
+
+def gen_outside(m, dif, ns):
+    """Teacher-forced steps of the unmodified reference's p_sample_compose_outside with the draws recorded."""
+    out = {}
+    real_randn_like = torch.randn_like
+    for name, (n, nc, start, guidance, mode, coef, cc, b, steps) in OUTSIDE_CASES.items():
+        target = torch.tensor([0.5, 0.5], dtype=float)
+        fn = ns["get_design_fn"](target, last_n_step=1, coef=coef, time_consistency_coef=cc, design_fn_mode="L2")
+        img = seeded((b, HORIZON + nc * start, 4 * n), 1900 + n)
+        out[name + ":x_init"] = img.numpy()
+        noises = []
+        gen = torch.Generator().manual_seed(5151 + n)
+
+        def logged_randn_like(t, **kw):
+            z = torch.randn(t.shape, generator=gen, dtype=t.dtype)
+            noises.append(z)
+            return z
+
+        torch.randn_like = logged_randn_like
+        try:
+            for si, t in enumerate(steps):
+                img, x0 = dif.p_sample_compose_outside(
+                    img, None, t, None, design_fn=fn, design_guidance=guidance, compose_mode=mode,
+                    n_composed=nc, compose_start_step=start, single_model_step=HORIZON, compose_n_bodies=n)
+                out[f"{name}:img_after_{si}"] = img.numpy()
+                out[f"{name}:x0_after_{si}"] = x0.numpy()
+        finally:
+            torch.randn_like = real_randn_like
+        out[name + ":noise"] = torch.stack(noises).numpy()
+        out[name + ":steps"] = np.asarray(steps, dtype=np.int32)
+    np.savez_compressed(os.path.join(GOLDEN, "outside.npz"), **out)
+    return {k: [list(x) if isinstance(x, tuple) else x for x in v] for k, v in OUTSIDE_CASES.items()}
+
+
 def gen_ddim(m, dif, ns):
     """Whole ddim_sample runs of the unmodified reference with every random draw recorded in order."""
     out = {}
@@ -307,16 +349,19 @@ def gen_ddim(m, dif, ns):
 
 
 def main():
-    if "--only-ddim" in sys.argv:
-        # add the DDIM vectors without regenerating the other files
+    if "--only-ddim" in sys.argv or "--only-outside" in sys.argv:
+        # add the DDIM / compose-outside vectors without regenerating the other files
         torch.set_num_threads(os.cpu_count())
         sd = init_unet_params(seed=0, randomize_affine=True)
         m, net, dif = build_reference(sd)
-        cases = gen_ddim(m, dif, reference_objective_namespace())
         meta = json.load(open(os.path.join(GOLDEN, "meta.json")))
-        meta["ddim_cases"] = cases
+        if "--only-ddim" in sys.argv:
+            meta["ddim_cases"] = gen_ddim(m, dif, reference_objective_namespace())
+            print("ddim.npz", os.path.getsize(os.path.join(GOLDEN, "ddim.npz")))
+        else:
+            meta["outside_cases"] = gen_outside(m, dif, reference_objective_namespace())
+            print("outside.npz", os.path.getsize(os.path.join(GOLDEN, "outside.npz")))
         json.dump(meta, open(os.path.join(GOLDEN, "meta.json"), "w"), indent=1)
-        print("ddim.npz", os.path.getsize(os.path.join(GOLDEN, "ddim.npz")))
         return
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -330,8 +375,10 @@ def main():
     gen_design_grad(ns)
     gen_trajectories(m, dif, ns)
     ddim_cases = gen_ddim(m, dif, ns)
+    outside_cases = gen_outside(m, dif, ns)
     meta = {
         "ddim_cases": ddim_cases,
+        "outside_cases": outside_cases,
         "weights": "cindm_b200.model.params.init_unet_params(seed=0, randomize_affine=True)",
         "torch": torch.__version__,
         "compose_cases": {k: list(v) for k, v in COMPOSE_CASES.items()},

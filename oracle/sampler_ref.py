@@ -103,10 +103,41 @@ def composed_eps(sd, x, t, n_composed, compose_start_step, compose_n_bodies, com
     if compose_mode == "mean-inside":
         per_win = (aggr.sum(-3) / (n - 1)).flatten(start_dim=3)
         return per_win.sum(0) / mask.sum(0)
-    if compose_mode == "sum-inside":
+    if compose_mode in ("sum-inside", "noise_sum"):       # noise_sum (:1452-1457) is the same expression as :997-999
         per_win = aggr.sum(-3).flatten(start_dim=3)
         return per_win.sum(0) / mask.mean(0)
     raise ValueError(compose_mode)
+
+
+def composed_posterior(sd, tables, x, t, n_composed, compose_start_step, compose_n_bodies, horizon=24, eps_model=None):
+    """compose_mode "mean" of p_sample_compose_outside (:1414-1451): p_mean_variance on every (window, pair)
+    slice (own clamped x_start and posterior mean), then mean over senders and over covering windows.
+    Returns (model_mean, x_start), each [B, T_total, 4n]."""
+    if eps_model is None:
+        eps_model = lambda xs, tt: unet_ref.unet_forward(sd, xs, tt)
+    b, t_total, f = x.shape
+    n = compose_n_bodies
+    time = torch.full((b,), t, dtype=torch.long)
+    mean_aggr = torch.zeros(n_composed + 1, b, t_total, n, n, 4, dtype=x.dtype)
+    x0_aggr = torch.zeros_like(mean_aggr)
+    mask = torch.zeros(n_composed + 1, b, t_total, f, dtype=x.dtype)
+    for kk in range(n_composed + 1):
+        lo = kk * compose_start_step
+        mask[kk, :, lo:lo + horizon] = 1.0
+        for ii in range(n):
+            for jj in range(ii + 1, n):
+                cols = torch.tensor(list(range(4 * ii, 4 * ii + 4)) + list(range(4 * jj, 4 * jj + 4)))
+                xs = x[:, lo:lo + horizon][:, :, cols]
+                e = eps_model(xs, time)
+                x0 = (tables["sqrt_recip_alphas_cumprod"][t] * xs - tables["sqrt_recipm1_alphas_cumprod"][t] * e).clamp(-1.0, 1.0)
+                mu = tables["posterior_mean_coef1"][t] * x0 + tables["posterior_mean_coef2"][t] * xs
+                mean_aggr[kk, :, lo:lo + horizon, jj, ii] = mu[..., :4]
+                mean_aggr[kk, :, lo:lo + horizon, ii, jj] = mu[..., 4:]
+                x0_aggr[kk, :, lo:lo + horizon, jj, ii] = x0[..., :4]
+                x0_aggr[kk, :, lo:lo + horizon, ii, jj] = x0[..., 4:]
+    mean_w = (mean_aggr.sum(-3) / (n - 1)).flatten(start_dim=3)
+    x0_w = (x0_aggr.sum(-3) / (n - 1)).flatten(start_dim=3)
+    return mean_w.sum(0) / mask.sum(0), x0_w.sum(0) / mask.sum(0)
 
 
 # --------------------------------------------------------------------------- objective
@@ -184,6 +215,8 @@ def p_sample_step(sd, tables, x, t, noise_fn, *, n_composed, compose_start_step,
     reps = recurrence_count(design_guidance)
 
     def mean_and_x0(xc):
+        if compose_mode == "mean":                        # p_sample_compose_outside (:1379-1652)
+            return composed_posterior(sd, tables, xc, t, n_composed, compose_start_step, compose_n_bodies, horizon, eps_model)
         eps = composed_eps(sd, xc, t, n_composed, compose_start_step, compose_n_bodies, compose_mode,
                            horizon, eps_model)
         if record is not None:

@@ -271,7 +271,7 @@ def test_philox_noise_is_sharding_invariant(diffusion):
 def test_unsupported_configurations_fail_loudly(diffusion):
     from cindm_b200.model.diffusion_1d import GaussianDiffusion1D, parse_design_guidance
     with pytest.raises(NotImplementedError):
-        diffusion.p_sample_loop((2, 24, 8), None, compose_mode="mean")
+        diffusion.p_sample_loop((2, 24, 8), None, compose_mode="EBMs")
     with pytest.raises(NotImplementedError):
         parse_design_guidance("universal-backward")
     with pytest.raises(NotImplementedError):
@@ -577,3 +577,66 @@ def test_ddim_dispatch_philox_and_errors(diffusion):
         diffusion.candidate_offset = 0
         set_precision(diffusion, "fp32")
         diffusion.sampling_timesteps, diffusion.ddim_sampling_eta = keep
+
+
+# ---------------------------------------------------------------------------------------------
+# compose_mode "mean" (the API default) / "noise_sum": reference p_sample_compose_outside :1379-1652
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", sorted(META.get("outside_cases", {})))
+def test_compose_outside_steps_fp32(diffusion, golden, case):
+    from cindm_b200.model.diffusion_1d import get_design_fn, parse_design_guidance
+    set_precision(diffusion, "fp32")
+    n, nc, start, guidance, mode, coef, cc, b, steps = META["outside_cases"][case]
+    g = golden("outside.npz")
+    fn = get_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, coef=coef, time_consistency_coef=cc)
+    _, recurrence = parse_design_guidance(guidance)
+    noise = list(torch.from_numpy(g[case + ":noise"]))
+    img = torch.from_numpy(g[case + ":x_init"])
+    tabs = golden("schedule.npz")
+    for si, t in enumerate(steps):
+        nz = golden_noise_for_step(noise, recurrence, t, img.shape)
+        out, x0 = diffusion.p_sample_compose_outside(
+            img, None, t, design_fn=fn, design_guidance=guidance, compose_mode=mode, n_composed=nc,
+            compose_start_step=start, single_model_step=24, compose_n_bodies=n, noise=nz)
+        assert rel_l2(out, g[f"{case}:img_after_{si}"]) < FP32_TOL, (si, t)
+        amp = max(1.0, float(tabs["sqrt_recip_alphas_cumprod"][t]))
+        assert rel_l2(x0, g[f"{case}:x0_after_{si}"]) < FP32_TOL * amp, (si, t)
+        img = torch.from_numpy(g[f"{case}:img_after_{si}"])
+    assert not noise
+
+
+@pytest.mark.parametrize("precision,engine", [("fp32", "simt"), ("fp16", "tcgen05"), ("bf16", "tcgen05")])
+def test_composed_posterior_vs_oracle(diffusion, test_weights, precision, engine):
+    """compose_mode 'mean': per-slice clamped x_start / posterior mean, composed (4 bodies, 2 windows, t = 400)."""
+    from oracle import sampler_ref
+    set_precision(diffusion, precision, engine)
+    x = torch.randn(3, 34, 16, generator=torch.Generator().manual_seed(21))
+    tabs = sampler_ref.cosine_schedule_tables()
+    ref_mean, ref_x0 = sampler_ref.composed_posterior(test_weights, tabs, x, 400, 1, 10, 4)
+    mean, x0 = diffusion.composed_posterior(x, 400, 1, 10, 4)
+    tol = {"fp32": FP32_TOL, "fp16": HALF_TOL, "bf16": 5 * HALF_TOL}[precision]
+    assert rel_l2(mean, ref_mean) < tol and rel_l2(x0, ref_x0) < tol
+    set_precision(diffusion, "fp32")
+
+
+def test_default_compose_mode_runs_and_noise_sum_is_sum_inside(diffusion):
+    """sample() with the reference's default compose_mode='mean'; 'noise_sum' == 'sum-inside' bit for bit."""
+    from cindm_b200 import _lib
+    from cindm_b200.model.diffusion_1d import get_design_fn
+    set_precision(diffusion, "fp16", "tcgen05")
+    fn = get_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, coef=0.2, time_consistency_coef=0.2)
+    steps = diffusion.num_timesteps
+    try:
+        diffusion.num_timesteps = 6
+        kw = dict(batch_size=3, n_composed=1, compose_start_step=10, compose_n_bodies=4, design_fn=fn,
+                  design_guidance="standard-recurrence-2")
+        out = diffusion.sample(**kw)                                        # compose_mode defaults to "mean"
+        assert out.shape == (3, 34, 16) and torch.isfinite(out).all()
+        a = diffusion.sample(compose_mode="noise_sum", **kw).cpu()
+        b = diffusion.sample(compose_mode="sum-inside", **kw).cpu()
+        assert torch.equal(a, b)
+        with pytest.raises(_lib.CindmError, match="no composed epsilon"):
+            diffusion.composed_eps(torch.zeros(1, 34, 16), 3, 1, 10, 4, compose_mode="mean")
+    finally:
+        diffusion.num_timesteps = steps
+        set_precision(diffusion, "fp32")

@@ -127,3 +127,22 @@ def test_ddim_sample_matches_reference(golden, test_weights, case):
     assert not noise                                   # same number of random draws as the reference
     assert rel_l2(img, g[case + ":img"]) < 1e-5
     assert sampler_ref.ddim_time_pairs(1000, 4) == [(999, 749), (749, 499), (499, 249), (249, -1)]
+
+
+@pytest.mark.parametrize("case", sorted(META.get("outside_cases", {})))
+def test_compose_outside_steps_match_reference(golden, test_weights, case):
+    """p_sample_compose_outside of the unmodified reference (compose_mode 'mean' / 'noise_sum'), teacher-forced."""
+    n, nc, start, guidance, mode, coef, cc, b, steps = META["outside_cases"][case]
+    g = golden("outside.npz")
+    tabs = sampler_ref.cosine_schedule_tables()
+    fn = sampler_ref.make_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, coef, cc, "L2")
+    noise = list(torch.from_numpy(g[case + ":noise"]))
+    img = torch.from_numpy(g[case + ":x_init"])
+    for si, t in enumerate(steps):
+        img, x0 = sampler_ref.p_sample_step(
+            test_weights, tabs, img, t, lambda shape: noise.pop(0), n_composed=nc, compose_start_step=start,
+            compose_n_bodies=n, compose_mode=mode, design_fn=fn, design_guidance=guidance)
+        assert rel_l2(x0, g[f"{case}:x0_after_{si}"]) < 1e-5, (si, t)
+        assert rel_l2(img, g[f"{case}:img_after_{si}"]) < 1e-5, (si, t)
+        img = torch.from_numpy(g[f"{case}:img_after_{si}"])
+    assert not noise
