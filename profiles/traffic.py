@@ -3,6 +3,7 @@
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
         -c 400 --csv --log-file gpurun_out/traffic.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline
     python profiles/traffic.py gpurun_out/traffic.csv > profiles/r1_evaluation_traffic.json
+    python profiles/traffic.py gpurun_out/traffic.csv --md > profiles/r1_evaluation_launches.md
 
 One evaluation = the launches from one stem_kernel up to (not including) the next one.
 """
@@ -42,6 +43,16 @@ def main(path):
         c["share"] = c["ms"] / total
     out = {"evaluation_kernels": len(ev), "total_ms": total,
            "classes": collections.OrderedDict(sorted(classes.items(), key=lambda kv: -kv[1]["ms"]))}
+    if "--md" in sys.argv:
+        print("One composed-epsilon evaluation (C4 per GPU: S = 43 008 slices) between two consecutive stem_kernel launches.")
+        print("ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
+              "(serialised, cold-cache: compare SHARES).\n")
+        print("| kernel | launches | total ms | share | DRAM read MB | DRAM write MB |\n|---|---|---|---|---|---|")
+        for k, c in out["classes"].items():
+            print(f"| `{k[:60]}` | {c['launches']} | {c['ms']:.3f} | {100 * c['share']:.1f}% | "
+                  f"{c['dram_read_bytes'] / 1e6:.0f} | {c['dram_write_bytes'] / 1e6:.0f} |")
+        print(f"\ntotal {out['total_ms']:.3f} ms over {out['evaluation_kernels']} kernels")
+        return
     json.dump(out, sys.stdout, indent=1)
     print()
 
