@@ -5,7 +5,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libcindm_b200.so")
+# CINDM_B200_LIB points at another build of the same library (A/B measurements of two kernel versions in one job)
+LIB_PATH = os.environ.get("CINDM_B200_LIB") or os.path.join(HERE, "lib", "libcindm_b200.so")
 
 PREC_F32, PREC_F16, PREC_BF16 = 0, 1, 2
 CONV_SIMT, CONV_TCGEN05 = 0, 1

@@ -65,14 +65,14 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
 // x * tanh(softplus(x)) exactly as torch evaluates nn.Mish in fp32 (reference model/diffusion_1d.py:210).
 __device__ __forceinline__ float mish_exact(float x) { return x * tanhf(log1pf(expf(x))); }
 
-// Same function with one ex2 and one rcp: tanh(log(1+w)) = (w^2+2w)/(w^2+2w+2), w = e^x.
-// The exponent is clamped at 20 where the ratio already rounds to 1.0f, so no branch is needed for large x.
+// Same function with one ex2 and one rcp: with w = e^x, tanh(log(1+w)) = (w^2+2w)/(w^2+2w+2) = 1 - 2/(w^2+2w+2), so
+// mish(x) = x - 2x / (w(w+2) + 2).  No clamp is needed: for large x the denominator overflows to +inf, its
+// reciprocal is 0 and the result is x; for very negative x, w = 0 and the result is x - x = 0.
 __device__ __forceinline__ float mish_fast(float x) {
     float w, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(fminf(x, 20.0f) * 1.4426950408889634f));
-    const float n = w * (w + 2.0f);
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n + 2.0f));
-    return x * (n * r);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(x * 1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(w, w + 2.0f, 2.0f)));
+    return fmaf(x * r, -2.0f, x);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

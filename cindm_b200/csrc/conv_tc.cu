@@ -396,8 +396,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                         for (int u = 0; u < 4; ++u) {
                             const int g = T3 ? 0 : (cc * 32 + i + u) / CPG;
                             const float rs = T3 ? t3_rstd : g_sc[g], nm = T3 ? t3_nm : g_sh[g];
-                            const float sc = rs * ga[u];
-                            const float x = fmaf(v[i + u], sc, fmaf(nm, ga[u], be[u]));      // (v - mean) * rstd * gamma + beta
+                            const float x = fmaf(fmaf(v[i + u], rs, nm), ga[u], be[u]);      // ((v - mean) * rstd) * gamma + beta
                             y[u] = mish_fast(x) + ad[u];
                         }
                     } else {
