@@ -148,8 +148,9 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         T16* out = reinterpret_cast<T16*>(p.out);
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cp * 32);
         const int g = lane >> 2, t4 = lane & 3;
-        // A 16-row fragment step of a task may reach past its slice into the next slice of the tile: those positions are
-        // cleared in the fragments (k index 16*ks + 2*t4 (+1) in the low registers, + 8 in the high ones)
+        // A 16-row fragment step covers more positions than a slice has: the surplus ldmatrix rows re-read the slice's own
+        // last row (never another slice's rows, which another warp may be rewriting) and are cleared in the fragments
+        // (k index 16*ks + 2*t4 (+1) in the low registers, + 8 in the high ones)
         uint32_t mlo[KS], mhi[KS];
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
@@ -211,7 +212,7 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
             const float sc = rstd, nm = -mean * rstd;
             // ---- q | k | v passes: TMEM -> normalise -> 16-bit rows of the shared-memory tile.  Rows beyond the tile's slices
-            //      carry stale operands; nothing reads them unmasked (see the fragment masks above) ----
+            //      carry stale operands; no task reads them (tasks exist for real slices only and stay inside their rows) ----
             for (int pass = 0; pass < 3; ++pass) {
                 mbar_wait_backoff(&tmem_full[acc], acc_phase);
                 tc_fence_after();
@@ -264,8 +265,7 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     for (int j = 0; j < H; ++j) tk[j * kTileRow] = (T16)(kv[j] * inv);
                 }
                 __syncwarp();
-                // ctx^T = V^T K_s : M = e (2 tiles of 16), N = d (4 tiles of 8), K = positions.  Rows beyond the slice belong to the
-                // next slice of the tile: masked out of both operands, so no value of another slice can reach this one.
+                // ctx^T = V^T K_s : M = e (2 tiles of 16), N = d (4 tiles of 8), K = positions; positions >= n masked out of both operands
                 float ct[2][4][4];
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt)
@@ -278,14 +278,14 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     uint32_t bk[2][4];
 #pragma unroll
                     for (int np = 0; np < 2; ++np) {
-                        const int r = min(r0 + 16 * ks + (lane & 7) + ((lane >> 3) & 1) * 8, 127), col = 16 * np + (lane >> 4) * 8;
+                        const int r = r0 + min(16 * ks + (lane & 7) + ((lane >> 3) & 1) * 8, n - 1), col = 16 * np + (lane >> 4) * 8;
                         ldsm_x4_trans(smem_u32(tq + 128 + r * kTileRow + col), bk[np]);
                         bk[np][0] &= mlo[ks]; bk[np][1] &= mhi[ks]; bk[np][2] &= mlo[ks]; bk[np][3] &= mhi[ks];
                     }
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt) {
                         uint32_t av[4];
-                        const int r = min(r0 + 16 * ks + (lane & 7) + (lane >> 4) * 8, 127), col = 16 * mt + ((lane >> 3) & 1) * 8;
+                        const int r = r0 + min(16 * ks + (lane & 7) + (lane >> 4) * 8, n - 1), col = 16 * mt + ((lane >> 3) & 1) * 8;
                         ldsm_x4_trans(smem_u32(tq + 256 + r * kTileRow + col), av);
                         av[0] &= mlo[ks]; av[1] &= mlo[ks]; av[2] &= mhi[ks]; av[3] &= mhi[ks];
 #pragma unroll
@@ -304,7 +304,7 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                     for (int kd = 0; kd < 2; ++kd) {
                         uint32_t aq[4];
-                        const int r = min(r0 + 16 * mt + (lane & 7) + ((lane >> 3) & 1) * 8, 127), col = 16 * kd + (lane >> 4) * 8;
+                        const int r = r0 + min(16 * mt + (lane & 7) + ((lane >> 3) & 1) * 8, n - 1), col = 16 * kd + (lane >> 4) * 8;
                         ldsm_x4(smem_u32(tq + r * kTileRow + col), aq);
 #pragma unroll
                         for (int ne = 0; ne < 4; ++ne) {

@@ -106,7 +106,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
     }
     tc_fence_before();
-    if (CG == 2) cluster_sync_all(); else __syncthreads();      // barrier inits / TMEM allocation visible to the whole pair
+    // barrier inits / TMEM allocation visible to the whole pair (the CTA barrier after the cluster barrier orders nothing
+    // new; it lets compute-sanitizer's racecheck, which does not follow cluster barriers, see the ordering)
+    if (CG == 2) cluster_sync_all();
+    __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
