@@ -106,10 +106,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
     }
     tc_fence_before();
-    // barrier inits / TMEM allocation visible to the whole pair (the CTA barrier after the cluster barrier orders nothing
-    // new; it lets compute-sanitizer's racecheck, which does not follow cluster barriers, see the ordering)
-    if (CG == 2) cluster_sync_all();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();      // barrier inits / TMEM allocation visible to the whole pair
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 

@@ -9,7 +9,8 @@ best-of-batch R_T value.  Everything numeric runs in libcindm_b200.so on the B20
 
 Differences, all forced by the environment or by the B200 design:
   * no dataset is needed for `--initialization_mode 0` (the reference loads one but never uses it in that
-    mode, :200-201, :313-314); modes 1/2 take `--initialization_npy`;
+    mode, :200-201, :313-314); modes 1/2 read the reference's dataset files through `cindm_b200.data` (or
+    `--initialization_npy`);
   * checkpoints are optional (`--checkpoint`): without one the model uses seeded random-init weights;
   * PDF plots are skipped (matplotlib is not installed);
   * launched under torchrun (one process per GPU) the `--val_batch_size` candidates are sharded over the ranks
@@ -139,9 +140,19 @@ def run(args):
     output_steps = rollout_steps + args.n_composed * args.compose_start_step
     init_img = None
     if args.initialization_mode != 0:
-        if not args.initialization_npy:
-            raise ValueError("initialization_mode 1/2 needs --initialization_npy")
-        init_img = torch.from_numpy(np.load(args.initialization_npy)).float()
+        if args.initialization_npy:
+            init_img = torch.from_numpy(np.load(args.initialization_npy)).float()
+        else:
+            # as the reference: y of the first unshuffled batch of the 2-body dataset (:182-201), so only
+            # compose_n_bodies = 2 has the right feature width (the reference's reshape fails otherwise, :1675)
+            from cindm_b200.data import NBodyDataset, first_batch_1d
+            dataset = NBodyDataset(dataset="nbody-2", input_steps=conditioned_steps, output_steps=output_steps,
+                                   time_interval=4, is_y_diff=False, is_train=not args.is_test, is_testdata=False,
+                                   dataset_path=args.dataset_path)
+            init_img = first_batch_1d(dataset, max(ast.literal_eval(args.batch_size_list)), "y")
+        if init_img.shape[-1] != 4 * args.compose_n_bodies or init_img.shape[1] != output_steps:
+            raise ValueError(f"initialization trajectories have shape {tuple(init_img.shape)}, the design tensor is "
+                             f"[B, {output_steps}, {4 * args.compose_n_bodies}]")
 
     results = []
     for sample_steps in ast.literal_eval(args.sample_steps_list):

@@ -359,6 +359,25 @@ def test_driver_cli_end_to_end(tmp_path):
         assert "MAE" in pickle.load(f)
 
 
+def test_driver_cli_ddim_from_dataset_initialization(tmp_path):
+    """The CLI with the reference's remaining switches: --sample_steps_list (DDIM, :100-101, :268-270), the default
+    compose_mode of the API ("mean"), and --initialization_mode 1 read from a trajectory file in the reference's layout."""
+    from cindm_b200.inference.inverse_design_diffusion_1d import main
+    rng = np.random.default_rng(3)
+    d = tmp_path / "nbody-2"
+    d.mkdir()
+    np.save(d / "trajectory_balls_2_simu_6000_steps_1000.npy", rng.uniform(20, 180, size=(2, 1000, 2, 4)).astype(np.float32))
+    common = ["--exp_id=test2", "--date_time=00-00", "--compose_n_bodies=2", "--design_coef=0.2", "--consistency_coef=0.2",
+              "--batch_size_list=[4]", "--model_name=Diffusion_cond-0_rollout-24_bodies-2", f"--results_dir={tmp_path}",
+              f"--dataset_path={tmp_path}"]
+    ddim = main(common + ["--n_composed=0", "--compose_mode=mean-inside", "--design_guidance=standard-recurrence-2",
+                          "--sample_steps_list=[8]"])[0]
+    assert ddim["pred"].shape == (4, 24, 8) and np.isfinite(ddim["pred"]).all() and np.abs(ddim["pred"]).max() <= 1.0
+    init = main(common + ["--n_composed=1", "--compose_mode=mean", "--design_guidance=standard", "--initialization_mode=1",
+                          "--sample_steps_list=[1000]"])[0]
+    assert init["pred"].shape == (4, 34, 8) and np.isfinite(init["pred"]).all()
+
+
 def test_full_size_c4_candidate_independence(diffusion):
     """BASELINE.json's full per-GPU size (C4: 512 candidates, 8 bodies, 3 windows -> 43 008 slices per evaluation) through
     a size-independent property: every candidate is an independent unit, so sampling candidates [100, 164) alone must
