@@ -343,10 +343,9 @@ template <typename T16, int H>
 int launch_instance(const CUtensorMap& ma, const CUtensorMap& mb, const AttnTcParams& p, cudaStream_t st) {
     auto kern = qkv_attn_kernel<T16, H>;
     constexpr size_t smem = attn_smem_bytes();
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.first_time()) {
         CINDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
     }
     const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
     kern<<<grid, kAttnThreads, smem, st>>>(ma, mb, p);

@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <atomic>
 #include <string>
 
 namespace cindm {
@@ -29,6 +30,19 @@ int fail(int code, const std::string& msg);      // records msg, returns code
             return ::cindm::fail(-101, std::string("kernel launch (") + __FILE__ + ":" +          \
                                            std::to_string(__LINE__) + "): " + cudaGetErrorString(_e)); \
     } while (0)
+
+// cudaFuncSetAttribute is per device.  A launcher keeps `static DeviceOnce once;` and configures its kernel the first
+// time it runs on each device (one process may drive several GPUs through several engine handles).
+struct DeviceOnce {
+    std::atomic<unsigned long long> done{0};
+    bool first_time() {
+        int d = 0;
+        cudaGetDevice(&d);
+        if (d < 0 || d >= 64) return true;
+        const unsigned long long bit = 1ull << d;
+        return (done.fetch_or(bit) & bit) == 0;
+    }
+};
 
 // ---- built-in tracing: launches counted always; per-kernel-class CUDA-event timing when enabled
 void count_launch();

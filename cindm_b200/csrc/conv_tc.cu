@@ -474,10 +474,9 @@ int launch_instance(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensor
                     cudaStream_t st) {
     auto kern = conv_tc_kernel<T16, N_TILE, CPG, EPI, CG>;
     constexpr size_t smem = smem_bytes_for<N_TILE, CG>();
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.first_time()) {
         CINDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
     }
     const int tiles = ((p.m_tiles + CG - 1) / CG) * p.n_tiles;          // (pair-)tiles
     const int slots = num_sms() / CG;                                   // clusters that fit on the machine

@@ -381,11 +381,10 @@ __global__ void __launch_bounds__(256) attn_core_mma_kernel(const T* __restrict_
 template <typename T>
 static int launch_attn_mma(const T* qkv, T* out, int64_t S, int n, cudaStream_t st) {
     const size_t smem = (size_t)8 * 3 * 32 * kMmaRow * sizeof(T);
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.first_time()) {
         CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_mma_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_mma_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -407,13 +406,12 @@ int launch_attn_core(const void* qkv, void* out, int64_t S, int n, int prec, cud
     if (prec == PREC_F16) return launch_attn_mma<__half>((const __half*)qkv, (__half*)out, S, n, st);
     if (prec == PREC_BF16) return launch_attn_mma<__nv_bfloat16>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, S, n, st);
     const size_t smem = attn_smem_bytes(n);
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.first_time()) {
         const int mx = (int)attn_smem_bytes(24);
         CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_tiled_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_tiled_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_tiled_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-        configured = true;
     }
     // persistent grid: as many CTAs as fit on the machine at this shared-memory footprint
     int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
