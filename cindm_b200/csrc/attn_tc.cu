@@ -259,7 +259,8 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     }
                     float sum = 0.f;
 #pragma unroll
-                    for (int j = 0; j < H; ++j) { kv[j] = __expf(kv[j] - m); sum += kv[j]; }
+                    const float m2 = m * 1.4426950408889634f;
+                    for (int j = 0; j < H; ++j) { kv[j] = ex2_approx(fmaf(kv[j], 1.4426950408889634f, -m2)); sum += kv[j]; }
                     const float inv = 1.0f / sum;
 #pragma unroll
                     for (int j = 0; j < H; ++j) tk[j * kTileRow] = (T16)(kv[j] * inv);
@@ -314,13 +315,12 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             mma16816<T16>(oc[ne], aq, b0, b1);
                         }
                     }
-                    const float scale = 0.17677669529663687f;             // 32^-0.5 (q * scale in the reference, :284)
-                    const int j0 = 16 * mt + g, j1 = j0 + 8;
+                    const int j0 = 16 * mt + g, j1 = j0 + 8;                   // (the 32^-0.5 query scale is folded into the q weights)
 #pragma unroll
                     for (int ne = 0; ne < 4; ++ne) {
                         const int e = 8 * ne + 2 * t4;
-                        if (j0 < n) *reinterpret_cast<uint32_t*>(dst + j0 * 128 + e) = pack2<T16>(oc[ne][0] * scale, oc[ne][1] * scale);
-                        if (j1 < n) *reinterpret_cast<uint32_t*>(dst + j1 * 128 + e) = pack2<T16>(oc[ne][2] * scale, oc[ne][3] * scale);
+                        if (j0 < n) *reinterpret_cast<uint32_t*>(dst + j0 * 128 + e) = pack2<T16>(oc[ne][0], oc[ne][1]);
+                        if (j1 < n) *reinterpret_cast<uint32_t*>(dst + j1 * 128 + e) = pack2<T16>(oc[ne][2], oc[ne][3]);
                     }
                 }
             }

@@ -79,6 +79,12 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
 // x * tanh(softplus(x)) exactly as torch evaluates nn.Mish in fp32 (reference model/diffusion_1d.py:210).
 __device__ __forceinline__ float mish_exact(float x) { return x * tanhf(log1pf(expf(x))); }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // Same function with one ex2 and one rcp: with w = e^x, tanh(log(1+w)) = (w^2+2w)/(w^2+2w+2) = 1 - 2/(w^2+2w+2), so
 // mish(x) = x - 2x / (w(w+2) + 2).  No clamp is needed: for large x the denominator overflows to +inf, its
 // reciprocal is 0 and the result is x; for very negative x, w = 0 and the result is x - x = 0.

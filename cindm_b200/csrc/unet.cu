@@ -142,7 +142,8 @@ struct Uploader {
         a.g = vec(prefix + ".fn.norm.g", c);
         conv(a.qkv, prefix + ".fn.fn.to_qkv", c, 384, 1, false);
         conv(a.out, prefix + ".fn.fn.to_out", 128, c, 1, true);
-        // folded operand of the fused tcgen05 attention kernel: W'[n][ci] = W[n][ci] * g[ci], and its row sums
+        // folded operand of the fused tcgen05 attention kernel: W'[n][ci] = W[n][ci] * g[ci] (the q rows also carry the
+        // 32^-0.5 query scale of :284), and its row sums
         const HostTensor* tg = find(prefix + ".fn.norm.g");
         const HostTensor* tw = find(prefix + ".fn.fn.to_qkv.weight");
         if (!tg || !tw || rc) return;
@@ -152,7 +153,7 @@ struct Uploader {
         for (int n = 0; n < 384; ++n) {
             float ah = 0.f, ab = 0.f;
             for (int ci = 0; ci < c; ++ci) {
-                const float v = tw->data[(size_t)n * c + ci] * tg->data[ci];
+                const float v = tw->data[(size_t)n * c + ci] * tg->data[ci] * (n < 128 ? 0.17677669529663687f : 1.0f);
                 wh[(size_t)n * c + ci] = __float2half_rn(v);
                 wb[(size_t)n * c + ci] = __float2bfloat16_rn(v);
                 ah += __half2float(wh[(size_t)n * c + ci]);
