@@ -81,6 +81,8 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         tma_prefetch_desc(&map_b);
     }
     if (warp == 1) tmem_alloc(tmem_slot, 256);
+    pdl_wait();                  // the previous kernel of the chain is complete: global memory may be touched from here on
+    pdl_trigger();
     for (int c = threadIdx.x; c < 384; c += blockDim.x) wsum[c] = p.wsum[c];
     tc_fence_before();
     __syncthreads();
@@ -348,7 +350,7 @@ int launch_instance(const CUtensorMap& ma, const CUtensorMap& mb, const AttnTcPa
         CINDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
-    kern<<<grid, kAttnThreads, smem, st>>>(ma, mb, p);
+    CINDM_CHECK_CUDA(launch_chain(kern, dim3(grid), dim3(kAttnThreads), smem, st, ma, mb, p));
     CINDM_CHECK_LAUNCH();
     return 0;
 }

@@ -26,6 +26,11 @@ void count_launch() { ++g_launches; }
 void add_launches(long long n) { g_launches += n; }
 long long launch_count() { return g_launches; }
 bool profiling_enabled() { return g_profiling; }
+bool pdl_enabled() {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("CINDM_PDL"); mode = (e && e[0] == '0') ? 0 : 1; }
+    return mode == 1;
+}
 void profile_record(const char* tag, cudaStream_t st, bool begin, double work) {
     if (begin) {
         ProfEntry pe; pe.tag = tag; pe.work = work;

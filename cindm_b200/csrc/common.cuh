@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <atomic>
 #include <string>
+#include <utility>
 
 namespace cindm {
 
@@ -43,6 +44,27 @@ struct DeviceOnce {
         return (done.fetch_or(bit) & bit) == 0;
     }
 };
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------
+// The kernels of one evaluation form a chain.  Launched with programmaticStreamSerializationAllowed, kernel k+1 may
+// become resident while kernel k is still running (on SMs k does not use - small batches - or has already left -
+// the tail of a persistent kernel) and do the work that depends on nothing: barrier init, TMEM allocation, tensor-map
+// prefetch.  It then blocks in pdl_wait() until kernel k has COMPLETED and its memory is visible; every global
+// access of every such kernel comes after that call.  pdl_trigger() lets the kernel after it be scheduled.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();        // CINDM_PDL=0 turns the launch attribute off (the device calls are then no-ops)
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // ---- built-in tracing: launches counted always; per-kernel-class CUDA-event timing when enabled
 void count_launch();

@@ -38,6 +38,8 @@ __global__ void __launch_bounds__(256) compose_gather_kernel(const float4* __res
 
 __global__ void __launch_bounds__(256) compose_scatter_kernel(const float4* __restrict__ eps_pair, float4* __restrict__ eps,
                                                               int B, int n, int W, int start, int H, int T, int mode) {
+    pdl_wait();
+    pdl_trigger();
     // one thread per (b, t, receiver): 16 bytes out, (n-1) * cover(t) 16-byte reads
     const int P = n * (n - 1) / 2;
     const long long total = (long long)B * T * n;
@@ -83,6 +85,8 @@ __global__ void __launch_bounds__(256) compose_scatter_posterior_kernel(
     const float4* __restrict__ eps_pair, const float4* __restrict__ x, float4* __restrict__ mean_out,
     float4* __restrict__ x0_out, int B, int n, int W, int start, int H, int T, const float* __restrict__ sched, int TS,
     int t_host, const int* __restrict__ t_dev) {
+    pdl_wait();
+    pdl_trigger();
     const int tt = t_dev ? *t_dev : t_host;
     const float A = sched[TAB_SQRT_RECIP_ACP * TS + tt], Bc = sched[TAB_SQRT_RECIPM1_ACP * TS + tt];
     const float c1 = sched[TAB_POST_C1 * TS + tt], c2 = sched[TAB_POST_C2 * TS + tt];
@@ -139,8 +143,8 @@ int launch_compose_scatter_posterior(const float* eps_pair, const float* x, floa
     KernelTimer kt("compose_scatter", st, (double)total * 48.0 + (double)W * (n * (n - 1) / 2) * B * H * 32.0);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    compose_scatter_posterior_kernel<<<blocks, 256, 0, st>>>((const float4*)eps_pair, (const float4*)x, (float4*)mean_out,
-                                                             (float4*)x0_out, B, n, W, start, H, T, sched, timesteps, t, t_dev);
+    CINDM_CHECK_CUDA(launch_chain(compose_scatter_posterior_kernel, dim3(blocks), dim3(256), 0, st, (const float4*)eps_pair,
+                                  (const float4*)x, (float4*)mean_out, (float4*)x0_out, B, n, W, start, H, T, sched, timesteps, t, t_dev));
     CINDM_CHECK_LAUNCH();
     return 0;
 }
@@ -165,7 +169,8 @@ int launch_compose_scatter(const float* eps_pair, float* eps, int B, int n, int 
     KernelTimer kt("compose_scatter", st, (double)total * 16.0 + (double)W * (n * (n - 1) / 2) * B * H * 32.0);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    compose_scatter_kernel<<<blocks, 256, 0, st>>>((const float4*)eps_pair, (float4*)eps, B, n, W, start, H, T, mode);
+    CINDM_CHECK_CUDA(launch_chain(compose_scatter_kernel, dim3(blocks), dim3(256), 0, st, (const float4*)eps_pair, (float4*)eps,
+                                  B, n, W, start, H, T, mode));
     CINDM_CHECK_LAUNCH();
     return 0;
 }

@@ -95,6 +95,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         tma_prefetch_desc(&map_b);
     }
     if (warp == 1) { if (CG == 2) tmem_alloc_pair(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
+    // everything above depends on nothing; the previous kernel of the chain must be complete before any global access
+    pdl_wait();
+    pdl_trigger();
     // per-layer channel vectors -> smem (epilogue broadcast reads)
     {
         const float* addv = p.add_vec;
@@ -483,10 +486,12 @@ int launch_instance(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensor
     const int grid = (tiles < slots ? tiles : slots) * CG;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads_for(N_TILE, EPI)); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     CINDM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a0, a1, b, mo, p));
     CINDM_CHECK_LAUNCH();
     return 0;

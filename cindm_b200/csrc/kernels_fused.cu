@@ -459,6 +459,8 @@ struct StemParams {
 template <typename T>
 __global__ void __launch_bounds__(256, 2) stem_kernel(StemParams p) {
     __shared__ float xs[4][24 + 4][8];                      // per-slice input with 2 zero rows of padding each side
+    pdl_wait();
+    pdl_trigger();
     const int sub = threadIdx.x >> 6, co = threadIdx.x & 63;
     const long long s = (long long)blockIdx.x * 4 + sub;
     const bool active = s < p.S;
@@ -544,8 +546,8 @@ int launch_stem(const StemLaunch& a, cudaStream_t st) {
     p.out_b0 = a.out_b0; p.out_res = a.out_res; p.S = a.S;
     p.gather = a.gather; p.B = a.B; p.n = a.n; p.P = a.n * (a.n - 1) / 2; p.start = a.start; p.T = a.T;
     const unsigned blocks = (unsigned)((a.S + 3) / 4);
-    if (a.prec == PREC_F16) stem_kernel<__half><<<blocks, 256, 0, st>>>(p);
-    else if (a.prec == PREC_BF16) stem_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p);
+    if (a.prec == PREC_F16) CINDM_CHECK_CUDA(launch_chain(stem_kernel<__half>, dim3(blocks), dim3(256), 0, st, p));
+    else if (a.prec == PREC_BF16) CINDM_CHECK_CUDA(launch_chain(stem_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, p));
     else return fail(-2, "stem kernel is built for the 16-bit precisions");
     CINDM_CHECK_LAUNCH();
     return 0;
@@ -561,6 +563,8 @@ __global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ in, con
                                                    long long rows) {
     __shared__ float sw[64][8];
     __shared__ float sb[8];
+    pdl_wait();
+    pdl_trigger();
     for (int i = threadIdx.x; i < 512; i += 256) sw[i >> 3][i & 7] = w[i];        // w: [1][64][8]
     if (threadIdx.x < 8) sb[threadIdx.x] = bias[threadIdx.x];
     __syncthreads();
@@ -588,8 +592,12 @@ int launch_head(const void* in, const ConvW& w, float* out, int64_t rows, int pr
     if (rows == 0) return 0;
     KernelTimer kt("head", st, (double)rows * (64.0 * elem_size(prec) + 32.0));
     const unsigned blocks = (unsigned)((rows + 255) / 256);
-    if (prec == PREC_F16) head_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)in, w.w, w.bias, out, rows);
-    else if (prec == PREC_BF16) head_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in, w.w, w.bias, out, rows);
+    if (prec == PREC_F16)
+        CINDM_CHECK_CUDA(launch_chain(head_kernel<__half>, dim3(blocks), dim3(256), 0, st, (const __half*)in, (const float*)w.w,
+                                      (const float*)w.bias, out, (long long)rows));
+    else if (prec == PREC_BF16)
+        CINDM_CHECK_CUDA(launch_chain(head_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)in,
+                                      (const float*)w.w, (const float*)w.bias, out, (long long)rows));
     else return fail(-2, "head kernel is built for the 16-bit precisions");
     CINDM_CHECK_LAUNCH();
     return 0;

@@ -67,10 +67,10 @@ int launch_fill_noise(float* x, int B, int T, int n, uint64_t seed, int64_t cand
     return 0;
 }
 
-__global__ void step_counter_kernel(int* t, int delta) { *t += delta; }
-__global__ void ddim_set_time_kernel(int* t, const int* times, const int* step) { *t = times[*step]; }
+__global__ void step_counter_kernel(int* t, int delta) { pdl_wait(); pdl_trigger(); *t += delta; }
+__global__ void ddim_set_time_kernel(int* t, const int* times, const int* step) { pdl_wait(); pdl_trigger(); *t = times[*step]; }
 int launch_step_counter(int* t_dev, int delta, cudaStream_t st) {
-    step_counter_kernel<<<1, 1, 0, st>>>(t_dev, delta);
+    CINDM_CHECK_CUDA(launch_chain(step_counter_kernel, dim3(1), dim3(1), 0, st, t_dev, delta));
     CINDM_CHECK_LAUNCH();
     return 0;
 }
@@ -149,6 +149,8 @@ struct UpdateParams {
 };
 
 __global__ void __launch_bounds__(256) ddpm_update_kernel(UpdateParams p) {
+    pdl_wait();
+    pdl_trigger();
     const int t = p.t_dev ? *p.t_dev : p.t_host;
     const int TS = p.timesteps;
     // coefficients, read from the fp32 buffers exactly as `extract` does (reference :454-462)
@@ -254,7 +256,7 @@ int launch_update(const UpdateLaunch& u, cudaStream_t st) {
     KernelTimer kt("ddpm_update", st, (double)total * 16.0 * (u.noise ? 4.0 : 3.0));
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    ddpm_update_kernel<<<blocks, 256, 0, st>>>(p);
+    CINDM_CHECK_CUDA(launch_chain(ddpm_update_kernel, dim3(blocks), dim3(256), 0, st, p));
     CINDM_CHECK_LAUNCH();
     return 0;
 }
@@ -323,7 +325,8 @@ static int issue_step(cindm_engine* e, const cindm_sample_config& c, float* bufs
     const int iters = ddim ? (guided ? c.recurrence : 1) : (c.recurrence > 0 ? c.recurrence : 1);
     const int draws = ddim ? (guided ? c.recurrence + 2 : 1) : (c.recurrence > 0 ? c.recurrence + 1 : 1);
     if (ddim) {
-        ddim_set_time_kernel<<<1, 1, 0, st>>>(e->sb.t_dev, e->sb.ddim_times, e->sb.step_dev);
+        CINDM_CHECK_CUDA(launch_chain(ddim_set_time_kernel, dim3(1), dim3(1), 0, st, e->sb.t_dev, (const int*)e->sb.ddim_times,
+                                      (const int*)e->sb.step_dev));
         CINDM_CHECK_LAUNCH();
     }
     for (int r = 0; r < iters; ++r) {
