@@ -115,6 +115,20 @@ def gather_scores(local_scores, counts, dist):
     return torch.cat([out[r * width: r * width + c] for r, c in enumerate(counts)])
 
 
+def gather_top_designs(local_designs, lo, top_indices, dist):
+    """The k winning designs [k, T, 4n] on every rank: each rank fills in the winners it owns (global ids lo .. lo+B_local),
+    one all-reduce(sum) of k small tensors completes them (optional second collective)."""
+    k = int(top_indices.numel())
+    out = torch.zeros((k,) + tuple(local_designs.shape[1:]), dtype=local_designs.dtype, device=local_designs.device)
+    idx = top_indices.to(local_designs.device)
+    mine = (idx >= lo) & (idx < lo + local_designs.shape[0])
+    if bool(mine.any()):
+        out[mine] = local_designs[idx[mine] - lo]
+    if dist is not None:
+        dist.all_reduce(out)
+    return out
+
+
 def run(args):
     rank, world, local = distributed_context()
     dist = None
@@ -212,6 +226,7 @@ def run(args):
                             top = torch.topk(torch.where(valid, obj_all, torch.full_like(obj_all, float("inf"))), k, largest=False)
                             record["top_k_indices"] = top.indices.cpu().numpy()
                             record["top_k_objective"] = top.values.cpu().numpy()
+                            record["top_k_designs"] = gather_top_designs(pred, lo, top.indices, dist).cpu().numpy()
                             best_loss_sum += caculate_confidence_interval(obj_all[valid])[3].item()
                             if rank == 0:
                                 record["pred"] = pred.cpu().numpy()

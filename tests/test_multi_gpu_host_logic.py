@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from cindm_b200.inference.inverse_design_diffusion_1d import build_parser, gather_scores, model_horizon, shard
+from cindm_b200.inference.inverse_design_diffusion_1d import build_parser, gather_scores, gather_top_designs, model_horizon, shard
 
 
 def _free_port():
@@ -28,7 +28,10 @@ def _worker(rank, world, port, batch, out_dir):
     local = torch.stack([(ids * 37 % 11) / 11.0, ids, -ids], 1).flatten().contiguous()
     full = gather_scores(local, [3 * c for c in counts], dist).reshape(-1, 3)
     top = torch.topk(full[:, 0], 3, largest=False)
-    torch.save({"full": full, "top": top.indices}, os.path.join(out_dir, f"rank{rank}.pt"))
+    # the designs of this rank's candidates, recognisable by their global id; second collective: the winners everywhere
+    designs = ids.to(torch.float32).reshape(-1, 1, 1) + torch.arange(6, dtype=torch.float32).reshape(1, 3, 2) / 10
+    winners = gather_top_designs(designs, lo, top.indices, dist)
+    torch.save({"full": full, "top": top.indices, "winners": winners}, os.path.join(out_dir, f"rank{rank}.pt"))
     dist.destroy_process_group()
 
 
@@ -42,6 +45,8 @@ def test_shard_allgather_topk_world2(tmp_path, batch):
     expect = torch.stack([(ids * 37 % 11) / 11.0, ids, -ids], 1)
     assert torch.equal(r0["full"], expect) and torch.equal(r1["full"], expect)
     assert torch.equal(r0["top"], r1["top"])                     # replicated top-k: every rank picks the same designs
+    want = r0["top"].to(torch.float32).reshape(-1, 1, 1) + torch.arange(6, dtype=torch.float32).reshape(1, 3, 2) / 10
+    assert torch.equal(r0["winners"], want) and torch.equal(r1["winners"], want)
 
 
 def test_shard_covers_every_candidate_once():
