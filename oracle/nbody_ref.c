@@ -18,6 +18,9 @@
  * lexicographic order (Chipmunk's order comes from its spatial index), and the ~1e-15 angular
  * velocities Chipmunk picks up from rounding in r x j are not carried.
  *
+ * A contact-order switch (nbody_ref_set_order) exists for the sensitivity study of DESIGN.md section 4;
+ * the default order 0 is the one the CUDA kernel implements and every parity test uses.
+ *
  * PARITY UNPINNED: the reference has no test or golden vector at this boundary and pymunk cannot be
  * run here; this oracle is pinned only by analytic known-answer tests (tests/test_nbody_oracle.py).
  *
@@ -31,6 +34,29 @@
 
 enum { NONE = 0, FIRST = 1, NORMAL = 2, CACHED = 3 };
 
+/* Contact solve order (sensitivity studies only; the CUDA kernel and every parity test use order 0).
+ * Chipmunk2D iterates its arbiters in the order its bounding-box tree reported the pairs, which depends
+ * on insertion history and on which leaves moved; that order cannot be reproduced without the library,
+ * so profiles/contact_order_study.py measures how far the scores move under other orders:
+ *   0 walls first (body-major), then disc pairs in lexicographic order          [default]
+ *   1 disc pairs first, then walls
+ *   2 the reverse of order 0
+ *   3 a fresh random permutation every step (xorshift64*, seeded per design)
+ *   4 body-major: for body i, its wall contacts, then its pairs (i, j > i)      [closest to a tree walk] */
+static int g_order_mode = 0;
+static unsigned long long g_order_seed = 0x9E3779B97F4A7C15ull;
+void nbody_ref_set_order(int mode, unsigned long long seed) { g_order_mode = mode; g_order_seed = seed ? seed : 1ull; }
+/* simultaneous-contact census of the last rollout call: steps with >= 2 active contacts sharing a body */
+static long g_multi_steps = 0, g_contact_steps = 0;
+void nbody_ref_census(long* multi_steps, long* contact_steps) { *multi_steps = g_multi_steps; *contact_steps = g_contact_steps; }
+
+static unsigned long long rng_next(unsigned long long* s) {
+    unsigned long long x = *s;
+    x ^= x >> 12; x ^= x << 25; x ^= x >> 27;
+    *s = x;
+    return x * 0x2545F4914F6CDD1Dull;
+}
+
 typedef struct {
     int n;
     double p[MAXB][2], v[MAXB][2], vb[MAXB][2];
@@ -38,7 +64,39 @@ typedef struct {
     double jn_acc[MAXARB];
     int n_active, slot[MAXARB], a[MAXARB], b[MAXARB];
     double nrm[MAXARB][2], n_mass[MAXARB], bias[MAXARB], bounce[MAXARB], j_bias[MAXARB];
+    int ord[MAXARB];               /* solve order: position -> index into the active list */
+    unsigned long long rng;
 } world_t;
+
+/* fill w->ord for the active contacts of this step (order 0 is the identity) */
+static void order_contacts(world_t* w) {
+    int m = w->n_active;
+    for (int k = 0; k < m; ++k) w->ord[k] = k;
+    if (g_order_mode == 1) {                      /* pairs, then walls; each group keeps its lexicographic order */
+        int q = 0;
+        for (int k = 0; k < m; ++k) if (w->b[k] >= 0) w->ord[q++] = k;
+        for (int k = 0; k < m; ++k) if (w->b[k] < 0) w->ord[q++] = k;
+    } else if (g_order_mode == 2) {
+        for (int k = 0; k < m; ++k) w->ord[k] = m - 1 - k;
+    } else if (g_order_mode == 3) {               /* Fisher-Yates */
+        for (int k = m - 1; k > 0; --k) {
+            int r = (int)(rng_next(&w->rng) % (unsigned long long)(k + 1));
+            int t = w->ord[k]; w->ord[k] = w->ord[r]; w->ord[r] = t;
+        }
+    } else if (g_order_mode == 4) {               /* stable sort by first body: walls of i, then pairs (i, j) */
+        int q = 0;
+        for (int i = 0; i < w->n; ++i)
+            for (int k = 0; k < m; ++k) if (w->a[k] == i) w->ord[q++] = k;
+    }
+    /* census */
+    if (m > 0) ++g_contact_steps;
+    int touched[MAXB] = {0}, multi = 0;
+    for (int k = 0; k < m; ++k) {
+        if (++touched[w->a[k]] > 1) multi = 1;
+        if (w->b[k] >= 0 && ++touched[w->b[k]] > 1) multi = 1;
+    }
+    if (multi) ++g_multi_steps;
+}
 
 static const double RADIUS = 20.0, WALL_RADIUS = 1.0, BOX = 200.0, DT = 1.0 / 60.0, SLOP = 0.1;
 
@@ -104,7 +162,9 @@ static void step_world(world_t* w, int step, double bias_coef, double dt_coef) {
         if (ticks >= 1 && w->state[s] != CACHED) w->state[s] = CACHED;
         if (ticks >= 3) w->state[s] = NONE;
     }
-    for (int k = 0; k < w->n_active; ++k) {
+    order_contacts(w);
+    for (int kk = 0; kk < w->n_active; ++kk) {
+        int k = w->ord[kk];
         int s = w->slot[k];
         if (w->state[s] == FIRST) continue;
         double jx = w->nrm[k][0] * w->jn_acc[s] * dt_coef, jy = w->nrm[k][1] * w->jn_acc[s] * dt_coef;
@@ -113,7 +173,8 @@ static void step_world(world_t* w, int step, double bias_coef, double dt_coef) {
         if (b >= 0) { w->v[b][0] = w->v[b][0] + jx; w->v[b][1] = w->v[b][1] + jy; }
     }
     for (int it = 0; it < 10; ++it)
-        for (int k = 0; k < w->n_active; ++k) {
+        for (int kk = 0; kk < w->n_active; ++kk) {
+            int k = w->ord[kk];
             int s = w->slot[k], a = w->a[k], b = w->b[k];
             double nx = w->nrm[k][0], ny = w->nrm[k][1];
             double vbx = -w->vb[a][0], vby = -w->vb[a][1], vrx = -w->v[a][0], vry = -w->v[a][1];
@@ -145,10 +206,13 @@ static void step_world(world_t* w, int step, double bias_coef, double dt_coef) {
 void nbody_ref_rollout(const double* state0, double* traj, int B, int n, int n_steps, int stride) {
     double bias_coef = 1.0 - pow(pow(1.0 - 0.1, 60.0), DT);
     int frames = n_steps / stride;
+    g_multi_steps = 0; g_contact_steps = 0;
     for (int b = 0; b < B; ++b) {
         world_t w;
         memset(&w, 0, sizeof w);
         w.n = n;
+        w.rng = g_order_seed ^ (0xD1B54A32D192ED03ull * (unsigned long long)(b + 1));
+        if (w.rng == 0) w.rng = 1;
         for (int i = 0; i < n; ++i) {
             const double* s = state0 + ((long)b * n + i) * 4;
             w.p[i][0] = s[0]; w.p[i][1] = s[1]; w.v[i][0] = s[2]; w.v[i][1] = s[3];

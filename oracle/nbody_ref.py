@@ -19,7 +19,27 @@ def _load():
         _lib = ctypes.CDLL(_build.build())
         _lib.nbody_ref_rollout.restype = None
         _lib.nbody_ref_rollout.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        _lib.nbody_ref_set_order.restype = None
+        _lib.nbody_ref_set_order.argtypes = [ctypes.c_int, ctypes.c_ulonglong]
+        _lib.nbody_ref_census.restype = None
+        _lib.nbody_ref_census.argtypes = [ctypes.POINTER(ctypes.c_long), ctypes.POINTER(ctypes.c_long)]
     return _lib
+
+
+ORDERS = {"walls-first lexicographic (default)": 0, "pairs before walls": 1, "reverse": 2, "random permutation per step": 3,
+          "body-major": 4}
+
+
+def set_contact_order(mode=0, seed=1):
+    """Contact solve order of subsequent rollouts (see nbody_ref.c); 0 is what the CUDA kernel implements."""
+    _load().nbody_ref_set_order(int(mode), int(seed))
+
+
+def census():
+    """(steps with two or more active contacts sharing a body, steps with any contact) of the last rollout call."""
+    a, b = ctypes.c_long(), ctypes.c_long()
+    _load().nbody_ref_census(ctypes.byref(a), ctypes.byref(b))
+    return a.value, b.value
 
 
 def rollout(state0, n_steps, stride=1):

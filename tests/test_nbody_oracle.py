@@ -90,3 +90,110 @@ def test_score_designs_arithmetic():
     full = np.concatenate([pred[:, :1].astype(np.float64), sim], 1)
     assert np.allclose(mae, np.abs(full - pred).mean((1, 2)))
     assert np.all(obj >= 0)
+
+
+# ---- hand-derived multi-contact known answers: the expected values below are computed from the
+#      published sequential-impulse scheme with pencil-and-paper formulas, not by calling the oracle.
+
+BIAS_COEF = 1.0 - (0.9 ** 60) ** DT          # = 0.1 at dt = 1/60 (cpSpaceStep: 1 - collisionBias^dt)
+
+
+def test_corner_hit_touches_two_walls_in_the_same_step():
+    # a disc flying diagonally into the (0, 0) corner reaches both walls in the same step; the two contact normals are
+    # orthogonal, so each wall reverses its own velocity component whatever the solve order: v -> (+u, +u) exactly.
+    u = 60.0
+    x0 = 21.0 + 0.5 * u * DT                      # half a step outside contact range: the first step penetrates by 0.5*u*dt
+    s0 = np.array([[[x0, x0, -u, -u]]])
+    traj = nbody_ref.rollout(s0, 6, 1)[0, :, 0]
+    assert traj[0].tolist() == [x0, x0, -u, -u]
+    # step 1: p = x0 - u dt (penetration u dt / 2 = 0.5 on both walls), then the impulse solve flips both components
+    assert traj[1, 0] == pytest.approx(x0 - u * DT, abs=1e-12) and traj[1, 1] == pytest.approx(x0 - u * DT, abs=1e-12)
+    assert traj[1, 2] == pytest.approx(u, abs=1e-12) and traj[1, 3] == pytest.approx(u, abs=1e-12)
+    # the penetration bias: pen = 0.5 > slop 0.1 -> bias velocity 0.1 * (0.5 - 0.1) / dt along each inward normal, applied
+    # to the NEXT position update only: p2 = p1 + (u + 0.1 * 0.4 / dt) * dt = p1 + u dt + 0.04
+    assert traj[2, 0] == pytest.approx(traj[1, 0] + u * DT + BIAS_COEF * (0.5 - 0.1), abs=1e-11)
+    assert traj[2, 1] == pytest.approx(traj[2, 0], abs=1e-12)
+    assert np.allclose(traj[2:, 2:], u, atol=1e-12)               # nothing touches the disc again
+    for order in nbody_ref.ORDERS.values():                        # orthogonal normals: every order gives the same bits
+        nbody_ref.set_contact_order(order, seed=5)
+        try:
+            assert np.array_equal(nbody_ref.rollout(s0, 6, 1)[0, :, 0], traj)
+        finally:
+            nbody_ref.set_contact_order(0)
+
+
+def test_three_discs_in_simultaneous_contact_match_the_coupled_solution():
+    # disc A moves along +x into discs B and C that sit symmetrically at +-30 degrees, so that both contacts form in the
+    # same step.  Sequential impulses with elasticity 1 converge to "every contact's normal velocity is reversed":
+    #   2 j1 + c j2 = 2 u cos(th),  2 j2 + c j1 = 2 u cos(th),  c = n1.n2 = cos(2 th)   ->   j = 2 u cos(th) / (2 + c)
+    # Gauss-Seidel contracts by (c/2)^2 = 1/16 per sweep: 10 sweeps leave ~1e-12 of the first residual.
+    u, th = 50.0, np.pi / 6
+    gap = 0.25                                                     # A starts `gap` short of touching along each normal
+    d = 40.0 + gap
+    a = np.array([70.0, 100.0])
+    b = a + d * np.array([np.cos(th), np.sin(th)])
+    c = a + d * np.array([np.cos(th), -np.sin(th)])
+    s0 = np.array([[[a[0], a[1], u, 0.0], [b[0], b[1], 0.0, 0.0], [c[0], c[1], 0.0, 0.0]]])
+    traj = nbody_ref.rollout(s0, 3, 1)[0]
+    # after step 1 A has moved u*dt = 0.833 > the gap along the normals: both contacts are live with the SAME geometry
+    a1 = a + np.array([u * DT, 0.0])
+    n1 = (b - a1) / np.linalg.norm(b - a1)
+    n2 = (c - a1) / np.linalg.norm(c - a1)
+    assert np.linalg.norm(b - a1) < 40.0
+    cc = float(n1 @ n2)
+    j = 2.0 * u * n1[0] / (2.0 + cc)
+    va = np.array([u, 0.0]) - j * n1 - j * n2
+    assert np.allclose(traj[1, 0, 2:], va, atol=1e-9)
+    assert np.allclose(traj[1, 1, 2:], j * n1, atol=1e-9)
+    assert np.allclose(traj[1, 2, 2:], j * n2, atol=1e-9)
+    # symmetric geometry: kinetic energy and momentum are conserved by the coupled solution
+    assert (traj[1, :, 2:] ** 2).sum() == pytest.approx(u * u, rel=1e-9)
+    assert np.allclose(traj[1, :, 2:].sum(0), [u, 0.0], atol=1e-9)
+    # solve order changes only the Gauss-Seidel iterates, not the fixed point
+    for order in nbody_ref.ORDERS.values():
+        nbody_ref.set_contact_order(order, seed=7)
+        try:
+            assert np.allclose(nbody_ref.rollout(s0, 3, 1)[0, 1, :, 2:], traj[1, :, 2:], atol=1e-9)
+        finally:
+            nbody_ref.set_contact_order(0)
+
+
+def test_persistent_contact_warm_start_cancels_and_bias_follows_the_recurrence():
+    # a disc that starts overlapping the right wall and moves into it stays in contact for several steps.  Hand-derived per step k >= 1 with
+    # pen_k = x_k - 179 (> 0 while overlapping), v the (outward) speed after the first bounce:
+    #   first contact step : jn = 2 v (normal velocity reversed), jnAcc = 2 v
+    #   persisting steps   : cached impulse re-applied (v_n -> 3 v outward), bounce was taken BEFORE it (= v), so the solver
+    #                        removes it again: jn = -(v + 3 v) -> jnAcc = max(2 v - 4 v, 0) = 0, applied -2 v -> v_n = v: unchanged
+    #   positions          : x_{k+1} = x_k - v dt - 0.1 * max(pen_k - 0.1, 0)     (bias velocity of the previous solve)
+    v, x0 = 30.0, 181.0
+    s0 = np.array([[[x0, 100.0, v, 0.0]]])
+    traj = nbody_ref.rollout(s0, 8, 1)[0, :, 0]
+    x = x0 + v * DT                                               # step 1: moves further in, pen = x - 179 = 2.5
+    assert traj[1, 0] == pytest.approx(x, abs=1e-12) and traj[1, 2] == pytest.approx(-v, abs=1e-12)
+    steps_in_contact = 0
+    for k in range(1, 7):
+        pen = x - 179.0
+        if pen <= 0.0:
+            break
+        steps_in_contact += 1
+        x = x - v * DT - BIAS_COEF * max(pen - 0.1, 0.0)
+        assert traj[k + 1, 0] == pytest.approx(x, abs=1e-10), k
+        assert traj[k + 1, 2] == pytest.approx(-v, abs=1e-10), k   # warm start + solver cancel exactly
+    assert steps_in_contact >= 3                                   # the cached-impulse path really ran
+    assert np.all(np.abs(traj[:, 3]) < 1e-12)
+
+
+def test_resting_overlap_is_pushed_out_geometrically_over_many_steps():
+    # two discs at rest overlapping by 2.1: no velocity ever appears (bounce = 0, jn = 0), only the bias pushes them apart.
+    # Each disc gets half of the bias impulse (nMass = 1/2): gap_{k+1} = gap_k + 0.1 * max(-(gap_k) - 0.1, 0)  for gap < 0,
+    # evaluated from the SECOND step on (the bias velocity of step k moves the discs in step k + 1).
+    s0 = np.array([[[80.0, 100.0, 0.0, 0.0], [117.9, 100.0, 0.0, 0.0]]])
+    traj = nbody_ref.rollout(s0, 12, 1)[0]
+    gap = 37.9 - 40.0
+    pending = 0.0
+    for k in range(1, 12):
+        gap = gap + pending                                        # position update with last step's bias velocity
+        assert traj[k, 1, 0] - traj[k, 0, 0] - 40.0 == pytest.approx(gap, abs=1e-10), k
+        pending = BIAS_COEF * max(-gap - 0.1, 0.0)
+    assert np.all(traj[:, :, 2:] == 0.0)                           # the arbiter persists >= 4 steps and never creates velocity
+    assert gap > -2.1 and gap < -0.1
