@@ -15,7 +15,15 @@ random-init weights, Philox noise generated in-kernel, fp16 operands / fp32 accu
 
 Rank 0 prints one JSON line (see the keys below).  `--impl reference` times the CPU oracle port
 (oracle/sampler_ref.py: the reference's own loop structure in PyTorch, all host threads) on a
-bounded sample of the same workload.
+bounded sample of the same workload: REF_BATCH candidates per step, stated in `cpu_baseline.sample`.
+
+At N = 1 the line also carries `extra` (driver-run secondary figures, each with its own roofline fraction):
+  fp32_simt   the SAME C4 step on the fp32 / SIMT path (the one that meets the 1e-5 parity bar)
+  C1, C2, C3  the smaller BASELINE.json configurations (R = 10), C1 also through the public sample() API for all 1000 steps
+  C4_4096     BASELINE's full 4096-candidate batch on one GPU
+  C5          fused scoring of 1e5 8-body designs
+and, at every N, `collective_ms`: the path's one collective (score all-gather + replicated top-k), timed with CUDA
+events, max over ranks, and folded into `value` (designs/sec = candidates / (1000 steps + the collective)).
 """
 import argparse
 import ctypes
@@ -40,6 +48,8 @@ PAIRS = N_BODIES * (N_BODIES - 1) // 2
 WINDOWS = N_COMPOSED + 1
 # algorithmic FLOP per slice-forward (nonzero-tap conv MACs + attention MACs, x2)
 FLOP_PER_SLICE = 116_533_248
+WEIGHT_BYTES_16 = 20_762_824 * 2          # U-Net parameters streamed once per evaluation when S is small (C1)
+REF_BATCH = 4                             # candidates per step of the CPU reference arm (bounded sample)
 
 
 def parse_args():
@@ -53,6 +63,7 @@ def parse_args():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary figures (fp32 arm, C1-C3, C4 at 4096, C5)")
     ap.add_argument("--profile", action="store_true", help="also print the per-kernel-class event timings")
     return ap.parse_args()
 
@@ -148,7 +159,7 @@ def workload_config(args, n_gpus):
         "design_guidance": f"standard-recurrence-{args.recurrence}" if args.recurrence > 0 else "standard",
         "compose_mode": "mean-inside", "design_coef": COEF, "consistency_coef": CONS_COEF,
         "ddpm_steps_per_design": DDPM_STEPS,
-        "step": "one DDPM step (R composed evaluations + updates) of the whole per-GPU batch; designs/sec = candidates/(1000*s_per_step)",
+        "step": "one DDPM step (R composed evaluations + updates) of the whole per-GPU batch; designs/sec = candidates/(1000*s_per_step + scoring + score all-gather/top-k)",
         "l2": "inputs larger than L2: each conv layer streams >=132 MB of activations per evaluation",
         "parallelism": f"dp{n_gpus} (independent candidates, no per-step communication)",
     }
@@ -157,25 +168,118 @@ def workload_config(args, n_gpus):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    batch = 2
-    sec = cpu_oracle_step_time(batch, args.recurrence, args.steps, min(args.warmup, 1))
+    batch = REF_BATCH
+    sec = cpu_oracle_step_time(batch, args.recurrence, args.steps, args.warmup)
     value = batch / (DDPM_STEPS * sec)
     cfg = workload_config(args, 1)
     cfg["candidates_per_gpu"] = cfg["candidates_total"] = batch
     cfg["slices_per_evaluation_per_gpu"] = WINDOWS * PAIRS * batch
     line = {
         "impl": "reference", "metric": "composed-sampling designs/sec (8-body, 1000 DDPM steps)", "value": value,
-        "unit": "designs/s", "n_gpus": 0, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+        "unit": "designs/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
         "config": cfg,
         "cpu_baseline": {"value": value, "unit": "designs/s", "cores": os.cpu_count(), "kind": "port",
-                         "sample": f"{batch} candidates x {args.steps} DDPM steps of the C4 shape (R={args.recurrence}), "
-                                   "oracle/sampler_ref.py in the reference's one-forward-per-(window,pair) loop form"},
+                         "sample": f"B={batch} candidates x {args.steps} DDPM steps (+{args.warmup} warm-up) of the C4 shape "
+                                   f"(R={args.recurrence}: {WINDOWS * PAIRS * max(args.recurrence, 1)} U-Net forwards of batch {batch} per step), "
+                                   "oracle/sampler_ref.py (port, fp32) in the reference's one-forward-per-(window,pair) loop form; "
+                                   "the B200 arm runs 512 candidates per GPU"},
         "e2e": {"value": value, "unit": "designs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
+
+
+# --------------------------------------------------------------------------------------------- secondary figures (N = 1)
+def run_extras(args, torch, _lib, L, dif, model, fn, dev, stream, st, peaks):
+    """Driver-run secondary figures, each with its own roofline fraction (see the module docstring)."""
+    from cindm_b200.utils import score_designs
+    tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    eng = model.engine()
+    out = {"peaks": {"tensor_tflops": tensor_peak, "hbm_gbs": hbm_peak,
+                     "source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback (of fallback)"}}
+
+    def time_steps(B, n, nc, guidance, warm, steps):
+        T = HORIZON + nc * START
+        x = torch.empty(B, T, 4 * n, device=dev)
+        _lib.check(L.cindm_fill_initial_noise(_lib.ptr(x), B, T, n, 0, 0, DDPM_STEPS, st))
+
+        def run(t0, k):
+            cfg = dif._sample_config(B, nc, START, n, "mean-inside", fn, guidance, t0, t0 - k + 1, True)
+            _lib.check(L.cindm_sample(eng.handle, ctypes.byref(cfg), _lib.ptr(x), None, None, st))
+
+        run(DDPM_STEPS - 1, warm)
+        stream.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run(DDPM_STEPS - 1 - warm, steps)
+        e1.record(stream)
+        stream.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    def record(name, B, n, nc, R, ms, note):
+        S = (nc + 1) * (n * (n - 1) // 2) * B
+        tf = FLOP_PER_SLICE * S * max(R, 1) / (ms * 1e-3) / 1e12
+        out[name] = {"ms_per_ddpm_step": ms, "designs_per_sec": B / ms, "candidates": B, "slices_per_evaluation": S,
+                     "recurrence": R, "model_tflops": tf, "tensor_roofline_frac": tf / tensor_peak, "note": note}
+        return out[name]
+
+    with torch.cuda.stream(stream):
+        # ---- the smaller BASELINE.json configurations on the throughput path (fp16 operands, tcgen05 convs)
+        dif.precision = model.precision = args.precision
+        dif.conv_engine = model.conv_engine = args.engine
+        g10 = "standard-recurrence-10"
+        for name, (B, n, nc) in {"C1": (50, 2, 0), "C2": (500, 2, 2), "C3": (500, 4, 0)}.items():
+            ms = time_steps(B, n, nc, g10, 4, 40)
+            r = record(name, B, n, nc, 10, ms, f"{n}-body, {nc + 1} window(s), batch {B}, standard-recurrence-10, 40 timed DDPM steps")
+            if name == "C1":
+                # launch / weight-streaming bound: the 41.5 MB of 16-bit weights are read once per evaluation
+                gbs = WEIGHT_BYTES_16 * 10 / (ms * 1e-3) / 1e9
+                r.update({"weight_stream_gbs": gbs, "hbm_roofline_frac_on_weight_bytes": gbs / hbm_peak})
+        # C1 through the public API, all 1000 steps, result read back to the host
+        stream.synchronize()
+        t0 = time.perf_counter()
+        pred = dif.sample(batch_size=50, cond=None, n_composed=0, compose_start_step=START, compose_n_bodies=2,
+                          compose_mode="mean-inside", design_fn=fn, design_guidance=g10).cpu()
+        dt = time.perf_counter() - t0
+        out["C1"]["full_sample_api"] = {"seconds": dt, "designs_per_sec": 50 / dt, "finite": bool(torch.isfinite(pred).all()),
+                                        "note": "GaussianDiffusion1D.sample(batch_size=50, ...) for all 1000 DDPM steps + .cpu()"}
+        # ---- BASELINE's full C4 batch (4096 candidates) on ONE GPU: the per-candidate rate holds
+        ms = time_steps(4096, N_BODIES, N_COMPOSED, g10, 3, 2)
+        record("C4_4096", 4096, N_BODIES, N_COMPOSED, 10, ms, "8-body, 3 windows, 4096 candidates on one GPU, 2 timed DDPM steps")
+        # ---- C5: fused scoring (172-step rollout + MAE + objective) of 1e5 8-body 44-frame designs
+        b = 100000
+        g = torch.Generator(device=dev).manual_seed(0)
+        designs = torch.rand(b, T_TOTAL, 4 * N_BODIES, device=dev, generator=g) * 0.76 + 0.12
+        designs[..., 2::4] -= 0.5
+        designs[..., 3::4] -= 0.5
+        score_designs(designs[:1000])
+        stream.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        mae, obj = score_designs(designs)
+        e1.record(stream)
+        stream.synchronize()
+        ms = e0.elapsed_time(e1)
+        gbs = b * (T_TOTAL * 4 * N_BODIES * 4 + 16) / (ms * 1e-3) / 1e9
+        out["C5"] = {"ms": ms, "designs_per_sec": b / (ms * 1e-3), "designs": b, "algorithmic_gbs": gbs,
+                     "hbm_roofline_frac": gbs / hbm_peak, "nan_designs": int(torch.isnan(mae).sum()),
+                     "note": "cindm_score_designs: one thread per design, fp64 sequential-impulse rollout; latency / local-memory bound, not HBM bound"}
+        del designs
+        # ---- the fp32-grade arm: the SAME C4 step on the fp32 / SIMT path (meets the 1e-5 per-step parity bar)
+        dif.precision = model.precision = "fp32"
+        dif.conv_engine = model.conv_engine = "simt"
+        B = args.candidates
+        ms = time_steps(B, N_BODIES, N_COMPOSED, f"standard-recurrence-{args.recurrence}" if args.recurrence > 0 else "standard", 3, 2)
+        r = record("fp32_simt", B, N_BODIES, N_COMPOSED, args.recurrence, ms,
+                   "same workload as the headline on the fp32 SIMT path (fp32 operands and accumulation), 2 timed DDPM steps")
+        r.update({"dtype": "fp32", "fp32_fma_nominal_tflops": 2 * 128 * 148 * 1.965e9 / 1e12,
+                  "fp32_fma_frac": r["model_tflops"] / (2 * 128 * 148 * 1.965e9 / 1e12)})
+        dif.precision = model.precision = args.precision
+        dif.conv_engine = model.conv_engine = args.engine
+    return out
 
 # --------------------------------------------------------------------------------------------- B200 arm
 def run_b200(args, rank, local_rank, world):
@@ -191,7 +295,9 @@ def run_b200(args, rank, local_rank, world):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+        # NCCL's INFO log (rank / nranks / transport lines) goes to stderr: stdout stays the one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     L = _lib.lib()
@@ -269,22 +375,50 @@ def run_b200(args, rank, local_rank, world):
         barrier()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
 
+    # ---- the end of the job: fused scoring of this rank's designs (rollout + objective + MAE), then the path's ONE
+    #      collective: all-gather of the per-candidate objectives and the same top-k on every rank
+    from cindm_b200.utils import score_designs
+    k_top = min(8, world * B)
+
+    def score_and_select():
+        mae, obj = score_designs(x)
+        score = obj.to(torch.float32).contiguous()
+        if dist is not None:
+            gathered = torch.empty(world * B, device=dev)
+            dist.all_gather_into_tensor(gathered, score)
+        else:
+            gathered = score
+        return torch.topk(torch.nan_to_num(gathered, nan=float("inf")), k=k_top, largest=False)
+
+    with torch.cuda.stream(stream):
+        x.clamp_(-1.0, 1.0)                       # K steps from t = 999 are not finished designs: keep the rollout inputs sane
+        score_and_select()                        # warm-up (NCCL connection set-up happens here)
+        barrier()
+        c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        c0.record(stream)
+        mae_l, obj_l = score_designs(x)
+        c1.record(stream)
+        score = obj_l.to(torch.float32).contiguous()
+        if dist is not None:
+            gathered = torch.empty(world * B, device=dev)
+            dist.all_gather_into_tensor(gathered, score)
+        else:
+            gathered = score
+        top = torch.topk(torch.nan_to_num(gathered, nan=float("inf")), k=k_top, largest=False)
+        c2.record(stream)
+        barrier()
+        score_ms, coll_ms = c0.elapsed_time(c1), c1.elapsed_time(c2)
+
     # ---- max over ranks
-    ms_t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    ms_t = torch.tensor([ms, e2e_s * 1e3, score_ms, coll_ms], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = ms_t.tolist()
+    ms_max, e2e_ms_max, score_ms_max, coll_ms_max = ms_t.tolist()
     sec_per_step = ms_max / 1e3 / steps
     total_cand = B * world
-    value = total_cand / (DDPM_STEPS * sec_per_step)
-    e2e_value = total_cand / (DDPM_STEPS * e2e_ms_max / 1e3)
-
-    # ---- final score all-gather (the path's only collective): one NCCL all-gather of per-candidate objectives
-    if dist is not None:
-        score = ((x[:, -1].reshape(B, N_BODIES, 4)[..., :2] - 0.5).norm(dim=-1)).mean(-1).contiguous()
-        gathered = torch.empty(world * B, device=dev)
-        dist.all_gather_into_tensor(gathered, score)
-        _ = torch.topk(gathered, k=min(8, world * B), largest=False)
+    tail_s = (score_ms_max + coll_ms_max) / 1e3          # once per job, after the 1000 steps
+    value = total_cand / (DDPM_STEPS * sec_per_step + tail_s)
+    e2e_value = total_cand / (DDPM_STEPS * e2e_ms_max / 1e3 + tail_s)
 
     if rank != 0:
         if dist is not None:
@@ -353,17 +487,22 @@ def run_b200(args, rank, local_rank, world):
                 "d2h_bytes_per_step": host_out.numel() * 4,
                 "note": "per DDPM step: pinned host x -> device, cindm_sample (one cached-graph replay), device -> pinned host"},
         "gpu_launches": int(launches), "clocks": clk,
+        "collective_ms": coll_ms_max, "scoring_ms": score_ms_max,
+        "collective": (f"all_gather_into_tensor of {B} fp32 objectives per rank over NCCL + top-{k_top} on every rank" if world > 1
+                       else f"single rank: top-{k_top} only, no communication"),
         "roofline": roofline,
         "model_tflops_per_gpu": FLOP_PER_SLICE * S * max(args.recurrence, 1) / sec_per_step / 1e12,
         "kernel_classes_one_evaluation": classes,
     }
+    if world == 1 and not args.no_extra:
+        line["extra"] = run_extras(args, torch, _lib, L, dif, model, fn, dev, stream, st, peaks)
     if not args.no_cpu_baseline:
         t0 = time.perf_counter()
-        cb, cr = 2, args.recurrence
+        cb, cr = REF_BATCH, args.recurrence
         sec = cpu_oracle_step_time(cb, cr, 1, 0)
         line["cpu_baseline"] = {
             "value": cb / (DDPM_STEPS * sec), "unit": "designs/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{cb} candidates x 1 DDPM step of the C4 shape (R={cr}; {WINDOWS * PAIRS * cr} U-Net forwards of batch {cb}) "
+            "sample": f"B={cb} candidates x 1 DDPM step of the C4 shape (R={cr}; {WINDOWS * PAIRS * max(cr, 1)} U-Net forwards of batch {cb}) "
                       f"with oracle/sampler_ref.py in the reference's loop form, {time.perf_counter() - t0:.0f} s of CPU work"}
     print(json.dumps(line))
     if args.profile:

@@ -30,7 +30,8 @@ class SampleConfig(Structure):
     _fields_ = [("batch", c_int), ("n_bodies", c_int), ("n_composed", c_int), ("compose_start_step", c_int),
                 ("compose_mode", c_int), ("recurrence", c_int), ("precision", c_int), ("conv_engine", c_int),
                 ("t_start", c_int), ("t_end", c_int), ("seed", c_uint64), ("candidate_offset", c_int64),
-                ("use_graph", c_int), ("objective", Objective)]
+                ("use_graph", c_int), ("objective", Objective), ("cond_rows", c_int), ("chain_blocks", c_int),
+                ("ebm_uncond_coef", c_float)]
 
 
 class CindmError(RuntimeError):

@@ -23,9 +23,17 @@ namespace {
 
 // pipeline depth per N tile: as deep as the 227 KB of shared memory allow (A 16 KB + B N*128 B per stage,
 // plus the output staging slabs of the N <= 128 kernels and ~20 KB of vectors / partials / barriers)
-constexpr int stages_for(int n_tile, int cg) {
-    return cg == 2 ? (n_tile == 256 ? 6 : 7) : (n_tile == 256 ? 4 : (n_tile == 192 ? 5 : (n_tile == 128 ? 5 : 6)));
+// OCC == 2 (two CTAs per SM, N <= 128): each CTA gets half of the shared memory and of the tensor memory, so that while
+// one CTA's epilogue warps sit at a barrier or wait for their accumulator the other CTA's can issue.
+constexpr int stages_for(int n_tile, int cg, int occ = 1) {
+    return occ == 2 ? (n_tile == 128 ? 2 : 3)
+                    : (cg == 2 ? (n_tile == 256 ? 6 : 7) : (n_tile == 256 ? 4 : (n_tile == 192 ? 5 : (n_tile == 128 ? 5 : 6))));
 }
+// floats per channel vector in shared memory, and how many vectors (bias | gamma | beta | add): the GroupNorm kernels with
+// N <= 128 always cover all output channels with one N tile; the plain kernels only need the bias (up to 512 channels)
+constexpr int vec_cap_for(int n_tile, int epi, int occ) { return occ == 2 ? (epi == EPI_BIAS ? 512 : n_tile) : 512; }
+constexpr int vec_count_for(int epi, int occ) { return (occ == 2 && epi == EPI_BIAS) ? 1 : 4; }
+constexpr int part_floats_for(int epi, int occ) { return (occ == 2 && epi == EPI_BIAS) ? 0 : 2048 + 704; }
 // warp 0 TMA, warp 1 MMA, then the epilogue warps: 4*PARTS of them, PARTS per TMEM lane quarter, each owning 1/PARTS of
 // the tile's columns.  PARTS = 2 everywhere: 4 (16 epilogue warps) was measured slower (96-register cap, spills).
 constexpr int epi_warps_for(int /*n_tile*/, int /*epi*/) { return 8; }
@@ -51,12 +59,13 @@ struct TcParams {
 };
 
 // ------------------------------------------------------------------ the kernel
-template <typename T16, int N_TILE, int CPG, int EPI, int CG>
-__global__ void __launch_bounds__(threads_for(N_TILE, EPI), 1)
+template <typename T16, int N_TILE, int CPG, int EPI, int CG, int OCC>
+__global__ void __launch_bounds__(threads_for(N_TILE, EPI), OCC)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out, const TcParams p) {
     // CG == 2: two CTAs of a cluster form one 256 x N_TILE MMA; each stages its own 128 A rows and N_TILE/2 rows of B
-    constexpr int kStages = stages_for(N_TILE, CG);
+    static_assert(OCC == 1 || (CG == 1 && N_TILE <= 128 && EPI != EPI_GN_MISH_T3), "two CTAs per SM: single-CTA N <= 128 kernels only");
+    constexpr int kStages = stages_for(N_TILE, CG, OCC);
     constexpr int kBTileBytes = N_TILE * 128 / CG;
     constexpr int kStageBytes = kATileBytes + kBTileBytes;
     constexpr int ACC_STRIDE = (N_TILE == 192) ? 256 : N_TILE;        // TMEM columns between the two accumulators
@@ -68,12 +77,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     uint8_t* tiles = smem;                                             // kStages x (A | B)
     constexpr int kStagingBytes = (N_TILE <= 128) ? (N_TILE / 64) * kATileBytes : 0;   // [N_TILE/64 slabs][128 rows][128 B]
     uint8_t* staging = smem + kStages * kStageBytes;                   // 1024-byte aligned (stage sizes are multiples of 1 KB)
+    constexpr int VC = vec_cap_for(N_TILE, EPI, OCC), VN = vec_count_for(EPI, OCC);
     float* vec_bias = reinterpret_cast<float*>(staging + kStagingBytes);
-    float* vec_gamma = vec_bias + 512;
-    float* vec_beta = vec_gamma + 512;
-    float* vec_add = vec_beta + 512;
-    float* part = vec_add + 512;                                       // GroupNorm partial sums [128][8] float2 + totals [43][8] float2
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(part + 2048 + 704);
+    float* vec_gamma = vec_bias + (VN == 4 ? VC : 0);                  // (the plain kernels at OCC == 2 keep the bias only)
+    float* vec_beta = vec_gamma + (VN == 4 ? VC : 0);
+    float* vec_add = vec_beta + (VN == 4 ? VC : 0);
+    float* part = vec_bias + VN * VC;                                  // GroupNorm partial sums [128][8] float2 + totals [43][8] float2
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(part + part_floats_for(EPI, OCC));
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full = empty_bar + kStages;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -94,7 +104,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         tma_prefetch_desc(&map_a0);
         tma_prefetch_desc(&map_b);
     }
-    if (warp == 1) { if (CG == 2) tmem_alloc_pair(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
+    constexpr uint32_t kTmemCols = OCC == 2 ? 2 * ACC_STRIDE : 512;    // (a power of two >= 32: 128 or 256 at OCC == 2)
+    if (warp == 1) { if (CG == 2) tmem_alloc_pair(tmem_slot, kTmemCols); else tmem_alloc(tmem_slot, kTmemCols); }
     // everything above depends on nothing; the previous kernel of the chain must be complete before any global access
     pdl_wait();
     pdl_trigger();
@@ -105,7 +116,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         for (int c = threadIdx.x; c < p.cout; c += blockDim.x) {
             vec_bias[c] = p.bias ? p.bias[c] : 0.f;
             if (HAS_GN) { vec_gamma[c] = p.gamma[c]; vec_beta[c] = p.beta[c]; }
-            vec_add[c] = addv ? addv[c] : 0.f;
+            if (VN == 4) vec_add[c] = addv ? addv[c] : 0.f;
         }
     }
     tc_fence_before();
@@ -301,7 +312,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             tc_fence_after();
             const uint32_t taddr = lane_base + (uint32_t)(acc * ACC_STRIDE);
             // accumulator values are read from TMEM once when they fit in registers (<= 64 columns per thread)
-            constexpr bool KEEP = HAS_GN && (NCHUNK == 1 || (NCHUNK == 2 && EW == 8));
+            constexpr bool KEEP = HAS_GN && (NCHUNK == 1 || (NCHUNK == 2 && EW == 8 && OCC == 1));   // (96-register budget at OCC == 2)
             float vk[KEEP ? NCHUNK : 1][32];
             float v[32];
             float g_sc[HG], g_sh[HG];                             // per group: rstd and -mean * rstd
@@ -329,12 +340,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
                 for (int g = 0; g < HG; ++g) pr[row * 8 + half * HG + g] = make_float2(s1[g], s2[g]);
                 asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
-                if (row < p.rows_used) {
-                    for (int g = row_in_slice; g < HG; g += p.H) {
+                {
+                    // (slice, group) totals, each the sum of H row partials.  A team of TS adjacent lanes owns one total:
+                    // every member adds H / TS consecutive rows in order and the members are combined by a fixed
+                    // shuffle tree, so the association order depends on h only.
+                    constexpr int G = N_TILE / CPG;                                  // groups per N tile
+                    const int n_tot = p.slices_per_tile * G;
+                    const int ts = (p.H % 4 == 0 && n_tot * 4 <= EW * 32) ? 4 : ((p.H % 2 == 0 && n_tot * 2 <= EW * 32) ? 2 : 1);
+                    const int per = p.H / ts;
+                    for (int base = 0; base < n_tot * ts; base += EW * 32) {
+                        const int item = base + et;
+                        const bool live = item < n_tot * ts;
+                        const int tid = live ? item / ts : 0, part = live ? item - tid * ts : 0;
+                        const int tsl = tid / G, tg = tid - tsl * G;
                         float a = 0.f, b2 = 0.f;
-                        const float2* src = pr + (sl * p.H) * 8 + half * HG + g;
-                        for (int h = 0; h < p.H; ++h) { const float2 t = src[h * 8]; a += t.x; b2 += t.y; }
-                        tot[sl * 8 + half * HG + g] = make_float2(a, b2);
+                        const float2* src = pr + (tsl * p.H + part * per) * 8 + tg;
+                        if (live)
+                            for (int h = 0; h < per; ++h) { const float2 t = src[h * 8]; a += t.x; b2 += t.y; }
+                        if (ts >= 2) { a += __shfl_xor_sync(0xffffffffu, a, 1); b2 += __shfl_xor_sync(0xffffffffu, b2, 1); }
+                        if (ts == 4) { a += __shfl_xor_sync(0xffffffffu, a, 2); b2 += __shfl_xor_sync(0xffffffffu, b2, 2); }
+                        if (live && part == 0) tot[tsl * 8 + tg] = make_float2(a, b2);
                     }
                 }
                 if (stage_out && et == 0) tma_store_wait_read();  // staging is free again after this barrier
@@ -461,28 +486,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     if (CG == 2) cluster_sync_all(); else __syncthreads();      // nobody leaves while its partner may still touch its smem / TMEM
     if (warp == 1) {
         tc_fence_after();
-        if (CG == 2) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+        if (CG == 2) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
 // ------------------------------------------------------------------ host side
-template <int N_TILE, int CG>
+template <int N_TILE, int CG, int OCC, int EPI>
 constexpr size_t smem_bytes_for() {
-    return 1024 + (size_t)stages_for(N_TILE, CG) * (kATileBytes + N_TILE * 128 / CG) + (N_TILE <= 128 ? (N_TILE / 64) * kATileBytes : 0) +
-           4 * 512 * 4 + (2048 + 704) * 4 + (2 * stages_for(N_TILE, CG) + 4) * 8 + 16;
+    return 1024 + (size_t)stages_for(N_TILE, CG, OCC) * (kATileBytes + N_TILE * 128 / CG) + (N_TILE <= 128 ? (N_TILE / 64) * kATileBytes : 0) +
+           (size_t)vec_count_for(EPI, OCC) * vec_cap_for(N_TILE, EPI, OCC) * 4 + (size_t)part_floats_for(EPI, OCC) * 4 +
+           (2 * stages_for(N_TILE, CG, OCC) + 4) * 8 + 16;
 }
 
-template <typename T16, int N_TILE, int CPG, int EPI, int CG>
+template <typename T16, int N_TILE, int CPG, int EPI, int CG, int OCC = 1>
 int launch_instance(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& mo, const TcParams& p,
                     cudaStream_t st) {
-    auto kern = conv_tc_kernel<T16, N_TILE, CPG, EPI, CG>;
-    constexpr size_t smem = smem_bytes_for<N_TILE, CG>();
+    auto kern = conv_tc_kernel<T16, N_TILE, CPG, EPI, CG, OCC>;
+    constexpr size_t smem = smem_bytes_for<N_TILE, CG, OCC, EPI>();
+    static_assert(OCC == 1 || smem <= 113 * 1024, "two CTAs per SM need <= 113 KB of shared memory each");
     static DeviceOnce once;
     if (once.first_time()) {
         CINDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     const int tiles = ((p.m_tiles + CG - 1) / CG) * p.n_tiles;          // (pair-)tiles
-    const int slots = num_sms() / CG;                                   // clusters that fit on the machine
+    const int slots = num_sms() * OCC / CG;                             // CTAs (clusters) resident on the machine at once
     const int grid = (tiles < slots ? tiles : slots) * CG;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads_for(N_TILE, EPI)); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -495,6 +522,15 @@ int launch_instance(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensor
     CINDM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a0, a1, b, mo, p));
     CINDM_CHECK_LAUNCH();
     return 0;
+}
+
+// two CTAs per SM for the N = 64 kernels (measured, same box: 64->64@H24 GroupNorm conv 0.145 -> 0.125 ms, the N = 64 plain
+// convs -5..-10 %; the N = 128 kernels got 10-15 % SLOWER with the two 32 KB stages that fit, so they stay at one CTA
+// per SM); CINDM_CONV_OCC2=0 selects the one-CTA-per-SM variant (A/B runs)
+bool occ2_mode() {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("CINDM_CONV_OCC2"); mode = (e && e[0] == '0') ? 0 : 1; }
+    return mode == 1;
 }
 
 // CTA-pair (cta_group::2) MMA for the N >= 192 kernels; CINDM_CONV_PAIR=0 selects the single-CTA variant (A/B runs)
@@ -518,7 +554,8 @@ int dispatch(const ConvTcLaunch& a, const CUtensorMap& m0, const CUtensorMap& m1
     }
     if (a.epilogue == EPI_GN_MISH) {
         switch (p.cout) {
-            case 64: return launch_instance<T16, 64, 8, EPI_GN_MISH, 1>(m0, m1, mb, mo, p, st);
+            case 64: return occ2_mode() ? launch_instance<T16, 64, 8, EPI_GN_MISH, 1, 2>(m0, m1, mb, mo, p, st)
+                                        : launch_instance<T16, 64, 8, EPI_GN_MISH, 1>(m0, m1, mb, mo, p, st);
             case 128: return launch_instance<T16, 128, 16, EPI_GN_MISH, 1>(m0, m1, mb, mo, p, st);
             case 256: return pair_mode() ? launch_instance<T16, 256, 32, EPI_GN_MISH, 2>(m0, m1, mb, mo, p, st)
                                          : launch_instance<T16, 256, 32, EPI_GN_MISH, 1>(m0, m1, mb, mo, p, st);
@@ -528,7 +565,8 @@ int dispatch(const ConvTcLaunch& a, const CUtensorMap& m0, const CUtensorMap& m1
         return fail(-2, "conv_tc: unsupported channel count for the GroupNorm epilogue");
     }
     switch (n_tile) {
-        case 64: return launch_instance<T16, 64, 8, EPI_BIAS, 1>(m0, m1, mb, mo, p, st);
+        case 64: return occ2_mode() ? launch_instance<T16, 64, 8, EPI_BIAS, 1, 2>(m0, m1, mb, mo, p, st)
+                                    : launch_instance<T16, 64, 8, EPI_BIAS, 1>(m0, m1, mb, mo, p, st);
         case 128: return launch_instance<T16, 128, 8, EPI_BIAS, 1>(m0, m1, mb, mo, p, st);
         case 256: return launch_instance<T16, 256, 8, EPI_BIAS, 1>(m0, m1, mb, mo, p, st);
     }

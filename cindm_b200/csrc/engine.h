@@ -197,11 +197,16 @@ struct UpdateLaunch {
     int ddim = 0; const float* ddim_coef = nullptr; const int* step_dev = nullptr;
     // "mean" (outside) composition: the posterior mean and x_start are inputs (eps is not read)
     const float* mean_in = nullptr; const float* x0_in = nullptr;
+    // conditioned models: frames [0, cond_rows) of every candidate are the condition: copied through unchanged, and an
+    // explicit noise tensor only covers the T - cond_rows sampled frames
+    int cond_rows = 0;
 };
 int launch_update(const UpdateLaunch& u, cudaStream_t st);
 int launch_fill_noise(float* x, int B, int T, int n, uint64_t seed, int64_t cand_off, int t, int draw,
                       cudaStream_t st);
 int launch_step_counter(int* t_dev, int delta, cudaStream_t st);
+// composing_time_sample (:1827-1829): block k+1's first cond_rows frames <- block k's last cond_rows frames
+int launch_chain_condition(float* x, int rows_per_block, int blocks, int T, int n, int cond_rows, cudaStream_t st);
 int sample_ddim(cindm_engine* e, const cindm_sample_config& c, int n_pairs, const int32_t* times, const int32_t* times_next,
                 const float* coef3, float* x, const float* noise, float* x0_out, cudaStream_t caller);
 

@@ -75,6 +75,35 @@ int launch_step_counter(int* t_dev, int delta, cudaStream_t st) {
     return 0;
 }
 
+// ---------------------------------------------------------------- chained conditions (composing_time_sample :1827-1829)
+__global__ void __launch_bounds__(256) chain_condition_kernel(float4* __restrict__ x, int rows_per_block, int blocks, int T, int n,
+                                                              int cond_rows) {
+    pdl_wait();
+    pdl_trigger();
+    const long long per = (long long)rows_per_block * cond_rows * n;          // float4 per block
+    const long long total = per * (blocks - 1);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i / per) + 1;                                     // destination block
+        long long r = i - (long long)(k - 1) * per;
+        const int j = (int)(r % n); r /= n;
+        const int row = (int)(r % cond_rows);
+        const long long b = r / cond_rows;
+        const long long src = (((long long)(k - 1) * rows_per_block + b) * T + (T - cond_rows + row)) * n + j;
+        const long long dst = (((long long)k * rows_per_block + b) * T + row) * n + j;
+        x[dst] = x[src];
+    }
+}
+
+int launch_chain_condition(float* x, int rows_per_block, int blocks, int T, int n, int cond_rows, cudaStream_t st) {
+    if (blocks < 2 || cond_rows <= 0) return 0;
+    const long long total = (long long)rows_per_block * cond_rows * n * (blocks - 1);
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    CINDM_CHECK_CUDA(launch_chain(chain_condition_kernel, dim3(grid), dim3(256), 0, st, (float4*)x, rows_per_block, blocks, T, n, cond_rows));
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
 // ---------------------------------------------------------------- objective gradient (closed form)
 // J = coef * sum_b sum_j d(p[b,T-1,j], target) + cc * sum_b mean_t sum_{j,xy} (p[t+1]-p[t])^2
 //   d = ||.||_2 (L2) or ||.||^2 (L2square); the distance term is evaluated in fp64 because the
@@ -146,6 +175,7 @@ struct UpdateParams {
     cindm_objective obj;
     int ddim; const float* ddim_coef; const int* step_dev;
     const float* mean_in; const float* x0_in;
+    int cond_rows;
 };
 
 __global__ void __launch_bounds__(256) ddpm_update_kernel(UpdateParams p) {
@@ -182,9 +212,10 @@ __global__ void __launch_bounds__(256) ddpm_update_kernel(UpdateParams p) {
     }
     const bool have_noise = nb != 0.f && (p.noise != nullptr || p.use_philox);
     const float4* noise = nullptr;
+    const int Tn = p.T - p.cond_rows;                               // frames an explicit noise tensor covers
     if (p.noise)
         noise = reinterpret_cast<const float4*>(
-            p.noise + ((long long)step * p.draws_per_step + p.draw) * ((long long)p.B * p.T * p.n * 4));
+            p.noise + ((long long)step * p.draws_per_step + p.draw) * ((long long)p.B * Tn * p.n * 4));
 
     const long long total = (long long)p.B * p.T * p.n;
     const int F = 4 * p.n;
@@ -195,6 +226,12 @@ __global__ void __launch_bounds__(256) ddpm_update_kernel(UpdateParams p) {
         int tt = (int)(bt % p.T);
         long long b = bt / p.T;
         float4 xv = reinterpret_cast<const float4*>(p.x)[i];
+        if (tt < p.cond_rows) {                                   // condition frames: seen by the model, never updated
+            reinterpret_cast<float4*>(p.x_out)[i] = xv;
+            if (p.pred_out) reinterpret_cast<float4*>(p.pred_out)[i] = xv;
+            if (p.x0_out) reinterpret_cast<float4*>(p.x0_out)[i] = xv;
+            continue;
+        }
         float4 ev = p.mean_in ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<const float4*>(p.eps)[i];
         float xs[4] = {xv.x, xv.y, xv.z, xv.w}, es[4] = {ev.x, ev.y, ev.z, ev.w};
         float mi[4] = {0.f, 0.f, 0.f, 0.f}, x0i[4] = {0.f, 0.f, 0.f, 0.f};
@@ -210,7 +247,8 @@ __global__ void __launch_bounds__(256) ddpm_update_kernel(UpdateParams p) {
             if (p.obj.guidance == CINDM_GUIDE_STANDARD_ALPHA) { g[0] = __fmul_rn(gscale, g[0]); g[1] = __fmul_rn(gscale, g[1]); }
         }
         float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (have_noise) nz = noise ? noise[i] : noise4(p.seed, p.cand_off + b, (int)(i - b * vec_per_cand), t, p.draw);
+        if (have_noise)
+            nz = noise ? noise[(b * Tn + (tt - p.cond_rows)) * p.n + j] : noise4(p.seed, p.cand_off + b, (int)(i - b * vec_per_cand), t, p.draw);
         float ns[4] = {nz.x, nz.y, nz.z, nz.w};
         float x0[4], pr[4], out[4];
 #pragma unroll
@@ -248,6 +286,8 @@ int launch_update(const UpdateLaunch& u, cudaStream_t st) {
     p.obj = u.obj;
     p.ddim = u.ddim; p.ddim_coef = u.ddim_coef; p.step_dev = u.step_dev;
     p.mean_in = u.mean_in; p.x0_in = u.x0_in;
+    p.cond_rows = u.cond_rows;
+    if (u.cond_rows < 0 || u.cond_rows >= u.T) return fail(-2, "cond_rows must be in [0, T)");
     if ((u.mean_in == nullptr) != (u.x0_in == nullptr)) return fail(-2, "composed posterior mean and x_start come together");
     if (u.mean_in && u.ddim) return fail(-5, "DDIM runs on the *-inside composition only (reference ddim_sample :1758-1771)");
     if (u.ddim && (!u.ddim_coef || !u.step_dev)) return fail(-2, "DDIM update needs the coefficient table and the step counter");
@@ -329,6 +369,8 @@ static int issue_step(cindm_engine* e, const cindm_sample_config& c, float* bufs
                                       (const int*)e->sb.step_dev));
         CINDM_CHECK_LAUNCH();
     }
+    if (c.chain_blocks > 1)
+        CINDM_TRY(launch_chain_condition(bufs[cur], c.batch / c.chain_blocks, c.chain_blocks, T, c.n_bodies, c.cond_rows, st));
     for (int r = 0; r < iters; ++r) {
         const bool outside = c.compose_mode == CINDM_COMPOSE_MEAN_OUTSIDE;
         CINDM_TRY(composed_eps(e, bufs[cur], e->sb.eps, c.batch, c.n_bodies, c.n_composed, c.compose_start_step,
@@ -343,6 +385,7 @@ static int issue_step(cindm_engine* e, const cindm_sample_config& c, float* bufs
         u.noise = noise; u.t_start = c.t_start; u.draws_per_step = draws;
         u.use_philox = noise == nullptr; u.seed = c.seed; u.cand_off = c.candidate_offset;
         u.obj = c.objective;
+        u.cond_rows = c.cond_rows;
         // the reference re-noises after the last recurrence too and then discards it (:1365-1370):
         // the last evaluation goes straight to the final posterior noise (draw id R)
         u.renoise = (c.recurrence > 0 && !last) ? 1 : 0;
@@ -356,6 +399,15 @@ static int issue_step(cindm_engine* e, const cindm_sample_config& c, float* bufs
         cur ^= 1;
     }
     if (ddim) CINDM_TRY(launch_step_counter(e->sb.step_dev, 1, st));
+    return 0;
+}
+
+static int check_condition_config(const cindm_sample_config& c, int T) {
+    if (c.cond_rows < 0 || c.cond_rows >= T) return fail(-2, "cond_rows must be in [0, T)");
+    if (c.chain_blocks > 1 && (c.cond_rows == 0 || c.batch % c.chain_blocks != 0))
+        return fail(-2, "chain_blocks needs cond_rows > 0 and a batch that is a multiple of chain_blocks");
+    if (c.cond_rows > 0 && c.objective.guidance != CINDM_GUIDE_NONE)
+        return fail(-5, "design guidance on a conditioned model is not on the CUDA fast path");
     return 0;
 }
 
@@ -390,6 +442,7 @@ static int sample_loop_on(cindm_engine* e, const cindm_sample_config& c, float* 
     if (c.compose_start_step >= e->cfg.horizon) return fail(-2, "compose_start_step must be < horizon");   // (:1679)
     if (c.batch <= 0) return fail(-2, "batch must be positive");
     const int T = e->cfg.horizon + c.n_composed * c.compose_start_step;
+    CINDM_TRY(check_condition_config(c, T));
     const size_t elems = (size_t)c.batch * T * c.n_bodies * 4;
     const int64_t S = (int64_t)(c.n_composed + 1) * (c.n_bodies * (c.n_bodies - 1) / 2) * c.batch;
     CINDM_TRY(reserve_workspace(e, S > e->ws.max_slices ? S : e->ws.max_slices, c.precision));
@@ -467,6 +520,7 @@ static int sample_ddim_on(cindm_engine* e, const cindm_sample_config& c, int n_p
     for (int i = 0; i < n_pairs; ++i)
         if (times[i] < 0 || times[i] >= e->cfg.timesteps) return fail(-2, "DDIM timestep out of range");
     const int T = e->cfg.horizon + c.n_composed * c.compose_start_step;
+    CINDM_TRY(check_condition_config(c, T));
     const size_t elems = (size_t)c.batch * T * c.n_bodies * 4;
     const int64_t S = (int64_t)(c.n_composed + 1) * (c.n_bodies * (c.n_bodies - 1) / 2) * c.batch;
     CINDM_TRY(reserve_workspace(e, S > e->ws.max_slices ? S : e->ws.max_slices, c.precision));

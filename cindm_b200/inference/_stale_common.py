@@ -49,7 +49,7 @@ def build_diffusion(args, device):
     model = TemporalUnet1D(horizon=horizon, transition_dim=2 * args.num_features, cond_dim=False, dim=64,
                            dim_mults=(1, 2, 4, 8), attention=args.attention, seed=args.seed)
     diffusion = GaussianDiffusion1D(model, image_size=horizon, conditioned_steps=0, timesteps=1000,
-                                    sampling_timesteps=1000, loss_type="l1").to(device)
+                                    sampling_timesteps=args.sample_steps, loss_type="l1").to(device)
     if args.checkpoint_path_basic_model:
         ckpt = torch.load(args.checkpoint_path_basic_model, map_location="cpu")
         diffusion.load_state_dict(ckpt["model"])

@@ -17,6 +17,9 @@ Differences, all forced by the environment or by the B200 design:
     with no per-step communication; per-candidate scores are collected with ONE NCCL all-gather and every rank
     takes the same top-k (the reference only ever takes the minimum, :382-386).
   * extra flags: --precision {fp32,fp16,bf16}, --conv_engine {simt,tcgen05}, --checkpoint, --results_dir, --top_k.
+  * flag defaults are the reference's, including the two that make the reference fail when left unset: `--model_name`
+    defaults to 'basic-model' (no branch of :141-156 matches it) and `--design_guidance` has no default; both raise here
+    with a message naming the accepted values.
 
     python -m cindm_b200.inference.inverse_design_diffusion_1d --n_composed=2 --compose_n_bodies=8 \
         --compose_mode=mean-inside --design_guidance=standard-recurrence-10 --design_coef=0.2 \
@@ -46,7 +49,7 @@ def build_parser():
     parser.add_argument("--date_time", default="09-23", type=str, help="date for the experiment folder")
     parser.add_argument("--dataset", default="nbody-2", type=str, help="dataset to evaluate")
     parser.add_argument("--model_type", default="temporal-unet1d", type=str, help="model type.")
-    parser.add_argument("--model_name", default="Diffusion_cond-0_rollout-24_bodies-2", type=str, help="model type.")
+    parser.add_argument("--model_name", default="basic-model", type=str, help="model type.")
     parser.add_argument("--conditioned_steps", default=4, type=int, help="conditioned steps")
     parser.add_argument("--rollout_steps", default=20, type=int, help="rollout steps")
     parser.add_argument("--time_interval", default=4, type=int, help="time interval")
@@ -54,13 +57,13 @@ def build_parser():
     parser.add_argument("--is_test", default=True, type=str2bool_reference, help="flag for testing")
     parser.add_argument("--sample_steps", default=1000, type=int, help="sample steps")
     parser.add_argument("--num_features", default=4, type=int, help="features per body")
-    parser.add_argument("--dataset_path", default="dataset/nbody_dataset", type=str, help="the path to load dataset")
+    parser.add_argument("--dataset_path", default=os.getcwd() + "/dataset/nbody_dataset", type=str, help="the path to load dataset")
     parser.add_argument("--gpuid", default=0, type=int, help="the id of gpu to use")
     parser.add_argument("--n_composed", default=0, type=int, help="how many prediction to be composed")
     parser.add_argument("--compose_start_step", default=10, type=int, help="Starting step of composition.")
     parser.add_argument("--compose_n_bodies", default=2, type=int, help="Number of total bodies.")
-    parser.add_argument("--design_guidance", type=str, default="standard-recurrence-10", help="string for list of design_guidance")
-    parser.add_argument("--compose_mode", default="mean-inside", type=str, help='"mean-inside" or "sum-inside"')
+    parser.add_argument("--design_guidance", type=str, help="string for list of design_guidance")
+    parser.add_argument("--compose_mode", default="mean", type=str, help='"mean" or "noise_sum"')
     parser.add_argument("--design_fn_mode", default="L2", type=str, help='Choose from "L2" and "L2square".')
     parser.add_argument("--design_coef", default="0.05", type=str, help="Coefficient for the design_fn")
     parser.add_argument("--consistency_coef", default="0.05", type=str, help="Coefficient for the consistency regularization")
@@ -80,13 +83,41 @@ def build_parser():
     return parser
 
 
+FAST_PATH_MODELS = ("Diffusion_cond-0_rollout-24_bodies-2", "Diffusion_cond-0_rollout-24_bodies-2_more_collision")
+
+
 def model_horizon(args):
-    """model_name -> (rollout_steps, conditioned_steps), as hard-wired in the reference (:141-156)."""
-    if args.model_name in ("Diffusion_cond-0_rollout-24_bodies-2", "Diffusion_cond-0_rollout-24_bodies-2_more_collision"):
+    """model_name -> (rollout_steps, conditioned_steps), as hard-wired in the reference (:141-156).
+
+    The reference's own default, 'basic-model', matches none of its branches ('basic_model' is spelled with an
+    underscore there) and ends in a bare `raise`; here every name that is not on the CUDA fast path fails with a
+    message that says which names are."""
+    if args.model_name in FAST_PATH_MODELS:
         return 24, 0
     if args.model_name in ("Diffusion_cond-0_rollout-44_bodies-2", "Diffusion_cond-0_rollout-44_bodies-2_Unet_dim-96"):
         raise NotImplementedError("the 44-step models use a different U-Net layout (horizon % 8 != 0): not on the CUDA fast path")
-    raise NotImplementedError(f"model_name {args.model_name!r}: only the cond-0 rollout-24 2-body models are on the CUDA fast path")
+    if args.model_name in ("basic_model", "single_step_model"):
+        raise NotImplementedError(
+            f"model_name {args.model_name!r} is a conditioned model (conditioned_steps=4): this driver samples with cond=None; "
+            "the conditioned 4+20-frame model runs through cindm_b200.inference.inference_1d_composing_time_steps")
+    raise NotImplementedError(
+        f"model_name {args.model_name!r}: the reference driver raises here too (:155-156; its default 'basic-model' matches no "
+        f"branch). Pass --model_name={FAST_PATH_MODELS[0]} (or ..._more_collision), the models on the CUDA fast path")
+
+
+def guidance_list(args):
+    """--design_guidance has no default in the reference (:82) and the driver splits it unconditionally (:283)."""
+    if not args.design_guidance:
+        raise ValueError("--design_guidance is required (the reference has no default and fails on None.split(',')): "
+                         "e.g. --design_guidance=standard-recurrence-10")
+    return args.design_guidance.split(",")
+
+
+def sample_stream_seed(seed, call_index):
+    """Philox key of the call_index-th sample() call of a run: all sampler noise is keyed by (seed, global candidate id, t,
+    draw), so repeated calls must not reuse a key or every --num_batchs / --batch_size_list / guidance / coefficient
+    iteration would replay the same designs (the reference draws fresh torch.randn numbers each time)."""
+    return (int(seed) + 0x9E3779B97F4A7C15 * int(call_index)) & 0xFFFFFFFFFFFFFFFF
 
 
 def distributed_context():
@@ -141,13 +172,18 @@ def run(args):
     else:
         device = torch.device("cuda", args.gpuid)
     rollout_steps, conditioned_steps = model_horizon(args)
+    guidances = guidance_list(args)
+    for batch_size_val in ast.literal_eval(args.batch_size_list):
+        if batch_size_val < world:          # an empty shard would leave its rank out of the collectives
+            raise ValueError(f"batch size {batch_size_val} is smaller than the number of ranks ({world})")
     setup_seed(args.seed)
     model = TemporalUnet1D(horizon=conditioned_steps + rollout_steps, transition_dim=2 * args.num_features, cond_dim=False,
                            dim=args.Unet_dim, dim_mults=(1, 2, 4, 8), attention=True, seed=args.seed)
     diffusion = GaussianDiffusion1D(model, image_size=rollout_steps, conditioned_steps=conditioned_steps, timesteps=1000,
                                     sampling_timesteps=args.sample_steps, loss_type="l1").to(device)
     if args.checkpoint:
-        ckpt = torch.load(args.checkpoint, map_location="cpu")
+        # reference Trainer1D checkpoints hold optimizer / EMA / GradScaler state next to "model" (:2635-2647)
+        ckpt = torch.load(args.checkpoint, map_location="cpu", weights_only=False)
         diffusion.load_state_dict(ckpt["model"])
     diffusion.precision, diffusion.conv_engine = args.precision, args.conv_engine
     diffusion.seed = args.seed
@@ -169,6 +205,7 @@ def run(args):
                              f"[B, {output_steps}, {4 * args.compose_n_bodies}]")
 
     results = []
+    sample_calls = 0          # every sample() call draws from its own Philox stream, like fresh torch.randn calls do
     for sample_steps in ast.literal_eval(args.sample_steps_list):
         diffusion.sampling_timesteps = sample_steps
         # as in the reference, --batch_size_list overrides --val_batch_size (:271-272)
@@ -176,12 +213,14 @@ def run(args):
             best_loss_sum = 0.0
             for _ in range(args.num_batchs):
                 pos_target = torch.tensor([0.5, 0.5], device=device, dtype=torch.float64)
-                for design_guidance in args.design_guidance.split(","):
+                for design_guidance in guidances:
                     for design_coef in (float(v) for v in args.design_coef.split(",")):
                         for consistency_coef in (float(v) for v in args.consistency_coef.split(",")):
                             lo, hi = shard(batch_size_val, rank, world)
                             counts = [shard(batch_size_val, r, world)[1] - shard(batch_size_val, r, world)[0] for r in range(world)]
                             diffusion.candidate_offset = lo
+                            diffusion.seed = sample_stream_seed(args.seed, sample_calls)
+                            sample_calls += 1
                             design_fn = get_design_fn(pos_target.cpu(), last_n_step=1, coef=design_coef,
                                                       time_consistency_coef=consistency_coef, design_fn_mode=args.design_fn_mode)
                             torch.cuda.synchronize(device)

@@ -168,7 +168,9 @@ class _Engine:
     def close(self):
         if self.handle:
             try:
-                _lib.lib().cindm_destroy(self.handle)
+                # cindm_destroy synchronises and frees on the CURRENT device: make it the engine's own
+                with torch.cuda.device(self.device):
+                    _lib.lib().cindm_destroy(self.handle)
             finally:
                 self.handle = ctypes.c_void_p()
 
@@ -516,20 +518,25 @@ class GaussianDiffusion1D:
     def ddim_sample(self, shape, cond, n_composed=None, clip_denoised=True, compose_start_step=4, compose_n_bodies=2,
                     compose_mode="mean", design_fn=None, design_guidance="standard", initial_state_overwrite=None,
                     initialization_mode=0, initialization_img=None, noise=None, img=None, pairs=None):
-        """DDIM sampling (reference :1723-1804).  The reference draws img = randn(shape) with shape = (B, image_size,
-        channels), so at HEAD it only runs for n_composed = 0, compose_n_bodies = 2; here the same loop runs on the
-        composed shape [B, image_size + n_composed * compose_start_step, 4 * compose_n_bodies] and is identical on the
-        reference's subset.  Like the reference it ignores initialization_mode / initialization_img.  `img` / `noise`
+        """DDIM sampling (reference :1723-1804).  Without design_fn the composition arguments are ignored, as in the
+        reference (plain model_predictions on [B, image_size, channels]).  With design_fn the reference draws
+        img = randn(shape) with shape = (B, image_size, channels) and then composes, so at HEAD it only runs for
+        n_composed = 0, compose_n_bodies = 2; here the same loop also runs on the composed shape
+        [B, image_size + n_composed * compose_start_step, 4 * compose_n_bodies] (a documented widening, identical on the
+        reference's subset).  Like the reference it ignores initialization_mode / initialization_img.  `img` / `noise`
         (optional) replace the Philox draws for parity runs: noise is [pairs, draws, B, T, F] with draws = R + 2
         (R re-noise draws, the unused posterior draw, the DDIM draw) with guidance, 1 without."""
         if cond is not None or initial_state_overwrite is not None or not clip_denoised:
             raise NotImplementedError("cond / initial_state_overwrite / clip_denoised=False are not on the CUDA fast path")
         n_composed = 0 if n_composed is None else n_composed
-        if "inside" not in compose_mode:
-            if design_fn is None and n_composed == 0 and compose_n_bodies == 2:
-                compose_mode = "mean-inside"      # model_predictions without composition == the 1-window, 1-pair operator
-            else:
-                raise NotImplementedError(f"compose_mode {compose_mode!r}: only the *-inside operators are on the CUDA fast path")
+        if design_fn is None:
+            # the reference calls model_predictions(img, cond, t) WITHOUT the composition kwargs here (:1754-1755): it ignores
+            # n_composed / compose_n_bodies / compose_mode and denoises [B, image_size, channels] with the plain 2-body
+            # model, which is the 1-window, 1-pair operator
+            n_composed, compose_n_bodies, compose_mode = 0, self.channels // 4, "mean-inside"
+        elif "inside" not in compose_mode:
+            raise NotImplementedError(f"compose_mode {compose_mode!r}: with guidance only the *-inside operators run under DDIM "
+                                      "(reference ddim_sample :1757-1771 always calls p_sample_compose_inside)")
         eng = self.model.engine()
         b = shape[0]
         t_total = shape[1] + n_composed * compose_start_step

@@ -73,6 +73,15 @@ typedef struct {
     int64_t candidate_offset; /* global id of local candidate 0 (sharding-invariant noise) */
     int use_graph;          /* capture one DDPM step in a CUDA graph and replay it */
     cindm_objective objective;
+    /* conditioned models (GaussianDiffusion1D(conditioned_steps=k), model/diffusion_1d.py:956-957, :1028-1030): the first
+     * cond_rows frames of every x[b] hold the condition; the model sees them (x = cat(cond, x)), the update leaves them
+     * untouched and explicit noise tensors do not cover them ([.., T - cond_rows, 4n]).  0 = unconditioned. */
+    int cond_rows;
+    /* composing_time_sample (:1806-1854): the batch is chain_blocks blocks of batch / chain_blocks trajectories; before
+     * every step block k+1 takes the last cond_rows frames of block k as its condition (:1827-1829).  0 / 1 = off. */
+    int chain_blocks;
+    /* CINDM_COMPOSE_EBM only: coefficient of the unconditional single-body epsilon (1.4 for 4 bodies, :1904) */
+    float ebm_uncond_coef;
 } cindm_sample_config;
 
 const char* cindm_last_error(void);

@@ -8,7 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from cindm_b200.inference.inverse_design_diffusion_1d import build_parser, gather_scores, gather_top_designs, model_horizon, shard
+from cindm_b200.inference.inverse_design_diffusion_1d import (build_parser, gather_scores, gather_top_designs, guidance_list,
+                                                                 model_horizon, sample_stream_seed, shard)
 
 
 def _free_port():
@@ -69,12 +70,25 @@ def test_cli_keeps_reference_flags_and_defaults():
     assert (args.design_fn_mode, args.design_coef, args.consistency_coef) == ("L2", "0.05", "0.05")
     assert (args.Unet_dim, args.initialization_mode, args.num_batchs) == (64, 0, 1)
     assert (args.batch_size_list, args.sample_steps_list, args.seed) == ("[50]", "[1000]", 0)
+    assert (args.model_type, args.is_test, args.dataset_path) == ("temporal-unet1d", True, os.getcwd() + "/dataset/nbody_dataset")
+    # the three defaults that make the reference itself fail when left unset are kept, and fail here with a message:
+    # --model_name 'basic-model' (:59, no branch of :141-156 matches), --design_guidance None (:82), --compose_mode "mean" (:84)
+    assert (args.model_name, args.design_guidance, args.compose_mode) == ("basic-model", None, "mean")
+    with pytest.raises(NotImplementedError, match="Diffusion_cond-0_rollout-24_bodies-2"):
+        model_horizon(args)
+    with pytest.raises(ValueError, match="--design_guidance is required"):
+        guidance_list(args)
+    for conditioned in ("basic_model", "single_step_model"):
+        args.model_name = conditioned
+        with pytest.raises(NotImplementedError, match="conditioned"):
+            model_horizon(args)
     paper = build_parser().parse_args(
         "--exp_id=new-standard-noise_sum --date_time=02-04 --n_composed=2 --compose_n_bodies=8 --design_coef=0.2 "
         "--consistency_coef=0.2 --design_guidance=standard-recurrence-10 --val_batch_size=500 "
         "--model_name=Diffusion_cond-0_rollout-24_bodies-2_more_collision --sample_steps=1000 --compose_mode=mean-inside "
         "--design_fn_mode=L2 --initialization_mode 0 --gpuid 7".split())
     assert model_horizon(paper) == (24, 0)
+    assert guidance_list(paper) == ["standard-recurrence-10"]
     assert paper.is_test is True
     with pytest.raises(NotImplementedError):
         paper.model_name = "Diffusion_cond-0_rollout-44_bodies-2"
@@ -95,3 +109,11 @@ def test_stale_script_flags_are_kept():
     assert (b.date_time, b.val_batch_size, b.sample_steps, b.multi_bodies_method, b.n_composed) == (
         "2023-09-07_test_for_2_bodies", 1, 250, "EBMs_compose", 2)
     assert b.checkpoint_path_direct_diffusion is None
+
+
+def test_every_sample_call_gets_its_own_philox_stream():
+    """--num_batchs / --batch_size_list / guidance sweeps must not replay the noise of the first call."""
+    seeds = [sample_stream_seed(0, k) for k in range(64)] + [sample_stream_seed(1, k) for k in range(64)]
+    assert len(set(seeds)) == len(seeds)
+    assert sample_stream_seed(7, 0) == 7                       # the first call of a run keeps the user's seed
+    assert all(0 <= s < 2 ** 64 for s in seeds)
