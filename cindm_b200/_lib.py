@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("CINDM_B200_LIB") or os.path.join(HERE, "lib", "libcin
 
 PREC_F32, PREC_F16, PREC_BF16 = 0, 1, 2
 CONV_SIMT, CONV_TCGEN05 = 0, 1
-COMPOSE_MEAN_INSIDE, COMPOSE_SUM_INSIDE, COMPOSE_MEAN_OUTSIDE, COMPOSE_NOISE_SUM = 0, 1, 2, 3
+COMPOSE_MEAN_INSIDE, COMPOSE_SUM_INSIDE, COMPOSE_MEAN_OUTSIDE, COMPOSE_NOISE_SUM, COMPOSE_EBM = 0, 1, 2, 3, 4
 OBJ_L2, OBJ_L2SQUARE = 0, 1
 GUIDE_NONE, GUIDE_STANDARD, GUIDE_STANDARD_ALPHA = 0, 1, 2
 
@@ -65,6 +65,11 @@ _SIGNATURES = {
     "cindm_design_grad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(Objective), c_void_p]),
     "cindm_posterior_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                        c_int, c_int, c_int, c_int, POINTER(Objective), c_void_p]),
+    "cindm_attach_unconditioned": (c_int, [c_void_p, c_void_p]),
+    "cindm_ebm_eps": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p]),
+    "cindm_ula_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_uint64, c_int64,
+                               c_int, c_int, c_void_p]),
+    "cindm_predict_start": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "cindm_sample": (c_int, [c_void_p, POINTER(SampleConfig), c_void_p, c_void_p, c_void_p, c_void_p]),
     "cindm_composed_posterior": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                          c_int, c_void_p]),

@@ -75,7 +75,7 @@ __global__ void tap_to_f32_cf(const T* __restrict__ in, float* __restrict__ out,
 extern "C" {
 
 const char* cindm_last_error(void) { return g_last_error.c_str(); }
-int cindm_version(void) { return 100; }
+int cindm_version(void) { return 200; }
 
 long long cindm_launch_count(void) { return launch_count(); }
 
@@ -123,7 +123,8 @@ int cindm_create(const cindm_config* cfg, cindm_engine** out) {
     if (!cfg || !out) return fail(-2, "null argument");
     if (cfg->dim != 64) return fail(-2, "only Unet_dim=64 is built (dim_mults (1,2,4,8))");
     if (cfg->horizon != 24) return fail(-2, "only horizon=24 (the 2-body 24-step model) is built");
-    if (cfg->transition_dim != 8) return fail(-2, "transition_dim must be 8 (two bodies x 4 features)");
+    if (cfg->transition_dim != 8 && cfg->transition_dim != 4)
+        return fail(-2, "transition_dim must be 8 (two bodies x 4 features) or 4 (the unconditional single-body model)");
     if (cfg->timesteps < 1 || cfg->timesteps > 65535) return fail(-2, "timesteps out of range");
     cindm_engine* e = new cindm_engine();
     e->cfg = *cfg;
@@ -370,6 +371,50 @@ int cindm_posterior_update(cindm_engine* e, const float* x, const float* eps, co
     if (obj) u.obj = *obj;
     else { memset(&u.obj, 0, sizeof(u.obj)); u.obj.guidance = CINDM_GUIDE_NONE; }
     return launch_update(u, (cudaStream_t)stream);
+    API_END
+}
+
+int cindm_attach_unconditioned(cindm_engine* e, cindm_engine* single) {
+    API_BEGIN
+    if (!e) return fail(-2, "null engine");
+    if (e->cfg.transition_dim != 8) return fail(-2, "the unconditional model attaches to a body-pair engine (transition_dim 8)");
+    if (single && (single->cfg.transition_dim != 4 || single->cfg.horizon != e->cfg.horizon || single->cfg.timesteps != e->cfg.timesteps))
+        return fail(-2, "the unconditional engine must have transition_dim 4 and the pair engine's horizon / timesteps");
+    if (e->uncond != single) { cudaDeviceSynchronize(); graph_cache_clear(e); }
+    e->uncond = single;
+    return 0;
+    API_END
+}
+
+int cindm_ebm_eps(cindm_engine* e, const float* x, float* eps, int B, int n, float uncond_coef, int t, int precision,
+                  int conv_engine, void* stream) {
+    API_BEGIN
+    if (!e || !x || !eps) return fail(-2, "null argument");
+    if (!e->uncond) return fail(-4, "no unconditional single-body engine attached (cindm_attach_unconditioned)");
+    if (t < 0 || t >= e->cfg.timesteps) return fail(-2, "timestep out of range");
+    if (n < 3) return fail(-2, "the EBM body composition needs at least 3 bodies");
+    const int64_t S = (int64_t)(n * (n - 1) / 2) * B, S1 = (int64_t)n * B;
+    CINDM_TRY(reserve_workspace(e, S > e->ws.max_slices ? S : e->ws.max_slices, precision));
+    CINDM_TRY(reserve_workspace(e->uncond, S1 > e->uncond->ws.max_slices ? S1 : e->uncond->ws.max_slices, precision));
+    return composed_eps(e, x, eps, B, n, 0, 1, CINDM_COMPOSE_EBM, t, nullptr, precision, conv_engine, (cudaStream_t)stream, nullptr,
+                        uncond_coef);
+    API_END
+}
+
+int cindm_ula_step(const float* x, const float* eps, const float* noise, float* x_out, int B, int T, int n, float grad_scale,
+                   float step_size, uint64_t seed, int64_t cand_off, int t, int draw, void* stream) {
+    API_BEGIN
+    if (!x || !eps || !x_out) return fail(-2, "null argument");
+    return launch_ula_step(x, eps, noise, x_out, B, T, n, grad_scale, step_size, seed, cand_off, t, draw, (cudaStream_t)stream);
+    API_END
+}
+
+int cindm_predict_start(cindm_engine* e, const float* x, const float* eps, float* x0_out, int64_t elems, int t, int clip,
+                        void* stream) {
+    API_BEGIN
+    if (!e || !x || !eps || !x0_out) return fail(-2, "null argument");
+    if (t < 0 || t >= e->cfg.timesteps) return fail(-2, "timestep out of range");
+    return launch_predict_start(x, eps, x0_out, elems, e->sched_dev, e->cfg.timesteps, t, clip, (cudaStream_t)stream);
     API_END
 }
 

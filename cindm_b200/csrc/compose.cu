@@ -175,4 +175,60 @@ int launch_compose_scatter(const float* eps_pair, float* eps, int B, int n, int 
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// EBM body composition with the unconditional single-body model (reference gradient() :1856-1982):
+//   eps[b][t][4r + f] = sum_{s != r} eps_pair({r, s})[slot(r)][f]  -  coef * eps_single(body r)[f]
+// The pair sum is the "sum-inside" operator with one window; the two kernels below feed and subtract the second term.
+// Single-body slice order: slice = body * B + b (the reference calls the unconditional model once per body, :1895-1898).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) body_gather_kernel(const float4* __restrict__ x, float4* __restrict__ slices, int B, int n,
+                                                          int H, int T) {
+    const long long total = (long long)n * B * H;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int h = (int)(i % H);
+        const long long s = i / H;
+        const int b = (int)(s % B), body = (int)(s / B);
+        slices[i] = x[((long long)b * T + h) * n + body];
+    }
+}
+
+__global__ void __launch_bounds__(256) ebm_subtract_kernel(float4* __restrict__ eps, const float4* __restrict__ eps_single, int B, int n,
+                                                           int T, float coef) {
+    pdl_wait();
+    pdl_trigger();
+    const long long total = (long long)B * T * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i % n);
+        const long long bt = i / n;
+        const int t = (int)(bt % T);
+        const long long b = bt / T;
+        const float4 u = eps_single[((long long)r * B + b) * T + t];
+        float4 e = eps[i];
+        // (sum of the pair terms) - (coef * unconditional): two rounded operations, as the reference's tensor expression
+        e.x = __fsub_rn(e.x, __fmul_rn(coef, u.x)); e.y = __fsub_rn(e.y, __fmul_rn(coef, u.y));
+        e.z = __fsub_rn(e.z, __fmul_rn(coef, u.z)); e.w = __fsub_rn(e.w, __fmul_rn(coef, u.w));
+        eps[i] = e;
+    }
+}
+
+int launch_body_gather(const float* x, float* slices, int B, int n, int H, int T, cudaStream_t st) {
+    const long long total = (long long)n * B * H;
+    if (total == 0) return 0;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    body_gather_kernel<<<blocks, 256, 0, st>>>((const float4*)x, (float4*)slices, B, n, H, T);
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
+int launch_ebm_subtract(float* eps, const float* eps_single, int B, int n, int T, float coef, cudaStream_t st) {
+    const long long total = (long long)B * T * n;
+    if (total == 0) return 0;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    CINDM_CHECK_CUDA(launch_chain(ebm_subtract_kernel, dim3(blocks), dim3(256), 0, st, (float4*)eps, (const float4*)eps_single, B, n, T, coef));
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
 }  // namespace cindm

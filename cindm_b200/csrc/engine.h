@@ -114,6 +114,10 @@ struct cindm_engine {
     cindm::Workspace ws;
     cindm::SampleBuffers sb;
 
+    // EBM body composition: the unconditional single-body engine (transition_dim 4) attached with
+    // cindm_attach_unconditioned; not owned
+    cindm_engine* uncond = nullptr;
+
     bool use_toeplitz = true;              // H=3 convs as one dense block-Toeplitz GEMM (tcgen05 engine)
     bool use_fused_attn = true;            // LayerNorm + to_qkv + attention core as one kernel (tcgen05 engine)
     bool taps_enabled = false;
@@ -165,7 +169,9 @@ int launch_stem(const StemLaunch& a, cudaStream_t st);
 int launch_head(const void* in, const ConvW& w, float* out, int64_t rows, int prec, cudaStream_t st);
 
 // when non-null, the U-Net reads its slices straight out of the design tensor x[B][T][4n]
-struct GatherSpec { const float* x; int B, n, nc, start; };
+struct GatherSpec { const float* x; int B, n, nc, start; };   // (an engine with transition_dim 4 gathers single bodies: slice = body * B + b)
+int launch_body_gather(const float* x, float* slices, int B, int n, int H, int T, cudaStream_t st);
+int launch_ebm_subtract(float* eps, const float* eps_single, int B, int n, int T, float coef, cudaStream_t st);
 
 // t_dev == nullptr: use the host value t; else the device integer *t_dev (CUDA-graph replay)
 int unet_forward(cindm_engine* e, const float* slices, int64_t S, int t, const int* t_dev, float* eps_pair,
@@ -205,6 +211,10 @@ int launch_update(const UpdateLaunch& u, cudaStream_t st);
 int launch_fill_noise(float* x, int B, int T, int n, uint64_t seed, int64_t cand_off, int t, int draw,
                       cudaStream_t st);
 int launch_step_counter(int* t_dev, int delta, cudaStream_t st);
+int launch_ula_step(const float* x, const float* eps, const float* noise, float* out, int B, int T, int n, float grad_scale,
+                    float ss, uint64_t seed, int64_t cand_off, int t, int draw, cudaStream_t st);
+int launch_predict_start(const float* x, const float* eps, float* x0, long long elems, const float* sched, int timesteps, int t,
+                         int clip, cudaStream_t st);
 // composing_time_sample (:1827-1829): block k+1's first cond_rows frames <- block k's last cond_rows frames
 int launch_chain_condition(float* x, int rows_per_block, int blocks, int T, int n, int cond_rows, cudaStream_t st);
 int sample_ddim(cindm_engine* e, const cindm_sample_config& c, int n_pairs, const int32_t* times, const int32_t* times_next,
@@ -215,8 +225,9 @@ int finalize_weights(cindm_engine* e, cudaStream_t st);
 int reserve_workspace(cindm_engine* e, int64_t S, int prec);
 int64_t workspace_bytes(int64_t S, int prec, int horizon);
 // x0_composed: required for (and only used by) CINDM_COMPOSE_MEAN_OUTSIDE, where `eps` receives the composed posterior mean
+// mode CINDM_COMPOSE_EBM: sum over pairs minus ebm_coef * the attached unconditional single-body model (nc must be 0)
 int composed_eps(cindm_engine* e, const float* x, float* eps, int B, int n, int nc, int start, int mode, int t,
-                 const int* t_dev, int prec, int conv_engine, cudaStream_t st, float* x0_composed = nullptr);
+                 const int* t_dev, int prec, int conv_engine, cudaStream_t st, float* x0_composed = nullptr, float ebm_coef = 0.f);
 int sample_loop(cindm_engine* e, const cindm_sample_config& cfg, float* x, const float* noise, float* x0_out,
                 cudaStream_t st);
 

@@ -442,13 +442,13 @@ int launch_attn_core(const void* qkv, void* out, int64_t S, int n, int prec, cud
 // One warp-pair (64 threads = 64 output channels) per slice; weights live in registers.
 // ------------------------------------------------------------------------------------------
 struct StemParams {
-    const float* x;            // gather: [B][T][4n];  else slices [S][24][8]
-    const float* w0;           // [5][8][64]
+    const float* x;            // gather: [B][T][4n];  else slices [S][24][F]   (F = 8: body pair, F = 4: single body)
+    const float* w0;           // [5][F][64]
     const float* b0;           // [64]
     const float* gamma; const float* beta;
     const float* tbias;        // [64] or [timesteps][64] with t_dev
     const int* t_dev;
-    const float* wr;           // [1][8][64]
+    const float* wr;           // [1][F][64]
     const float* br;           // [64]
     void* out_b0;              // [S][24][64]
     void* out_res;             // [S][24][64]
@@ -456,23 +456,24 @@ struct StemParams {
     int gather, B, n, P, start, T;
 };
 
-template <typename T>
+template <typename T, int F>
 __global__ void __launch_bounds__(256, 2) stem_kernel(StemParams p) {
-    __shared__ float xs[4][24 + 4][8];                      // per-slice input with 2 zero rows of padding each side
+    __shared__ float xs[4][24 + 4][F];                      // per-slice input with 2 zero rows of padding each side
     pdl_wait();
     pdl_trigger();
     const int sub = threadIdx.x >> 6, co = threadIdx.x & 63;
     const long long s = (long long)blockIdx.x * 4 + sub;
     const bool active = s < p.S;
-    // ---- load the slice (24 x 8 floats = 48 float4; 64 threads)
+    // ---- load the slice (24 x F floats = 24 * F/4 float4; 64 threads)
+    constexpr int BODIES = F / 4;                           // bodies per slice: 2 (pair model) or 1 (unconditional single-body model)
     if (co < 4) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) { xs[sub][co < 2 ? co : 24 + co][c] = 0.f; }
+        for (int c = 0; c < F; ++c) { xs[sub][co < 2 ? co : 24 + co][c] = 0.f; }
     }
-    if (active && co < 48) {
-        const int h = co >> 1, half = co & 1;
+    if (active && co < 24 * BODIES) {
+        const int h = co / BODIES, half = co - h * BODIES;
         float4 v;
-        if (p.gather) {
+        if (p.gather && BODIES == 2) {
             const int b = (int)(s % p.B);
             const int wp = (int)(s / p.B);
             const int pr = wp % p.P, kk = wp / p.P;
@@ -481,19 +482,23 @@ __global__ void __launch_bounds__(256, 2) stem_kernel(StemParams p) {
             const int jj = ii + 1 + rem;
             const int body = half ? jj : ii;
             v = reinterpret_cast<const float4*>(p.x)[((long long)b * p.T + kk * p.start + h) * p.n + body];
+        } else if (p.gather) {
+            // single-body slices of the EBM composition (reference gradient() :1866-1870): slice = body * B + b
+            const int b = (int)(s % p.B), body = (int)(s / p.B);
+            v = reinterpret_cast<const float4*>(p.x)[((long long)b * p.T + h) * p.n + body];
         } else {
-            v = reinterpret_cast<const float4*>(p.x)[(s * 24 + h) * 2 + half];
+            v = reinterpret_cast<const float4*>(p.x)[(s * 24 + h) * BODIES + half];
         }
         *reinterpret_cast<float4*>(&xs[sub][h + 2][half * 4]) = v;
     }
     // ---- weights of this output channel
-    float w[5][8], wr[8];
+    float w[5][F], wr[F];
 #pragma unroll
     for (int k = 0; k < 5; ++k)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) w[k][c] = p.w0[(k * 8 + c) * 64 + co];
+        for (int c = 0; c < F; ++c) w[k][c] = p.w0[(k * F + c) * 64 + co];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) wr[c] = p.wr[c * 64 + co];
+    for (int c = 0; c < F; ++c) wr[c] = p.wr[c * 64 + co];
     const float bias0 = p.b0[co], biasr = p.br[co];
     const float ga = p.gamma[co], be = p.beta[co];
     const float tb = p.t_dev ? p.tbias[(long long)(*p.t_dev) * 64 + co] : p.tbias[co];
@@ -507,7 +512,7 @@ __global__ void __launch_bounds__(256, 2) stem_kernel(StemParams p) {
 #pragma unroll
         for (int k = 0; k < 5; ++k)
 #pragma unroll
-            for (int c = 0; c < 8; ++c) a = fmaf(w[k][c], xs[sub][h + k][c], a);
+            for (int c = 0; c < F; ++c) a = fmaf(w[k][c], xs[sub][h + k][c], a);
         y[h] = a;
         sum += a;
     }
@@ -532,22 +537,26 @@ __global__ void __launch_bounds__(256, 2) stem_kernel(StemParams p) {
         ob[h * 64] = from_f32<T>(v);
         float r = biasr;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) r = fmaf(wr[c], xs[sub][h + 2][c], r);
+        for (int c = 0; c < F; ++c) r = fmaf(wr[c], xs[sub][h + 2][c], r);
         orr[h * 64] = from_f32<T>(r);
     }
 }
 
 int launch_stem(const StemLaunch& a, cudaStream_t st) {
     if (a.S == 0) return 0;
-    KernelTimer kt("stem", st, (double)a.S * 24 * (32.0 + 2.0 * 64 * elem_size(a.prec)));
+    const int F = a.conv0->cin;
+    if (F != 8 && F != 4) return fail(-2, "stem kernel is built for 8 (body pair) or 4 (single body) input features");
+    KernelTimer kt("stem", st, (double)a.S * 24 * (4.0 * F + 2.0 * 64 * elem_size(a.prec)));
     StemParams p;
     p.x = a.x; p.w0 = a.conv0->w; p.b0 = a.conv0->bias; p.gamma = a.gn->gamma; p.beta = a.gn->beta;
     p.tbias = a.tbias; p.t_dev = a.t_dev; p.wr = a.res->w; p.br = a.res->bias;
     p.out_b0 = a.out_b0; p.out_res = a.out_res; p.S = a.S;
     p.gather = a.gather; p.B = a.B; p.n = a.n; p.P = a.n * (a.n - 1) / 2; p.start = a.start; p.T = a.T;
     const unsigned blocks = (unsigned)((a.S + 3) / 4);
-    if (a.prec == PREC_F16) CINDM_CHECK_CUDA(launch_chain(stem_kernel<__half>, dim3(blocks), dim3(256), 0, st, p));
-    else if (a.prec == PREC_BF16) CINDM_CHECK_CUDA(launch_chain(stem_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, p));
+    if (a.prec == PREC_F16 && F == 8) CINDM_CHECK_CUDA(launch_chain(stem_kernel<__half, 8>, dim3(blocks), dim3(256), 0, st, p));
+    else if (a.prec == PREC_F16) CINDM_CHECK_CUDA(launch_chain(stem_kernel<__half, 4>, dim3(blocks), dim3(256), 0, st, p));
+    else if (a.prec == PREC_BF16 && F == 8) CINDM_CHECK_CUDA(launch_chain(stem_kernel<__nv_bfloat16, 8>, dim3(blocks), dim3(256), 0, st, p));
+    else if (a.prec == PREC_BF16) CINDM_CHECK_CUDA(launch_chain(stem_kernel<__nv_bfloat16, 4>, dim3(blocks), dim3(256), 0, st, p));
     else return fail(-2, "stem kernel is built for the 16-bit precisions");
     CINDM_CHECK_LAUNCH();
     return 0;
@@ -557,22 +566,22 @@ int launch_stem(const StemLaunch& a, cudaStream_t st) {
 // Head: final 1x1 conv 64 -> 8 (+bias) from 16-bit activations to fp32 eps_pair [S][24][8]
 // (reference final_conv[1], model/diffusion_1d.py:607).  One thread per (slice, position) row.
 // ------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int F>
 __global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ in, const float* __restrict__ w,
                                                    const float* __restrict__ bias, float* __restrict__ out,
                                                    long long rows) {
-    __shared__ float sw[64][8];
-    __shared__ float sb[8];
+    __shared__ float sw[64][F];
+    __shared__ float sb[F];
     pdl_wait();
     pdl_trigger();
-    for (int i = threadIdx.x; i < 512; i += 256) sw[i >> 3][i & 7] = w[i];        // w: [1][64][8]
-    if (threadIdx.x < 8) sb[threadIdx.x] = bias[threadIdx.x];
+    for (int i = threadIdx.x; i < 64 * F; i += 256) sw[i / F][i % F] = w[i];      // w: [1][64][F]
+    if (threadIdx.x < F) sb[threadIdx.x] = bias[threadIdx.x];
     __syncthreads();
     const long long r = (long long)blockIdx.x * 256 + threadIdx.x;
     if (r >= rows) return;
-    float acc[8];
+    float acc[F];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o] = sb[o];
+    for (int o = 0; o < F; ++o) acc[o] = sb[o];
     const T* src = in + r * 64;
 #pragma unroll
     for (int c8 = 0; c8 < 64; c8 += 8) {
@@ -581,24 +590,28 @@ __global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ in, con
 #pragma unroll
         for (int k = 0; k < 8; ++k)
 #pragma unroll
-            for (int o = 0; o < 8; ++o) acc[o] = fmaf(v[k], sw[c8 + k][o], acc[o]);
+            for (int o = 0; o < F; ++o) acc[o] = fmaf(v[k], sw[c8 + k][o], acc[o]);
     }
-    float4* dst = reinterpret_cast<float4*>(out + r * 8);
-    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    float4* dst = reinterpret_cast<float4*>(out + r * F);
+#pragma unroll
+    for (int o = 0; o < F; o += 4) dst[o >> 2] = make_float4(acc[o], acc[o + 1], acc[o + 2], acc[o + 3]);
 }
 
 int launch_head(const void* in, const ConvW& w, float* out, int64_t rows, int prec, cudaStream_t st) {
     if (rows == 0) return 0;
-    KernelTimer kt("head", st, (double)rows * (64.0 * elem_size(prec) + 32.0));
+    const int F = w.cout;
+    if (F != 8 && F != 4) return fail(-2, "head kernel is built for 8 or 4 output features");
+    KernelTimer kt("head", st, (double)rows * (64.0 * elem_size(prec) + 4.0 * F));
     const unsigned blocks = (unsigned)((rows + 255) / 256);
-    if (prec == PREC_F16)
-        CINDM_CHECK_CUDA(launch_chain(head_kernel<__half>, dim3(blocks), dim3(256), 0, st, (const __half*)in, (const float*)w.w,
-                                      (const float*)w.bias, out, (long long)rows));
-    else if (prec == PREC_BF16)
-        CINDM_CHECK_CUDA(launch_chain(head_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)in,
-                                      (const float*)w.w, (const float*)w.bias, out, (long long)rows));
-    else return fail(-2, "head kernel is built for the 16-bit precisions");
+    if (prec != PREC_F16 && prec != PREC_BF16) return fail(-2, "head kernel is built for the 16-bit precisions");
+#define CINDM_HEAD(T, FF)                                                                                                     \
+    CINDM_CHECK_CUDA(launch_chain(head_kernel<T, FF>, dim3(blocks), dim3(256), 0, st, (const T*)in, (const float*)w.w,      \
+                                  (const float*)w.bias, out, (long long)rows))
+    if (prec == PREC_F16 && F == 8) CINDM_HEAD(__half, 8);
+    else if (prec == PREC_F16) CINDM_HEAD(__half, 4);
+    else if (F == 8) CINDM_HEAD(__nv_bfloat16, 8);
+    else CINDM_HEAD(__nv_bfloat16, 4);
+#undef CINDM_HEAD
     CINDM_CHECK_LAUNCH();
     return 0;
 }

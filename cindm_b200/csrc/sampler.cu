@@ -301,10 +301,92 @@ int launch_update(const UpdateLaunch& u, cudaStream_t st) {
     return 0;
 }
 
+// ---------------------------------------------------------------- unadjusted Langevin step (sample_step_ULA :2047-2073)
+__global__ void __launch_bounds__(256) ula_step_kernel(const float4* __restrict__ x, const float4* __restrict__ eps,
+                                                       const float4* __restrict__ noise, float4* __restrict__ out, long long nvec,
+                                                       int vec_per_cand, float grad_scale, float ss, float std, unsigned long long seed,
+                                                       long long cand_off, int t, int draw) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / vec_per_cand;
+        const float4 xv = x[i], ev = eps[i];
+        const float4 nz = noise ? noise[i] : noise4(seed, cand_off + b, (int)(i - b * vec_per_cand), t, draw);
+        // grad = grad_scale * eps;  x + grad * ss + (randn * std)      (:2056-2061, three rounded operations per term)
+        float4 o;
+        o.x = __fadd_rn(__fadd_rn(xv.x, __fmul_rn(__fmul_rn(grad_scale, ev.x), ss)), __fmul_rn(nz.x, std));
+        o.y = __fadd_rn(__fadd_rn(xv.y, __fmul_rn(__fmul_rn(grad_scale, ev.y), ss)), __fmul_rn(nz.y, std));
+        o.z = __fadd_rn(__fadd_rn(xv.z, __fmul_rn(__fmul_rn(grad_scale, ev.z), ss)), __fmul_rn(nz.z, std));
+        o.w = __fadd_rn(__fadd_rn(xv.w, __fmul_rn(__fmul_rn(grad_scale, ev.w), ss)), __fmul_rn(nz.w, std));
+        out[i] = o;
+    }
+}
+
+int launch_ula_step(const float* x, const float* eps, const float* noise, float* out, int B, int T, int n, float grad_scale,
+                    float ss, uint64_t seed, int64_t cand_off, int t, int draw, cudaStream_t st) {
+    const long long nvec = (long long)B * T * n;
+    if (nvec == 0) return 0;
+    int blocks = (int)((nvec + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    const float std = sqrtf(2.0f * ss);                              // (2 * ss) ** .5 on an fp32 tensor element (:2055)
+    ula_step_kernel<<<blocks, 256, 0, st>>>((const float4*)x, (const float4*)eps, (const float4*)noise, (float4*)out, nvec, T * n,
+                                            grad_scale, ss, std, seed, cand_off, t, draw);
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---------------------------------------------------------------- x_start from epsilon (predict_start_from_noise :914-918)
+__global__ void __launch_bounds__(256) predict_start_kernel(const float4* __restrict__ x, const float4* __restrict__ eps,
+                                                            float4* __restrict__ x0, long long nvec, const float* __restrict__ sched,
+                                                            int timesteps, int t, int clip) {
+    const float A = sched[TAB_SQRT_RECIP_ACP * timesteps + t], Bc = sched[TAB_SQRT_RECIPM1_ACP * timesteps + t];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const float4 a = x[i], b = eps[i];
+        float v[4] = {__fsub_rn(__fmul_rn(A, a.x), __fmul_rn(Bc, b.x)), __fsub_rn(__fmul_rn(A, a.y), __fmul_rn(Bc, b.y)),
+                      __fsub_rn(__fmul_rn(A, a.z), __fmul_rn(Bc, b.z)), __fsub_rn(__fmul_rn(A, a.w), __fmul_rn(Bc, b.w))};
+        if (clip) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = fminf(fmaxf(v[q], -1.0f), 1.0f);
+        }
+        x0[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+int launch_predict_start(const float* x, const float* eps, float* x0, long long elems, const float* sched, int timesteps, int t,
+                         int clip, cudaStream_t st) {
+    if (!sched) return fail(-4, "schedule tables not set (cindm_set_schedule)");
+    if (elems % 4) return fail(-2, "element count must be a multiple of 4");
+    const long long nvec = elems / 4;
+    if (nvec == 0) return 0;
+    int blocks = (int)((nvec + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    predict_start_kernel<<<blocks, 256, 0, st>>>((const float4*)x, (const float4*)eps, (float4*)x0, nvec, sched, timesteps, t, clip);
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
 // ---------------------------------------------------------------- composed epsilon + loop
 int composed_eps(cindm_engine* e, const float* x, float* eps, int B, int n, int nc, int start, int mode, int t,
-                 const int* t_dev, int prec, int conv_engine, cudaStream_t st, float* x0_composed) {
+                 const int* t_dev, int prec, int conv_engine, cudaStream_t st, float* x0_composed, float ebm_coef) {
     const int H = e->cfg.horizon;
+    if (e->cfg.transition_dim != 8) return fail(-2, "the composition operator runs on the body-pair model (transition_dim 8)");
+    if (mode == CINDM_COMPOSE_EBM) {
+        // gradient() (:1856-1982): pair terms summed per receiver (one window), minus coef x the unconditional single-body model
+        cindm_engine* u = e->uncond;
+        if (!u) return fail(-4, "compose mode EBM needs an unconditional single-body engine (cindm_attach_unconditioned)");
+        if (nc != 0) return fail(-5, "the EBM body composition has one window (n_composed = 0)");
+        if (n < 3) return fail(-2, "the EBM body composition needs at least 3 bodies");
+        const int64_t S1 = (int64_t)n * B;
+        if (S1 > u->ws.max_slices || u->ws.precision != prec)
+            return fail(-6, "unconditional engine: workspace not reserved for this slice count / precision");
+        CINDM_TRY(composed_eps(e, x, eps, B, n, 0, start, CINDM_COMPOSE_SUM_INSIDE, t, t_dev, prec, conv_engine, st));
+        if (prec == PREC_F32) {
+            CINDM_TRY(launch_body_gather(x, u->ws.slices, B, n, H, H, st));
+            CINDM_TRY(unet_forward(u, u->ws.slices, S1, t, t_dev, u->ws.eps_pair, prec, conv_engine, st));
+        } else {
+            GatherSpec gs{x, B, n, 0, start};
+            CINDM_TRY(unet_forward(u, nullptr, S1, t, t_dev, u->ws.eps_pair, prec, conv_engine, st, &gs));
+        }
+        return launch_ebm_subtract(eps, u->ws.eps_pair, B, n, H, ebm_coef, st);
+    }
     if (mode == CINDM_COMPOSE_NOISE_SUM) mode = CINDM_COMPOSE_SUM_INSIDE;      // same operator (:1452-1457 vs :997-999)
     if (mode == CINDM_COMPOSE_MEAN_OUTSIDE && !x0_composed)
         return fail(-5, "compose_mode 'mean' composes the posterior, not epsilon: there is no composed epsilon to return");
@@ -374,7 +456,8 @@ static int issue_step(cindm_engine* e, const cindm_sample_config& c, float* bufs
     for (int r = 0; r < iters; ++r) {
         const bool outside = c.compose_mode == CINDM_COMPOSE_MEAN_OUTSIDE;
         CINDM_TRY(composed_eps(e, bufs[cur], e->sb.eps, c.batch, c.n_bodies, c.n_composed, c.compose_start_step,
-                               c.compose_mode, t, t_dev, c.precision, c.conv_engine, st, outside ? e->sb.x0c : nullptr));
+                               c.compose_mode, t, t_dev, c.precision, c.conv_engine, st, outside ? e->sb.x0c : nullptr,
+                               c.ebm_uncond_coef));
         const bool last = r == iters - 1;
         UpdateLaunch u;
         u.x = bufs[cur]; u.eps = e->sb.eps; u.x_out = bufs[cur ^ 1];
@@ -441,11 +524,20 @@ static int sample_loop_on(cindm_engine* e, const cindm_sample_config& c, float* 
     if (c.t_start >= e->cfg.timesteps || c.t_end < 0 || c.t_end > c.t_start) return fail(-2, "bad timestep range");
     if (c.compose_start_step >= e->cfg.horizon) return fail(-2, "compose_start_step must be < horizon");   // (:1679)
     if (c.batch <= 0) return fail(-2, "batch must be positive");
+    if (e->cfg.transition_dim != 8) return fail(-2, "sampling runs on the body-pair engine (transition_dim 8)");
+    if (c.compose_mode == CINDM_COMPOSE_EBM && c.objective.guidance != CINDM_GUIDE_NONE)
+        return fail(-5, "design guidance with the EBM body composition is not on the CUDA fast path");
     const int T = e->cfg.horizon + c.n_composed * c.compose_start_step;
     CINDM_TRY(check_condition_config(c, T));
     const size_t elems = (size_t)c.batch * T * c.n_bodies * 4;
     const int64_t S = (int64_t)(c.n_composed + 1) * (c.n_bodies * (c.n_bodies - 1) / 2) * c.batch;
     CINDM_TRY(reserve_workspace(e, S > e->ws.max_slices ? S : e->ws.max_slices, c.precision));
+    if (c.compose_mode == CINDM_COMPOSE_EBM) {
+        if (!e->uncond) return fail(-4, "compose mode EBM needs an unconditional single-body engine (cindm_attach_unconditioned)");
+        if (!e->uncond->finalized) return fail(-4, "unconditional engine: weights not finalized");
+        const int64_t S1 = (int64_t)c.n_bodies * c.batch;
+        CINDM_TRY(reserve_workspace(e->uncond, S1 > e->uncond->ws.max_slices ? S1 : e->uncond->ws.max_slices, c.precision));
+    }
     CINDM_TRY(ensure_sample_buffers(e, elems));
     float* bufs[2] = {x, e->sb.x_alt};
     int cur = 0;
@@ -515,6 +607,7 @@ static int sample_ddim_on(cindm_engine* e, const cindm_sample_config& c, int n_p
     // single-pass "standard" branch hands ddim_sample the posterior sample in place of epsilon (:1283)
     if (c.compose_mode != CINDM_COMPOSE_MEAN_INSIDE && c.compose_mode != CINDM_COMPOSE_SUM_INSIDE)
         return fail(-5, "DDIM runs on the *-inside composition only (reference ddim_sample :1758-1771)");
+    if (e->cfg.transition_dim != 8) return fail(-2, "sampling runs on the body-pair engine (transition_dim 8)");
     if (guided && c.recurrence <= 0)
         return fail(-5, "DDIM sampling with guidance needs a '-recurrence-K' design_guidance (reference :1283 vs :1372-1376)");
     for (int i = 0; i < n_pairs; ++i)

@@ -7,9 +7,11 @@ every tensor operation of the sampling path is a call into the C ABI declared in
 include/cindm_b200.h (hand-written sm_100a CUDA).  PyTorch only owns device memory and streams.
 
 Fast-path subset (anything else raises NotImplementedError — there is no silent fallback):
-objective 'pred_noise', conditioned_steps 0, cond None, compose_mode in {mean-inside, sum-inside},
-design_guidance in {standard, standard-alpha}[-recurrence-K], DDPM (sampling_timesteps == timesteps) or DDIM,
-horizon 24, dim 64, attention=True.
+objective 'pred_noise'; compose_mode in {mean-inside, sum-inside, mean, noise_sum}; design_guidance in {standard,
+standard-alpha}[-recurrence-K]; DDPM (sampling_timesteps == timesteps) or DDIM; model horizon 24, dim 64, attention=True.
+conditioned_steps = 0 with cond = None is the inverse-design path; conditioned_steps = k > 0 (image_size + k = 24, the
+"basic model": 4 condition frames + 20 rollout frames) is the conditioned model behind model_predictions / ddim_sample
+with cond, autoregress_time_compose_sample and composing_time_sample.
 """
 import ctypes
 import math
@@ -17,8 +19,12 @@ from collections import OrderedDict
 
 import torch
 
+from collections import namedtuple
+
 from .. import _lib
 from .params import init_unet_params, unet_param_shapes
+
+ModelPrediction = namedtuple("ModelPrediction", ["pred_noise", "pred_x_start"])          # reference :43
 
 SCHEDULE_KEYS = (
     "betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod",
@@ -297,8 +303,9 @@ class GaussianDiffusion1D:
                  num_time_steps_UHMC=100, is_diffusion_condition=None, backward_steps=5, backward_lr=1):
         if objective != "pred_noise":
             raise NotImplementedError("only objective='pred_noise' is on the CUDA fast path")
-        if conditioned_steps != 0:
-            raise NotImplementedError("only conditioned_steps=0 is on the CUDA fast path")
+        if conditioned_steps < 0 or image_size + conditioned_steps != model.horizon:
+            raise NotImplementedError(f"image_size + conditioned_steps must equal the model horizon ({model.horizon}): "
+                                      "the model sees cat(cond, x) (reference :956-957)")
         if model_unconditioned is not None:
             raise NotImplementedError("model_unconditioned (EBM body composition) is not on the CUDA fast path")
         self.model = model
@@ -401,7 +408,7 @@ class GaussianDiffusion1D:
         return g
 
     def _sample_config(self, batch, n_composed, compose_start_step, compose_n_bodies, compose_mode, design_fn,
-                       design_guidance, t_start, t_end, use_graph):
+                       design_guidance, t_start, t_end, use_graph, cond_rows=0, chain_blocks=0, ebm_uncond_coef=0.0):
         if design_fn is None:
             guidance, recurrence = parse_design_guidance(design_guidance)
             obj = _lib.Objective(0.0, 0.0, 0.0, 0.0, _lib.OBJ_L2, _lib.GUIDE_NONE)
@@ -414,7 +421,8 @@ class GaussianDiffusion1D:
             obj = design_fn.as_struct(guidance)
         return _lib.SampleConfig(
             batch, compose_n_bodies, n_composed, compose_start_step, _compose_mode(compose_mode), recurrence,
-            self._prec(), self._conv(), t_start, t_end, self.seed, self.candidate_offset, int(use_graph), obj)
+            self._prec(), self._conv(), t_start, t_end, self.seed, self.candidate_offset, int(use_graph), obj,
+            int(cond_rows), int(chain_blocks), float(ebm_uncond_coef))
 
     def p_sample_compose_inside(self, x, cond, t, x_self_cond=None, clip_denoised=True, design_fn=None,
                                 design_guidance="standard", initial_state_overwrite=None, compose_mode="mean-inside",
@@ -460,6 +468,122 @@ class GaussianDiffusion1D:
                 eng.handle, _lib.ptr(x), _lib.ptr(mean), _lib.ptr(x0), b, compose_n_bodies, n_composed, compose_start_step,
                 int(t), self._prec(), self._conv(), _lib.stream_ptr(self.device)))
         return mean, x0
+
+    # --- model_predictions (reference :951-1031) ----------------------------------------------------------------
+    def model_predictions(self, x, cond, t, x_self_cond=None, clip_x_start=False, rederive_pred_noise=False, **kwargs):
+        """(pred_noise, x_start) for x [B, image_size(+composition), F] at the (batch-uniform) timestep t.
+
+        conditioned_steps > 0: the model sees cat(cond, x) and both results are cut back to x's frames (:956-957,
+        :1028-1030).  With the `compose_mode="...-inside"` kwargs of p_mean_variance it is the composition operator."""
+        if rederive_pred_noise:
+            raise NotImplementedError("rederive_pred_noise is not on the CUDA fast path")
+        tt = int(t.reshape(-1)[0].item()) if torch.is_tensor(t) else int(t)
+        x = x.to(self.device, torch.float32).contiguous()
+        k = self.conditioned_steps
+        if k:
+            if cond is None or cond.shape[1] != k:
+                raise ValueError(f"a model with conditioned_steps={k} needs cond [B, {k}, F]")
+            full = torch.cat([cond.to(self.device, torch.float32), x], dim=1).contiguous()
+        else:
+            full = x
+        if "compose_mode" in kwargs and "inside" in kwargs["compose_mode"]:
+            if k:
+                raise NotImplementedError("composition on a conditioned model is not on the CUDA fast path")
+            assert kwargs["single_model_step"] > 0                                 # reference :965
+            eps = self.composed_eps(full, tt, kwargs["n_composed"], kwargs["compose_start_step"], kwargs["compose_n_bodies"],
+                                    kwargs["compose_mode"])
+        else:
+            self.model.precision, self.model.conv_engine = self.precision, self.conv_engine
+            eps = self.model(full, tt, None)
+        x0 = torch.empty_like(eps)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cindm_predict_start(self.model.engine().handle, _lib.ptr(full), _lib.ptr(eps), _lib.ptr(x0),
+                                                      full.numel(), tt, int(bool(clip_x_start)), _lib.stream_ptr(self.device)))
+        return ModelPrediction(eps[:, k:].contiguous(), x0[:, k:].contiguous())
+
+    def _window_seed(self, index):
+        return (int(self.seed) + 0x9E3779B97F4A7C15 * int(index)) & 0xFFFFFFFFFFFFFFFF
+
+    def _conditioned_ddim(self, state, chain_blocks, noise, pairs, seed):
+        """DDIM loop (reference :1751-1797 without guidance) on state [Bx, conditioned_steps + image_size, F] whose first
+        conditioned_steps frames are the condition; returns the final state (x_start on the last pair)."""
+        if not self.is_ddim_sampling and pairs is None and self.sampling_timesteps != self.num_timesteps:
+            raise ValueError("sampling_timesteps must be <= timesteps")
+        pairs, coef = self.ddim_schedule(pairs)
+        times = torch.tensor([p[0] for p in pairs], dtype=torch.int32)
+        times_next = torch.tensor([p[1] for p in pairs], dtype=torch.int32)
+        bx, t_full, f = state.shape
+        keep = self.seed
+        self.seed = seed
+        try:
+            cfg = self._sample_config(bx, 0, self.model.horizon - 1, f // 4, "mean-inside", None, "standard", 0, 0,
+                                      self.use_cuda_graph, cond_rows=self.conditioned_steps, chain_blocks=chain_blocks)
+        finally:
+            self.seed = keep
+        if noise is not None:
+            noise = noise.to(self.device, torch.float32).contiguous()
+            assert tuple(noise.shape) == (len(pairs), 1, bx, t_full - self.conditioned_steps, f), tuple(noise.shape)
+        x0 = torch.empty_like(state)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cindm_sample_ddim(self.model.engine().handle, ctypes.byref(cfg), len(pairs), times.data_ptr(),
+                                                    times_next.data_ptr(), coef.data_ptr(), _lib.ptr(state),
+                                                    _lib.ptr(noise) if noise is not None else None, _lib.ptr(x0),
+                                                    _lib.stream_ptr(self.device)))
+        self.last_x_start = x0[:, self.conditioned_steps:]
+        return state
+
+    def _initial_frames(self, batch, frames, f, seed, img=None):
+        if img is not None:
+            return img.to(self.device, torch.float32).reshape(batch, frames, f).contiguous()
+        out = torch.empty((batch, frames, f), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cindm_fill_initial_noise(_lib.ptr(out), batch, frames, f // 4, seed, self.candidate_offset,
+                                                           self.num_timesteps, _lib.stream_ptr(self.device)))
+        return out
+
+    def autoregress_time_compose_sample(self, batch_size, cond, n_composed, is_single_step_prediction=False, prediction_steps=40,
+                                        noise=None, img=None, pairs=None):
+        """Chained windows (reference :2239-2327): window i is sampled with the DDIM-form loop over every (time, time_next)
+        pair, conditioned on the last conditioned_steps frames of window i - 1 (the given cond for i = 0); returns
+        [B, (n_composed + 1) * rollout_steps, F].  Optional parity inputs: img [windows, B, rollout, F] (the reference's
+        per-window randn) and noise [windows, pairs, 1, B, rollout, F] (its per-pair randn_like)."""
+        if is_single_step_prediction:
+            raise NotImplementedError("is_single_step_prediction needs the cond-4 / rollout-4 model (horizon 8): not on the CUDA fast path")
+        k, r = self.conditioned_steps, self.rollout_steps
+        if not k:
+            raise NotImplementedError("autoregress_time_compose_sample runs on a conditioned model (conditioned_steps > 0)")
+        cond = cond.to(self.device, torch.float32)
+        b, f = cond.shape[0], cond.shape[2]
+        out = torch.empty((b, (n_composed + 1) * r, f), device=self.device, dtype=torch.float32)
+        for i in range(n_composed + 1):
+            seed = self._window_seed(i)
+            frames = self._initial_frames(b, r, f, seed, None if img is None else img[i])
+            state = torch.cat([cond[:, -k:], frames], dim=1).contiguous()
+            state = self._conditioned_ddim(state, 0, None if noise is None else noise[i], pairs, seed)
+            window = state[:, k:]
+            out[:, i * r:(i + 1) * r] = window
+            cond = window                                                           # :2294: cond = img[:, -conditioned_steps:]
+        return out
+
+    def composing_time_sample(self, shape, cond, clip_denoised=True, n_composed=2, noise=None, img=None, pairs=None):
+        """All windows denoised TOGETHER (reference :1806-1854): the batch is n_composed + 1 blocks; before every step block
+        i + 1 takes the last conditioned_steps frames of block i's CURRENT iterate as its condition (:1827-1829).
+        Returns (img [B, rollout, F], img_infered [B, n_composed * 20, F]) like the reference (its `-20:` is kept)."""
+        if not clip_denoised:
+            raise NotImplementedError("clip_denoised=False is not on the CUDA fast path")
+        k = self.conditioned_steps
+        if not k:
+            raise NotImplementedError("composing_time_sample runs on a conditioned model (conditioned_steps > 0)")
+        b, r, f = shape
+        blocks = n_composed + 1
+        frames = self._initial_frames(blocks * b, r, f, self.seed, img)
+        conds = torch.zeros((blocks * b, k, f), device=self.device, dtype=torch.float32)
+        conds[:b] = cond.to(self.device, torch.float32)                            # blocks >= 1 are overwritten before every step
+        state = torch.cat([conds, frames], dim=1).contiguous()
+        state = self._conditioned_ddim(state, blocks, noise, pairs, self.seed)
+        first = state[:b, k:].contiguous()
+        rest = torch.cat([state[i * b:(i + 1) * b, -20:] for i in range(1, blocks)], dim=1) if blocks > 1 else state[:0, -20:]
+        return first, rest.contiguous()
 
     # --- the reference's public sampling API -------------------------------------------------
     def p_sample_loop(self, shape, cond, n_composed=0, compose_start_step=4, compose_n_bodies=2, compose_mode="mean",
@@ -526,8 +650,22 @@ class GaussianDiffusion1D:
         reference's subset).  Like the reference it ignores initialization_mode / initialization_img.  `img` / `noise`
         (optional) replace the Philox draws for parity runs: noise is [pairs, draws, B, T, F] with draws = R + 2
         (R re-noise draws, the unused posterior draw, the DDIM draw) with guidance, 1 without."""
-        if cond is not None or initial_state_overwrite is not None or not clip_denoised:
-            raise NotImplementedError("cond / initial_state_overwrite / clip_denoised=False are not on the CUDA fast path")
+        if initial_state_overwrite is not None or not clip_denoised:
+            raise NotImplementedError("initial_state_overwrite / clip_denoised=False are not on the CUDA fast path")
+        if self.conditioned_steps:
+            # conditioned model: model_predictions(img, cond, t) on cat(cond, img) (:1754-1755); the last pair returns x_start
+            if design_fn is not None:
+                raise NotImplementedError("design guidance on a conditioned model is not on the CUDA fast path")
+            if cond is None:
+                raise ValueError(f"a model with conditioned_steps={self.conditioned_steps} needs cond")
+            b, frames, f = shape
+            x = self._initial_frames(b, frames, f, self.seed, img)
+            state = torch.cat([cond.to(self.device, torch.float32), x], dim=1).contiguous()
+            if noise is not None:
+                noise = noise.reshape(noise.shape[0], 1, b, frames, f)
+            return self._conditioned_ddim(state, 0, noise, pairs, self.seed)[:, self.conditioned_steps:].contiguous()
+        if cond is not None:
+            raise NotImplementedError("cond on an unconditioned model (in-painting by q_sample, :1795-1797) is not on the CUDA fast path")
         n_composed = 0 if n_composed is None else n_composed
         if design_fn is None:
             # the reference calls model_predictions(img, cond, t) WITHOUT the composition kwargs here (:1754-1755): it ignores

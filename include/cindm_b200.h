@@ -37,8 +37,12 @@ enum { CINDM_CONV_SIMT = 0, CINDM_CONV_TCGEN05 = 1 };
  *   "mean-inside" / "sum-inside": composed epsilon inside model_predictions (:959-1001), then one posterior;
  *   "mean" (the API default): p_sample_compose_outside (:1379-1652) - every (window, pair) slice gets its own clamped
  *       x_start and posterior mean, and THOSE are averaged over senders and covering windows (:1446-1451);
- *   "noise_sum": the summed epsilon of :1452-1461, which is the sum-inside operator followed by the same posterior. */
-enum { CINDM_COMPOSE_MEAN_INSIDE = 0, CINDM_COMPOSE_SUM_INSIDE = 1, CINDM_COMPOSE_MEAN_OUTSIDE = 2, CINDM_COMPOSE_NOISE_SUM = 3 };
+ *   "noise_sum": the summed epsilon of :1452-1461, which is the sum-inside operator followed by the same posterior.
+ *   CINDM_COMPOSE_EBM: gradient() (:1856-1982, reached through model_predictions when model_unconditioned is set, :1003):
+ *       sum over the pairs containing a body of the pair model's epsilon for it, minus ebm_uncond_coef x the epsilon of the
+ *       unconditional single-body model (an engine with transition_dim 4 attached by cindm_attach_unconditioned). */
+enum { CINDM_COMPOSE_MEAN_INSIDE = 0, CINDM_COMPOSE_SUM_INSIDE = 1, CINDM_COMPOSE_MEAN_OUTSIDE = 2, CINDM_COMPOSE_NOISE_SUM = 3,
+       CINDM_COMPOSE_EBM = 4 };
 /* design objective: get_design_fn design_fn_mode (inference/inverse_design_diffusion_1d.py:215-222) */
 enum { CINDM_OBJ_L2 = 0, CINDM_OBJ_L2SQUARE = 1 };
 /* guidance scaling: "standard*" (g) or "standard-alpha*" (beta_t/sqrt(abar_prev_t) * g) (:1321-1324) */
@@ -46,7 +50,7 @@ enum { CINDM_GUIDE_NONE = 0, CINDM_GUIDE_STANDARD = 1, CINDM_GUIDE_STANDARD_ALPH
 
 typedef struct {
     int horizon;        /* 24: TemporalUnet1D(horizon=...)            model/diffusion_1d.py:521 */
-    int transition_dim; /* 8 : two bodies x (x,y,vx,vy)                                     :522 */
+    int transition_dim; /* 8 : two bodies x (x,y,vx,vy); 4: the unconditional single-body model  :522 */
     int dim;            /* 64: Unet_dim                                                     :524 */
     int timesteps;      /* 1000: GaussianDiffusion1D(timesteps=...)                         :810 */
 } cindm_config;
@@ -153,6 +157,21 @@ int cindm_composed_eps(cindm_engine* e, const float* x_dev, float* eps_dev, int 
 int cindm_composed_posterior(cindm_engine* e, const float* x_dev, float* mean_dev, float* x0_dev, int batch, int n_bodies,
                              int n_composed, int compose_start_step, int t, int precision, int conv_engine, void* stream);
 
+/* ---- EBM body composition (inference_1d_composing_multibodies.py:224-226 -> sample_compose_multibodies :1985-2042) ----
+ * cindm_attach_unconditioned: `single` (created with transition_dim = 4, weights of the unconditional single-body model
+ * loaded) becomes the model_unconditioned of `e` (:827); not owned, must outlive e's sampling calls; NULL detaches.
+ * cindm_ebm_eps: gradient() for t <= 400 (:1856-1982): x[B][24][4n] -> eps[B][24][4n] =
+ *   sum_{s != r} eps_pair({r,s})[slot(r)] - uncond_coef * eps_single(body r)      (uncond_coef 1.4 for 4 bodies :1904, 1 for 3 :1961)
+ * cindm_ula_step: one unadjusted-Langevin update of sample_step_ULA (:2047-2073) on all frames:
+ *   x_out = x + (grad_scale * eps) * step_size + sqrt(2 step_size) * noise      (grad_scale = -scalar_for_gradient[t] for t > 400)
+ *   noise_dev == NULL draws Philox N(0,1) keyed by (seed, candidate, t, draw). */
+int cindm_attach_unconditioned(cindm_engine* e, cindm_engine* single);
+int cindm_ebm_eps(cindm_engine* e, const float* x_dev, float* eps_dev, int batch, int n_bodies, float uncond_coef, int t,
+                  int precision, int conv_engine, void* stream);
+int cindm_ula_step(const float* x_dev, const float* eps_dev, const float* noise_dev, float* x_out_dev, int batch, int t_total,
+                   int n_bodies, float grad_scale, float step_size, uint64_t seed, int64_t candidate_offset, int t, int draw,
+                   void* stream);
+
 /* ---- guidance gradient: replaces torch.autograd.grad(design_fn(x), x) (:1316-1320) with the
  *      closed form of get_design_fn (inference/inverse_design_diffusion_1d.py:211-229) --------- */
 int cindm_design_grad(const float* x_dev, float* grad_dev, int batch, int t_total, int n_bodies,
@@ -167,6 +186,11 @@ int cindm_design_grad(const float* x_dev, float* grad_dev, int batch, int t_tota
 int cindm_posterior_update(cindm_engine* e, const float* x_dev, const float* eps_dev, const float* noise_dev,
                            float* x_out_dev, float* pred_out_dev, float* x0_out_dev, int batch, int t_total,
                            int n_bodies, int t, int renoise, const cindm_objective* obj, void* stream);
+
+/* x_start = sqrt(1/abar_t) x - sqrt(1/abar_t - 1) eps, optionally clamped to [-1, 1]: predict_start_from_noise (:914-918) with
+ * the `maybe_clip` of model_predictions (:1009-1013).  elems = number of floats (a multiple of 4). */
+int cindm_predict_start(cindm_engine* e, const float* x_dev, const float* eps_dev, float* x0_out_dev, int64_t elems, int t,
+                        int clip, void* stream);
 
 /* ---- the sampling loop: p_sample_loop / p_sample_compose_inside (:1655-1720, :1189-1376) ----
  * x_dev[B][T][4n] holds the initial noise on entry and the designs on exit.  noise_dev == NULL

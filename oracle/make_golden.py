@@ -348,7 +348,135 @@ def gen_ddim(m, dif, ns):
     return {k: list(v) for k, v in DDIM_CASES.items()}
 
 
+# ---------------------------------------------------------------------------------------------
+# conditioned model: GaussianDiffusion1D(image_size=20, conditioned_steps=4) around the same 24-frame
+# U-Net.  The reference builds its DDIM grid from self.num_timesteps (linspace(-1, T-1, S+1), :1741, :1810, :2246); the runs
+# below set that attribute to 500 on the reference OBJECT (code untouched, the 1000-entry schedule buffers are simply
+# indexed up to 499) so that the grid starts at t = 499 instead of t = 999, where x_start = A_t x - B_t eps would multiply
+# fp32 rounding differences by 2e4 and make whole-run goldens useless at the 1e-5 bar.
+# ---------------------------------------------------------------------------------------------
+COND_GRID_T = 500
+
+
+def build_reference_conditioned(sd, sampling_timesteps, eta):
+    m = ref_shim.load()
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = m.TemporalUnet1D(horizon=HORIZON, transition_dim=8, cond_dim=False, dim=64, dim_mults=(1, 2, 4, 8), attention=True)
+        dif = m.GaussianDiffusion1D(net, image_size=20, conditioned_steps=4, timesteps=1000,
+                                    sampling_timesteps=sampling_timesteps, loss_type="l1", ddim_sampling_eta=eta)
+    net.load_state_dict(sd)
+    dif.eval()
+    return m, dif
+
+
+def _grid_pairs(total, steps):
+    times = torch.linspace(-1, total - 1, steps=steps + 1)
+    times = list(reversed(times.int().tolist()))
+    return list(zip(times[:-1], times[1:]))
+
+
+def gen_conditioned(sd):
+    out = {}
+    real_randn_like, real_randn = torch.randn_like, torch.randn
+    b = 2
+    cond = seeded((b, 4, 8), 31) * 0.5
+    out["cond"] = cond.numpy()
+
+    def recording(gen, draws):
+        def logged_randn_like(t, **kw):
+            z = real_randn(t.shape, generator=gen, dtype=t.dtype)
+            draws.append(z)
+            return z
+
+        def logged_randn(*shape, **kw):
+            shape = tuple(shape[0]) if len(shape) == 1 and not isinstance(shape[0], int) else tuple(shape)
+            z = real_randn(shape, generator=gen)
+            draws.append(z)
+            return z
+        return logged_randn_like, logged_randn
+
+    # (1) model_predictions with cond: cat, model, x_start, slice (:956-957, :1009-1013, :1028-1030)
+    m, dif = build_reference_conditioned(sd, 1000, 0.0)
+    x = seeded((b, 20, 8), 32)
+    for t, clip in ((300, True), (980, False)):
+        m.grad_mean_list.clear()
+        with torch.no_grad():
+            pr = dif.model_predictions(x, cond, torch.full((b,), t, dtype=torch.long), None, clip_x_start=clip)
+        out[f"mp_t{t}:x"] = x.numpy()
+        out[f"mp_t{t}:eps"] = pr.pred_noise.numpy()
+        out[f"mp_t{t}:x0"] = pr.pred_x_start.numpy()
+
+    # (2) ddim_sample with cond (:1723-1804)
+    steps, eta = 4, 0.5
+    m, dif = build_reference_conditioned(sd, steps, eta)
+    dif.num_timesteps = COND_GRID_T
+    draws = []
+    torch.randn_like, torch.randn = recording(torch.Generator().manual_seed(41), draws)
+    try:
+        m.grad_mean_list.clear()
+        with torch.no_grad():
+            img = dif.ddim_sample((b, 20, 8), cond)
+    finally:
+        torch.randn_like, torch.randn = real_randn_like, real_randn
+    assert len(draws) == 1 + steps
+    out["ddim:x_init"] = draws[0].numpy()
+    out["ddim:noise"] = torch.stack(draws[1:]).numpy()
+    out["ddim:img"] = img.numpy()
+    out["ddim:pairs"] = np.asarray(_grid_pairs(COND_GRID_T, steps), dtype=np.int32)
+    out["ddim:eta"] = np.float64(eta)
+
+    # (3) autoregress_time_compose_sample (:2239-2327): 3 chained windows
+    steps, eta, nc = 3, 0.3, 2
+    m, dif = build_reference_conditioned(sd, steps, eta)
+    dif.num_timesteps = COND_GRID_T
+    draws = []
+    torch.randn_like, torch.randn = recording(torch.Generator().manual_seed(42), draws)
+    try:
+        m.grad_mean_list.clear()
+        with torch.no_grad():
+            y = dif.autoregress_time_compose_sample(batch_size=b, cond=cond, n_composed=nc, is_single_step_prediction=False,
+                                                    prediction_steps=20 * (nc + 1))
+    finally:
+        torch.randn_like, torch.randn = real_randn_like, real_randn
+    assert len(draws) == 1 + (nc + 1) * (1 + steps)              # img_composed, then per window: img + one draw per pair
+    per = 1 + steps
+    out["auto:x_init"] = torch.stack([draws[1 + w * per] for w in range(nc + 1)]).numpy()
+    out["auto:noise"] = torch.stack([torch.stack(draws[2 + w * per: 1 + (w + 1) * per]) for w in range(nc + 1)]).numpy()
+    out["auto:out"] = y.numpy()
+    out["auto:pairs"] = np.asarray(_grid_pairs(COND_GRID_T, steps), dtype=np.int32)
+    out["auto:eta"] = np.float64(eta)
+
+    # (4) composing_time_sample (:1806-1854): 3 blocks denoised together, conditions chained every step
+    m, dif = build_reference_conditioned(sd, steps, eta)
+    dif.num_timesteps = COND_GRID_T
+    draws = []
+    torch.randn_like, torch.randn = recording(torch.Generator().manual_seed(43), draws)
+    try:
+        m.grad_mean_list.clear()
+        with torch.no_grad():
+            first, rest = dif.composing_time_sample((b, 20, 8), cond, True, nc)
+    finally:
+        torch.randn_like, torch.randn = real_randn_like, real_randn
+    assert len(draws) == 6 + steps                                # six initial randn tensors, then one randn_like per pair
+    out["chain:x_init"] = draws[1].numpy()                        # img_infered [(nc+1)*B, 20, 8]
+    out["chain:noise"] = torch.stack(draws[6:]).numpy()
+    out["chain:img"] = first.numpy()
+    out["chain:img_infered"] = rest.numpy()
+    out["chain:pairs"] = np.asarray(_grid_pairs(COND_GRID_T, steps), dtype=np.int32)
+    out["chain:eta"] = np.float64(eta)
+    np.savez_compressed(os.path.join(GOLDEN, "conditioned.npz"), **out)
+    return {"batch": b, "n_composed": nc, "grid_timesteps": COND_GRID_T}
+
+
 def main():
+    if "--only-conditioned" in sys.argv:
+        torch.set_num_threads(os.cpu_count())
+        sd = init_unet_params(seed=0, randomize_affine=True)
+        meta = json.load(open(os.path.join(GOLDEN, "meta.json")))
+        meta["conditioned"] = gen_conditioned(sd)
+        json.dump(meta, open(os.path.join(GOLDEN, "meta.json"), "w"), indent=1)
+        print("conditioned.npz", os.path.getsize(os.path.join(GOLDEN, "conditioned.npz")))
+        return
     if "--only-ddim" in sys.argv or "--only-outside" in sys.argv:
         # add the DDIM / compose-outside vectors without regenerating the other files
         torch.set_num_threads(os.cpu_count())
@@ -376,7 +504,9 @@ def main():
     gen_trajectories(m, dif, ns)
     ddim_cases = gen_ddim(m, dif, ns)
     outside_cases = gen_outside(m, dif, ns)
+    conditioned = gen_conditioned(sd)
     meta = {
+        "conditioned": conditioned,
         "ddim_cases": ddim_cases,
         "outside_cases": outside_cases,
         "weights": "cindm_b200.model.params.init_unet_params(seed=0, randomize_affine=True)",

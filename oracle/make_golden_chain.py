@@ -35,8 +35,8 @@ GOLDEN = make_golden.GOLDEN
 
 # name: (n_bodies, n_composed, start, guidance, compose_mode, coef, cc, B, torch seed)
 CHAIN_CASES = {
-    # BASELINE.json config 1 (2-body, 24 steps, batch 50) with the cheap guidance variant
-    "c1_2body_std": (2, 0, 10, "standard", "mean-inside", 0.4, 0.1, 50, 1234),
+    # BASELINE.json config 1 (2-body, 24 steps) with the cheap guidance variant; 256 candidates tighten the comparison
+    "c1_2body_std": (2, 0, 10, "standard", "mean-inside", 0.4, 0.1, 256, 1234),
     # BASELINE.json config 1 with the paper's recurrence guidance, shortened to R=3
     "c1_2body_rec3": (2, 0, 10, "standard-recurrence-3", "mean-inside", 0.4, 0.1, 50, 4321),
     # body AND time composition together: 4 bodies (6 pairs) x 2 windows, recurrence
