@@ -3,6 +3,8 @@
 #pragma once
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <map>
 #include <string>
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -209,9 +211,31 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     return fn;
 }
 
+// Encoded descriptors are cached per translation unit: a descriptor is a pure function of (base, type, extents, box), the
+// workspace and weight buffers are long-lived, and an un-graphed evaluation would otherwise call the driver's encoder
+// 3-4 times for each of its ~70 launches.  (Not thread-safe per engine, like the rest of the step functions.)
+struct MapKey {
+    const void* base; long long a, b, c; int prec, kind, x, y, z;
+    bool operator<(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) < 0; }
+};
+inline bool map_cache_get(const MapKey& k, CUtensorMap* out, std::map<MapKey, CUtensorMap>*& cache) {
+    static std::map<MapKey, CUtensorMap> table;
+    cache = &table;
+    if (table.size() > 4096) table.clear();            // workspaces were re-allocated many times: start over
+    auto it = table.find(k);
+    if (it == table.end()) return false;
+    *out = it->second;
+    return true;
+}
+
 // box_rows positions per slice are loaded, every h_stride-th position starting at the tap's H coordinate
 int encode_act_map(CUtensorMap* map, const void* base, int prec, long long S, int H, int C, int box_slices,
                    int box_rows, int h_stride) {
+    MapKey key;
+    memset(&key, 0, sizeof key);
+    key.base = base; key.a = S; key.b = H; key.c = C; key.prec = prec; key.kind = 1; key.x = box_slices; key.y = box_rows; key.z = h_stride;
+    std::map<MapKey, CUtensorMap>* cache = nullptr;
+    if (map_cache_get(key, map, cache)) return 0;
     auto enc = get_encode();
     if (!enc) return fail(-100, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)S};
@@ -222,10 +246,16 @@ int encode_act_map(CUtensorMap* map, const void* base, int prec, long long S, in
                      const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(-100, "cuTensorMapEncodeTiled(activations) failed: " + std::to_string((int)r));
+    (*cache)[key] = *map;
     return 0;
 }
 
 int encode_weight_map(CUtensorMap* map, const void* base, int prec, int rows, int cin, int box_rows) {
+    MapKey key;
+    memset(&key, 0, sizeof key);
+    key.base = base; key.a = rows; key.b = cin; key.prec = prec; key.kind = 2; key.x = box_rows;
+    std::map<MapKey, CUtensorMap>* cache = nullptr;
+    if (map_cache_get(key, map, cache)) return 0;
     auto enc = get_encode();
     if (!enc) return fail(-100, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)rows};
@@ -236,6 +266,7 @@ int encode_weight_map(CUtensorMap* map, const void* base, int prec, int rows, in
                      const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(-100, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r));
+    (*cache)[key] = *map;
     return 0;
 }
 

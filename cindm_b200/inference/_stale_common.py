@@ -1,9 +1,9 @@
 """Shared pieces of the two older reference drivers (inference_1d_composing_time_steps.py and
-inference_1d_composing_multibodies.py).  Both are stale at the reference's HEAD (pre-package imports, an API
-that drifted: SURVEY.md section 0 item 9, section 3.5); their command-line surface is kept verbatim and their
-`EBMs_compose` branches are mapped onto the LIVE composition operator (p_sample_loop -> p_sample_compose_inside
--> model_predictions), their `SimuSolver` branches onto the CUDA rollout.  Every other method needs models that
-are outside the hot path (GNS, forward model, direct / autoregressive conditioned diffusion) and raises."""
+inference_1d_composing_multibodies.py).  Both are stale at the reference's HEAD (pre-package imports, an API that drifted:
+SURVEY.md section 0 item 9, section 3.5); their command-line surface is kept verbatim and their diffusion branches run the
+methods they were written for -- autoregress_time_compose_sample / composing_time_sample on the conditioned 4 + 20-frame
+model, sample_compose_multibodies with the unconditional single-body model -- on the CUDA path; `SimuSolver` runs the CUDA
+ground-truth rollout.  GNS / Forward_model / direct models are surrogates outside the hot path and raise."""
 import os
 
 import numpy as np
@@ -40,28 +40,54 @@ def add_common_flags(parser, date_default, val_batch_default, sample_steps_defau
     parser.add_argument("--conv_engine", default="tcgen05", choices=["simt", "tcgen05"])
     parser.add_argument("--seed", default=0, type=int)
     parser.add_argument("--results_dir", default="results/composing", type=str)
+    parser.add_argument("--cond_npy", default=None, type=str,
+                        help="[B, conditioned_steps, n_bodies*4] normalised condition frames; default: the first batch of the "
+                             "reference's dataset under --dataset_path")
 
 
 def build_diffusion(args, device):
-    """The 24-frame 2-body model both scripts build (conditioned_steps + rollout_steps = 24 frames, :119-131)."""
+    """The conditioned 2-body model both scripts build: horizon = conditioned_steps + rollout_steps = 24 frames,
+    GaussianDiffusion1D(image_size=rollout_steps, conditioned_steps=conditioned_steps, sampling_timesteps=sample_steps)
+    (inference_1d_composing_time_steps.py:119-138, inference_1d_composing_multibodies.py:121-165)."""
     horizon = args.conditioned_steps + args.rollout_steps
     setup_seed(args.seed)
     model = TemporalUnet1D(horizon=horizon, transition_dim=2 * args.num_features, cond_dim=False, dim=64,
                            dim_mults=(1, 2, 4, 8), attention=args.attention, seed=args.seed)
-    diffusion = GaussianDiffusion1D(model, image_size=horizon, conditioned_steps=0, timesteps=1000,
+    diffusion = GaussianDiffusion1D(model, image_size=args.rollout_steps, conditioned_steps=args.conditioned_steps, timesteps=1000,
                                     sampling_timesteps=args.sample_steps, loss_type="l1").to(device)
     if args.checkpoint_path_basic_model:
-        ckpt = torch.load(args.checkpoint_path_basic_model, map_location="cpu")
+        ckpt = torch.load(args.checkpoint_path_basic_model, map_location="cpu", weights_only=False)
         diffusion.load_state_dict(ckpt["model"])
     diffusion.precision, diffusion.conv_engine, diffusion.seed = args.precision, args.conv_engine, args.seed
     return diffusion
 
 
-def simu_solver(first_frame, n_bodies, n_frames, time_interval=4):
-    """`SimuSolver`: roll the ground-truth simulator forward from one normalised frame [B, n*4] -> [B, n_frames, n*4]."""
-    state = (first_frame * 200.0).reshape(first_frame.shape[0], n_bodies, 4)
-    traj = simulation(state, n_frames * time_interval, stride=time_interval)
-    return (traj.reshape(traj.shape[0], traj.shape[1], -1) / 200.0).float()
+def load_condition(args, n_bodies, output_steps):
+    """cond [B, conditioned_steps, n_bodies*4] (normalised): --cond_npy, else the first unshuffled batch of the reference's
+    dataset (the reference shuffles its DataLoader, inference_1d_composing_time_steps.py:165; any batch of the split serves)."""
+    if args.cond_npy:
+        cond = torch.from_numpy(np.load(args.cond_npy)).float()
+    else:
+        from ..data import NBodyDataset, first_batch_1d
+        dataset = NBodyDataset(dataset=f"nbody-{n_bodies}", input_steps=args.conditioned_steps, output_steps=output_steps,
+                               time_interval=args.time_interval, is_y_diff=False, is_train=not args.is_test, is_testdata=False,
+                               dataset_path=args.dataset_path)
+        cond = first_batch_1d(dataset, args.val_batch_size, "x")
+    cond = cond[:args.val_batch_size]
+    if cond.dim() != 3 or cond.shape[1] != args.conditioned_steps or cond.shape[2] != n_bodies * args.num_features:
+        raise ValueError(f"condition frames have shape {tuple(cond.shape)}, expected [B, {args.conditioned_steps}, {n_bodies * args.num_features}]")
+    return cond
+
+
+def simu_solver(cond, n_bodies, n_steps):
+    """`SimuSolver` (inference_1d_composing_time_steps.py:330-347): roll the ground-truth simulator n_steps forward from the
+    LAST condition frame (x200 -> pixel units); y = states after 4, 8, ... steps and, as the reference appends it, the final
+    recorded state (after n_steps - 1 steps), normalised again."""
+    state = (cond[:, -1] * 200.0).reshape(cond.shape[0], n_bodies, 4)
+    traj = simulation(state, n_steps, stride=1)                       # entry k = state after k steps
+    flat = traj.reshape(traj.shape[0], traj.shape[1], -1)
+    y = flat[:, ::4] / 200.0
+    return torch.cat([y[:, 1:], flat[:, -1:] / 200.0], dim=1).float()
 
 
 def save(args, name, array):

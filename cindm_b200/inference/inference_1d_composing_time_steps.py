@@ -1,9 +1,10 @@
 """Flag-compatible mirror of the reference's inference/inference_1d_composing_time_steps.py (flags :25-67).
 
-`--time_compose_method EBMs_compose` (reference :171-178, broken at HEAD) runs the LIVE time-composition operator:
-a trajectory of 24 + n_composed*10 frames from overlapping 24-frame windows (`compose_mode=mean-inside`,
-`compose_start_step=10`), on the CUDA path.  `SimuSolver` rolls the CUDA ground-truth simulator.  The other
-methods (autoregress, direct, GNS, Forward_model) need conditioned / surrogate models outside the hot path."""
+`--time_compose_method autoregress` (the default, reference :179-217) samples n_composed + 1 chained 20-frame windows with
+GaussianDiffusion1D.autoregress_time_compose_sample on the conditioned 4 + 20-frame model; `EBMs_compose` (:171-178, whose
+`sample(is_composing_time=True)` call is broken at the reference's HEAD) runs the method that branch was written for,
+composing_time_sample: all windows denoised together with the conditions chained at every step; `SimuSolver` (:330-347) rolls
+the CUDA ground-truth simulator.  direct / GNS / Forward_model need other models (out of scope) and raise."""
 import argparse
 
 import torch
@@ -25,23 +26,26 @@ def build_parser():
 
 def analyse(args):
     device = torch.device("cuda")
-    if args.time_compose_method == "EBMs_compose":
+    n_bodies, r, nc = 2, args.rollout_steps, args.n_composed
+    cond = common.load_condition(args, n_bodies, r * (nc + 1)).to(device)
+    b = cond.shape[0]
+    if args.time_compose_method == "autoregress":
         diffusion = common.build_diffusion(args, device)
-        pred = diffusion.sample(batch_size=args.val_batch_size, cond=None, is_composing_time=True, n_composed=args.n_composed,
-                                compose_start_step=10, compose_n_bodies=2, compose_mode="mean-inside", design_fn=None,
-                                design_guidance="standard")
+        y = diffusion.autoregress_time_compose_sample(batch_size=b, cond=cond, n_composed=nc,
+                                                      is_single_step_prediction=args.is_single_step_prediction,
+                                                      prediction_steps=r * (1 + nc))
+    elif args.time_compose_method == "EBMs_compose":
+        diffusion = common.build_diffusion(args, device)
+        pred, pred_infered = diffusion.composing_time_sample((b, r, cond.shape[2]), cond, True, nc)
+        y = torch.cat([pred, pred_infered], dim=1)
     elif args.time_compose_method == "SimuSolver":
-        gen = torch.Generator().manual_seed(args.seed)
-        frame0 = torch.rand(args.val_batch_size, 8, generator=gen) * 0.6 + 0.2
-        frame0[:, 2::4] = frame0[:, 2::4] - 0.5
-        frame0[:, 3::4] = frame0[:, 3::4] - 0.5
-        pred = common.simu_solver(frame0.to(device), 2, args.rollout_steps + args.n_composed * 10)
+        y = common.simu_solver(cond, n_bodies, r * (nc + 1) * args.time_interval)
     else:
-        raise NotImplementedError(f"time_compose_method {args.time_compose_method!r}: only EBMs_compose and SimuSolver run on the "
-                                  "CUDA fast path (the others need conditioned / surrogate models that are out of scope)")
-    path = common.save(args, f"time_compose_{args.time_compose_method}_n_composed-{args.n_composed}", pred.cpu().numpy())
-    print(f"{args.time_compose_method}: trajectory {tuple(pred.shape)} -> {path}")
-    return pred
+        raise NotImplementedError(f"time_compose_method {args.time_compose_method!r}: autoregress, EBMs_compose and SimuSolver run on "
+                                  "the CUDA path (direct / GNS / Forward_model need surrogate or longer-horizon models: out of scope)")
+    path = common.save(args, f"time_compose_{args.time_compose_method}_n_composed-{nc}", y.cpu().numpy())
+    print(f"{args.time_compose_method}: trajectory {tuple(y.shape)} -> {path}")
+    return y
 
 
 def main(argv=None):

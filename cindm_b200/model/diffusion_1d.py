@@ -201,8 +201,9 @@ class TemporalUnet1D:
         self.dim_mults = tuple(dim_mults)
         self.attention = attention
         self._shapes = unet_param_shapes(horizon, transition_dim, dim, self.dim_mults, attention)
-        if dim != 64 or self.dim_mults != (1, 2, 4, 8) or horizon != 24 or transition_dim != 8:
-            raise NotImplementedError("CUDA fast path is built for horizon=24, transition_dim=8, dim=64, dim_mults=(1,2,4,8)")
+        if dim != 64 or self.dim_mults != (1, 2, 4, 8) or horizon != 24 or transition_dim not in (8, 4):
+            raise NotImplementedError("CUDA fast path is built for horizon=24, dim=64, dim_mults=(1,2,4,8) and transition_dim 8 "
+                                      "(body-pair model) or 4 (unconditional single-body model)")
         self._params = init_unet_params(self._shapes, seed=seed)
         self._device = torch.device("cpu")
         self._engine = None
@@ -306,10 +307,11 @@ class GaussianDiffusion1D:
         if conditioned_steps < 0 or image_size + conditioned_steps != model.horizon:
             raise NotImplementedError(f"image_size + conditioned_steps must equal the model horizon ({model.horizon}): "
                                       "the model sees cat(cond, x) (reference :956-957)")
-        if model_unconditioned is not None:
-            raise NotImplementedError("model_unconditioned (EBM body composition) is not on the CUDA fast path")
         self.model = model
-        self.model_unconditioned = None
+        # EBM body composition (reference :827, :1002-1003): an unconditional single-body TemporalUnet1D (transition_dim 4); the
+        # stale driver assigns the attribute after construction (inference_1d_composing_multibodies.py:169), so it is a property
+        self._model_unconditioned = None
+        self.model_unconditioned = model_unconditioned
         self.betas_inference = betas_inference
         self.channels = model.channels
         self.image_size = image_size
@@ -341,8 +343,40 @@ class GaussianDiffusion1D:
         self.candidate_offset = 0        # global id of local candidate 0 (multi-GPU sharding)
         self.use_cuda_graph = True
         self.last_x_start = None
+        # fp16 activations overflow at 65 504 (the residual stream, the 1x1 residual convs and the down / up-sampling convs are
+        # stored un-normalised); an overflow turns into inf -> NaN in the next GroupNorm and reaches the output, so it is
+        # detected on the result.  "bf16": re-run the call with bf16 activations (same Philox noise) and count the event;
+        # "raise": fail; "ignore": return what fp16 produced.
+        self.on_fp16_overflow = "bf16"
+        self.fp16_overflow_events = 0
 
     # --- nn.Module-like surface -------------------------------------------------------------
+    @property
+    def model_unconditioned(self):
+        return self._model_unconditioned
+
+    @model_unconditioned.setter
+    def model_unconditioned(self, m):
+        if m is not None and (not isinstance(m, TemporalUnet1D) or m.transition_dim != 4 or m.horizon != self.model.horizon):
+            raise NotImplementedError("model_unconditioned must be a cindm_b200 TemporalUnet1D with transition_dim=4 and the pair "
+                                      "model's horizon (the reference's single-body model, inference_1d_composing_multibodies.py:130-137)")
+        self._model_unconditioned = m
+        if m is not None:
+            m._timesteps = self.num_timesteps if hasattr(self, "num_timesteps") else m._timesteps
+
+    def _attach_unconditioned(self):
+        """Both engines exist on the sampler's device and the pair engine knows its unconditional partner."""
+        m = self._model_unconditioned
+        if m is None:
+            raise ValueError("model_unconditioned is not set")
+        m._timesteps = self.num_timesteps
+        m.to(self.device)
+        m.precision, m.conv_engine = self.precision, self.conv_engine
+        eng, ueng = self.model.engine(), m.engine()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cindm_attach_unconditioned(eng.handle, ueng.handle))
+        return eng
+
     @property
     def is_ddim_sampling(self):
         return self.sampling_timesteps < self.num_timesteps
@@ -377,6 +411,21 @@ class GaussianDiffusion1D:
     def device(self):
         return self.model._device
 
+    def _guard_fp16(self, run):
+        """run() -> tensor; re-run in bf16 (or raise) when the fp16 path produced non-finite values (see on_fp16_overflow)."""
+        out = run()
+        if self.precision != "fp16" or self.on_fp16_overflow == "ignore" or bool(torch.isfinite(out).all()):
+            return out
+        if self.on_fp16_overflow == "raise":
+            raise _lib.CindmError("non-finite result on the fp16 path: activation overflow (|x| > 65504) suspected; "
+                                  "use precision='bf16' (or on_fp16_overflow='bf16')")
+        self.fp16_overflow_events += 1
+        self.precision = "bf16"
+        try:
+            return run()
+        finally:
+            self.precision = "fp16"
+
     # --- pieces of the step, exposed for parity tests ---------------------------------------
     def _prec(self):
         return _lib.PRECISIONS[self.precision]
@@ -389,13 +438,16 @@ class GaussianDiffusion1D:
         eng = self.model.engine()
         x = x.to(self.device, torch.float32).contiguous()
         b, t_total, f = x.shape
-        assert f == 4 * compose_n_bodies and t_total == self.image_size + n_composed * compose_start_step
-        eps = torch.empty_like(x)
-        with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().cindm_composed_eps(
-                eng.handle, _lib.ptr(x), _lib.ptr(eps), b, compose_n_bodies, n_composed, compose_start_step,
-                _compose_mode(compose_mode), int(t), self._prec(), self._conv(), _lib.stream_ptr(self.device)))
-        return eps
+        assert f == 4 * compose_n_bodies and t_total == self.model.horizon + n_composed * compose_start_step
+
+        def run():
+            eps = torch.empty_like(x)
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().cindm_composed_eps(
+                    eng.handle, _lib.ptr(x), _lib.ptr(eps), b, compose_n_bodies, n_composed, compose_start_step,
+                    _compose_mode(compose_mode), int(t), self._prec(), self._conv(), _lib.stream_ptr(self.device)))
+            return eps
+        return self._guard_fp16(run)
 
     def design_grad(self, x, design_fn):
         """Closed-form gradient of a DesignObjective (replaces autograd at reference :1316-1320)."""
@@ -492,6 +544,8 @@ class GaussianDiffusion1D:
             assert kwargs["single_model_step"] > 0                                 # reference :965
             eps = self.composed_eps(full, tt, kwargs["n_composed"], kwargs["compose_start_step"], kwargs["compose_n_bodies"],
                                     kwargs["compose_mode"])
+        elif self._model_unconditioned is not None:
+            eps = self.gradient(full, tt, 4)                                       # (:1002-1003: n_bodies is hard-wired to 4)
         else:
             self.model.precision, self.model.conv_engine = self.precision, self.conv_engine
             eps = self.model(full, tt, None)
@@ -584,6 +638,126 @@ class GaussianDiffusion1D:
         first = state[:b, k:].contiguous()
         rest = torch.cat([state[i * b:(i + 1) * b, -20:] for i in range(1, blocks)], dim=1) if blocks > 1 else state[:0, -20:]
         return first, rest.contiguous()
+
+    def p_sample(self, x, cond, t, x_self_cond=None, clip_denoised=True, design_fn=None, design_guidance="standard",
+                 initial_state_overwrite=None, noise=None):
+        """One reverse step t -> t-1 WITHOUT composition arguments (reference :1046-1186): -> (pred_img, x_start).
+
+        conditioned_steps > 0: the model sees cat(cond, x); with model_unconditioned set its epsilon is gradient() (the EBM
+        body composition, :1002-1003).  conditioned_steps = 0: the plain 2-body model, i.e. the 1-window, 1-pair operator.
+        noise (optional) [1, B, frames, F]: the reference's randn_like draw."""
+        if initial_state_overwrite is not None or not clip_denoised:
+            raise NotImplementedError("initial_state_overwrite / clip_denoised=False are not on the CUDA fast path")
+        k = self.conditioned_steps
+        if not k:
+            if cond is not None:
+                raise NotImplementedError("cond on an unconditioned model is not on the CUDA fast path")
+            return self.p_sample_compose_inside(x, None, t, None, True, design_fn, design_guidance, None, "mean-inside", 0,
+                                                self.model.horizon - 1, self.model.horizon, x.shape[-1] // 4, noise)
+        if design_fn is not None:
+            raise NotImplementedError("design guidance on a conditioned model is not on the CUDA fast path")
+        x = x.to(self.device, torch.float32)
+        b, frames, f = x.shape
+        ebm = self._model_unconditioned is not None
+        eng = self._attach_unconditioned() if ebm else self.model.engine()
+        state = torch.cat([cond.to(self.device, torch.float32), x], dim=1).contiguous()
+        cfg = self._sample_config(b, 0, self.model.horizon - 1, f // 4, "mean-inside", None, "standard", int(t), int(t), False,
+                                  cond_rows=k, ebm_uncond_coef=self._ebm_coef(4) if ebm else 0.0)
+        if ebm:
+            if f != 16:
+                raise NotImplementedError("model_predictions calls gradient(x, t, 4): four bodies (reference :1003)")
+            cfg.compose_mode = _lib.COMPOSE_EBM
+        if noise is not None:
+            noise = noise.to(self.device, torch.float32).reshape(1, b, frames, f).contiguous()
+        x0 = torch.empty_like(state)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cindm_sample(eng.handle, ctypes.byref(cfg), _lib.ptr(state), _lib.ptr(noise) if noise is not None else None,
+                                               _lib.ptr(x0), _lib.stream_ptr(self.device)))
+        return state[:, k:].contiguous(), x0[:, k:].contiguous()
+
+    # --- EBM body composition with the unconditional single-body model (SURVEY section 8 f3) ----------------------
+    @staticmethod
+    def _ebm_coef(n_bodies):
+        if n_bodies == 4:
+            return 1.4                                   # coefficient_unconditioned_grad (:1904)
+        if n_bodies == 3:
+            return 1.0                                   # (:1961-1963)
+        raise NotImplementedError("gradient() is written for 4 and 3 bodies (reference :1866, :1932)")
+
+    def gradient(self, x_t, t, n_bodies, scalar_for_gradient=None):
+        """Composed epsilon of the EBM body composition (reference :1856-1982): x_t [B, 24, 4n] ->
+        sum over the pairs containing a body of the pair model's epsilon for it - coef * unconditional single-body epsilon;
+        for t > 400 scaled by -scalar_for_gradient[t] like the reference.  (The reference's 3-body branch hard-codes a batch of
+        20, :1958-1960; here any batch works and equals the reference at B = 20.)"""
+        eng = self._attach_unconditioned()
+        x = x_t.to(self.device, torch.float32).contiguous()
+        b, frames, f = x.shape
+        assert f == 4 * n_bodies and frames == self.model.horizon
+        tt = int(t.reshape(-1)[0].item()) if torch.is_tensor(t) else int(t)
+        eps = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cindm_ebm_eps(eng.handle, _lib.ptr(x), _lib.ptr(eps), b, n_bodies, self._ebm_coef(n_bodies), tt,
+                                                self._prec(), self._conv(), _lib.stream_ptr(self.device)))
+        if tt > 400:
+            return -1 * scalar_for_gradient[tt].to(self.device) * eps            # (:1921-1922) one scalar multiply of the result
+        return eps
+
+    def sample_step_ULA(self, x, ts, num_samples_per_step, n_bodies, N, scalar_for_gradient, noise=None):
+        """num_samples_per_step unadjusted-Langevin updates at timestep ts[0] (reference :2047-2073); all frames move,
+        the condition frames included.  noise (optional) [L, B, 24, 4n] replaces the Philox draws."""
+        eng = self._attach_unconditioned()
+        t = int(ts[0])
+        ss = float((self.betas_inference.to(torch.float32) * 0.035)[t])          # fp32, like the reference's tensor product
+        gscale = float(-scalar_for_gradient[t]) if t > 400 else 1.0
+        x = x.to(self.device, torch.float32).contiguous()
+        b, frames, f = x.shape
+        eps = torch.empty_like(x)
+        L = _lib.lib()
+        for i in range(num_samples_per_step):
+            out = torch.empty_like(x)
+            nz = None if noise is None else noise[i].to(self.device, torch.float32).contiguous()
+            with torch.cuda.device(self.device):
+                _lib.check(L.cindm_ebm_eps(eng.handle, _lib.ptr(x), _lib.ptr(eps), b, n_bodies, self._ebm_coef(n_bodies), t,
+                                           self._prec(), self._conv(), _lib.stream_ptr(self.device)))
+                _lib.check(L.cindm_ula_step(_lib.ptr(x), _lib.ptr(eps), _lib.ptr(nz), _lib.ptr(out), b, frames, n_bodies, gscale, ss,
+                                            self.seed, self.candidate_offset, t, i, _lib.stream_ptr(self.device)))
+            x = out
+        return x
+
+    def sample_compose_multibodies(self, cond, N, L, n_bodies, noise=None, img=None, ula_noise=None):
+        """More bodies from the 2-body model (reference :1985-2042): timesteps i = N-1 .. 0; for i > 400 L Langevin updates on
+        gradient(), else one p_sample step (:1046-1186, no guidance) whose epsilon is gradient(cat(cond, x), i).  Returns the
+        rollout frames [B, rollout_steps, 4n].  Parity inputs: img [B, rollout, 4n] (the initial randn), noise [steps, B,
+        rollout, 4n] (p_sample's randn_like per step with t > 0), ula_noise [N-401, L, B, 24, 4n]."""
+        k = self.conditioned_steps
+        if not k:
+            raise NotImplementedError("sample_compose_multibodies runs on a conditioned model (conditioned_steps > 0)")
+        if self.betas_inference is None:
+            raise ValueError("set diffusion.betas_inference = linear_beta_schedule(N) first (inference_1d_composing_multibodies.py:170-171)")
+        eng = self._attach_unconditioned()
+        cond = cond.to(self.device, torch.float32)
+        b, f = cond.shape[0], cond.shape[2]
+        assert f == 4 * n_bodies
+        frames = self._initial_frames(b, self.rollout_steps, f, self.seed, img)
+        x = torch.cat([cond, frames], dim=1).contiguous()
+        betas_inf = self.betas_inference.to(torch.float32).cpu()
+        scalar = torch.sqrt(1 / (1 - torch.cumprod(1.0 - betas_inf, dim=0)))                      # (:1997-1998)
+        for i in range(N - 1, 400, -1):                                                             # ULA branch
+            x = self.sample_step_ULA(x, [i] * b, L, n_bodies, N, scalar, None if ula_noise is None else ula_noise[N - 1 - i])
+        t_start = min(N - 1, 400)
+        if t_start >= 0:
+            cfg = self._sample_config(b, 0, self.model.horizon - 1, n_bodies, "mean-inside", None, "standard", t_start, 0,
+                                      self.use_cuda_graph, cond_rows=k, ebm_uncond_coef=self._ebm_coef(n_bodies))
+            cfg.compose_mode = _lib.COMPOSE_EBM
+            if noise is not None:
+                noise = noise.to(self.device, torch.float32).contiguous()
+                assert tuple(noise.shape[1:]) == (b, self.rollout_steps, f) and noise.shape[0] >= t_start
+            x0 = torch.empty_like(x)
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().cindm_sample(eng.handle, ctypes.byref(cfg), _lib.ptr(x), _lib.ptr(noise) if noise is not None else None,
+                                                   _lib.ptr(x0), _lib.stream_ptr(self.device)))
+            self.last_x_start = x0[:, k:]
+        return x[:, k:].contiguous()
 
     # --- the reference's public sampling API -------------------------------------------------
     def p_sample_loop(self, shape, cond, n_composed=0, compose_start_step=4, compose_n_bodies=2, compose_mode="mean",
@@ -707,13 +881,13 @@ class GaussianDiffusion1D:
                compose_n_bodies=2, compose_mode="mean", design_fn=None, design_guidance="standard",
                initial_state_overwrite=None, initialization_mode=0, initialization_img=None):
         if self.sampling_timesteps < self.num_timesteps:              # reference :2347-2362
-            return self.ddim_sample((batch_size, self.image_size, self.channels), cond=cond, n_composed=n_composed,
-                                    compose_start_step=compose_start_step, compose_n_bodies=compose_n_bodies,
-                                    compose_mode=compose_mode, design_fn=design_fn, design_guidance=design_guidance,
-                                    initial_state_overwrite=initial_state_overwrite,
-                                    initialization_mode=initialization_mode, initialization_img=initialization_img)
-        return self.p_sample_loop((batch_size, self.image_size, self.channels), cond=cond, n_composed=n_composed,
-                                  compose_start_step=compose_start_step, compose_n_bodies=compose_n_bodies,
-                                  compose_mode=compose_mode, design_fn=design_fn, design_guidance=design_guidance,
-                                  initial_state_overwrite=initial_state_overwrite, initialization_mode=initialization_mode,
-                                  initialization_img=initialization_img)
+            return self._guard_fp16(lambda: self.ddim_sample(
+                (batch_size, self.image_size, self.channels), cond=cond, n_composed=n_composed,
+                compose_start_step=compose_start_step, compose_n_bodies=compose_n_bodies, compose_mode=compose_mode,
+                design_fn=design_fn, design_guidance=design_guidance, initial_state_overwrite=initial_state_overwrite,
+                initialization_mode=initialization_mode, initialization_img=initialization_img))
+        return self._guard_fp16(lambda: self.p_sample_loop(
+            (batch_size, self.image_size, self.channels), cond=cond, n_composed=n_composed,
+            compose_start_step=compose_start_step, compose_n_bodies=compose_n_bodies, compose_mode=compose_mode,
+            design_fn=design_fn, design_guidance=design_guidance, initial_state_overwrite=initial_state_overwrite,
+            initialization_mode=initialization_mode, initialization_img=initialization_img))

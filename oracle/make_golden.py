@@ -468,7 +468,113 @@ def gen_conditioned(sd):
     return {"batch": b, "n_composed": nc, "grid_timesteps": COND_GRID_T}
 
 
+# ---------------------------------------------------------------------------------------------
+# EBM body composition with the unconditional single-body model: gradient() (:1856-1982),
+# sample_step_ULA (:2047-2073), p_sample with model_unconditioned set (:1046-1186 -> :1002-1003), and a short
+# sample_compose_multibodies run (:1985-2042).  Unconditional model weights: init_unet_params(shapes(transition_dim=4), seed=7).
+# ---------------------------------------------------------------------------------------------
+def uncond_weights():
+    from cindm_b200.model.params import unet_param_shapes
+    return init_unet_params(unet_param_shapes(HORIZON, 4), seed=7, randomize_affine=True)
+
+
+def gen_ebm(sd):
+    m = ref_shim.load()
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = m.TemporalUnet1D(horizon=HORIZON, transition_dim=8, cond_dim=False, dim=64, dim_mults=(1, 2, 4, 8), attention=True)
+        net1 = m.TemporalUnet1D(horizon=HORIZON, transition_dim=4, cond_dim=False, dim=64, dim_mults=(1, 2, 4, 8), attention=True)
+        dif = m.GaussianDiffusion1D(net, image_size=20, conditioned_steps=4, timesteps=1000, sampling_timesteps=250, loss_type="l1")
+    net.load_state_dict(sd)
+    net1.load_state_dict(uncond_weights())
+    dif.model_unconditioned = net1
+    dif.eval()
+    out = {}
+    real_randn_like, real_randn = torch.randn_like, torch.randn
+
+    def record_into(draws, gen):
+        def logged_randn_like(t, **kw):
+            z = real_randn(t.shape, generator=gen, dtype=t.dtype)
+            draws.append(z)
+            return z
+
+        def logged_randn(*shape, **kw):
+            shape = tuple(shape[0]) if len(shape) == 1 and not isinstance(shape[0], int) else tuple(shape)
+            z = real_randn(shape, generator=gen)
+            draws.append(z)
+            return z
+        return logged_randn_like, logged_randn
+
+    n_inf = 500
+    dif.betas_inference = m.linear_beta_schedule(n_inf)
+    scalar = torch.sqrt(1 / (1 - torch.cumprod(1. - dif.betas_inference, dim=0)))
+    out["scalar_for_gradient"] = scalar.numpy()
+    # (1) gradient(): 4 bodies below and above t = 400, 3 bodies at the reference's hard-coded batch of 20
+    x4 = seeded((2, 24, 16), 51)
+    x3 = seeded((20, 24, 12), 52)
+    with torch.no_grad():
+        out["grad4_t300:x"] = x4.numpy()
+        out["grad4_t300:eps"] = dif.gradient(x4, 300, 4).numpy()
+        out["grad4_t450:eps"] = dif.gradient(x4, 450, 4, scalar).numpy()
+        out["grad3_t100:x"] = x3.numpy()
+        out["grad3_t100:eps"] = dif.gradient(x3, 100, 3).numpy()
+    # (2) sample_step_ULA: two Langevin updates at t = 450
+    draws = []
+    torch.randn_like, torch.randn = record_into(draws, torch.Generator().manual_seed(61))
+    try:
+        with torch.no_grad():
+            y = dif.sample_step_ULA(x4.clone(), torch.tensor([450, 450]), 2, 4, n_inf, scalar)
+    finally:
+        torch.randn_like, torch.randn = real_randn_like, real_randn
+    assert len(draws) == 2
+    out["ula:noise"] = torch.stack(draws).numpy()
+    out["ula:out"] = y.numpy()
+    # (3) p_sample with model_unconditioned at moderate timesteps (teacher-forced, one recorded draw each)
+    cond = seeded((2, 4, 16), 53) * 0.5
+    x = seeded((2, 20, 16), 54)
+    out["ps:cond"] = cond.numpy()
+    out["ps:x"] = x.numpy()
+    for t in (400, 150, 0):
+        draws = []
+        torch.randn_like, torch.randn = record_into(draws, torch.Generator().manual_seed(70 + t))
+        try:
+            m.grad_mean_list.clear()
+            with torch.no_grad():
+                img, x0 = dif.p_sample(x, cond, t)
+        finally:
+            torch.randn_like, torch.randn = real_randn_like, real_randn
+        assert len(draws) == (1 if t > 0 else 0)
+        out[f"ps_t{t}:noise"] = (draws[0] if draws else torch.zeros_like(x)).numpy()
+        out[f"ps_t{t}:img"] = img.numpy()
+        out[f"ps_t{t}:x0"] = x0.numpy()
+    # (4) sample_compose_multibodies with N = 4, L = 0: four p_sample steps t = 3..0 on cat(cond, randn)
+    n_small = 4
+    dif.betas_inference = m.linear_beta_schedule(n_small)
+    draws = []
+    torch.randn_like, torch.randn = record_into(draws, torch.Generator().manual_seed(81))
+    try:
+        m.grad_mean_list.clear()
+        with torch.no_grad(), contextlib.redirect_stderr(io.StringIO()):
+            y = dif.sample_compose_multibodies(cond=cond, N=n_small, L=0, n_bodies=4)
+    finally:
+        torch.randn_like, torch.randn = real_randn_like, real_randn
+    assert len(draws) == 1 + (n_small - 1)                       # the initial randn, then one randn_like per step with t > 0
+    out["scm:x_init"] = draws[0].numpy()
+    out["scm:noise"] = torch.stack(draws[1:]).numpy()
+    out["scm:out"] = y.numpy()
+    m.grad_mean_list.clear()
+    np.savez_compressed(os.path.join(GOLDEN, "ebm.npz"), **out)
+    return {"n_inference": n_inf, "uncond_weights": "init_unet_params(unet_param_shapes(24, 4), seed=7, randomize_affine=True)"}
+
+
 def main():
+    if "--only-ebm" in sys.argv:
+        torch.set_num_threads(os.cpu_count())
+        sd = init_unet_params(seed=0, randomize_affine=True)
+        meta = json.load(open(os.path.join(GOLDEN, "meta.json")))
+        meta["ebm"] = gen_ebm(sd)
+        json.dump(meta, open(os.path.join(GOLDEN, "meta.json"), "w"), indent=1)
+        print("ebm.npz", os.path.getsize(os.path.join(GOLDEN, "ebm.npz")))
+        return
     if "--only-conditioned" in sys.argv:
         torch.set_num_threads(os.cpu_count())
         sd = init_unet_params(seed=0, randomize_affine=True)
@@ -505,7 +611,9 @@ def main():
     ddim_cases = gen_ddim(m, dif, ns)
     outside_cases = gen_outside(m, dif, ns)
     conditioned = gen_conditioned(sd)
+    ebm = gen_ebm(sd)
     meta = {
+        "ebm": ebm,
         "conditioned": conditioned,
         "ddim_cases": ddim_cases,
         "outside_cases": outside_cases,

@@ -7,7 +7,7 @@ keys without the `model.` prefix).  It exists only so that tests, `smoke()` and 
 `cpu_baseline` leg of `bench.py` can check / time the CUDA path against the
 reference's arithmetic.  Nothing under `cindm_b200/` imports it.
 
-Pinned against: the live reference module (tests/test_oracle_vs_reference.py, runs
+Pinned against: the live reference module (tests/test_oracle_golden.py and tests/test_integration_stub.py, which run
 when /root/reference is mounted) and the committed golden vectors in tests/golden/
 produced by oracle/make_golden.py from the unmodified reference.
 

@@ -31,7 +31,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 META = json.load(open(os.path.join(HERE, "golden", "meta.json")))
 CASES = sorted(META.get("chain_cases", {}))
 
-# CUDA candidates per case (the reference ran 50 / 50 / 24): enough that the reference's sample size dominates the error
+# CUDA candidates per case (the reference ran 256 / 50 / 24): enough that the reference's sample size dominates the error
 N_GPU = {"c1_2body_std": 4096, "c1_2body_rec3": 2048, "4body_w2_rec2": 512}
 
 

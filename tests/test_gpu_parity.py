@@ -426,17 +426,36 @@ def test_empty_batch_is_a_no_op(diffusion):
     assert tuple(out.shape) == (0, 24, 8)
 
 
-def test_stale_script_mirrors_run_on_the_live_operator(tmp_path):
+def test_stale_script_mirrors_run_their_own_methods(tmp_path):
+    """The two older drivers, flags unchanged: autoregress / EBMs_compose on the conditioned model, EBMs_compose with the
+    unconditional single-body model, SimuSolver on the CUDA rollout (numerics of each method: test_gpu_conditioned / _ebm)."""
+    import numpy as np
     from cindm_b200.inference import inference_1d_composing_multibodies as mb
     from cindm_b200.inference import inference_1d_composing_time_steps as ts
-    p = ts.main(["--time_compose_method=EBMs_compose", "--n_composed=2", "--val_batch_size=3", f"--results_dir={tmp_path}"])
-    assert tuple(p.shape) == (3, 44, 8) and torch.isfinite(p).all()
-    p = mb.main(["--multi_bodies_method=EBMs_compose", "--n_composed=2", "--val_batch_size=2", f"--results_dir={tmp_path}"])
-    assert tuple(p.shape) == (2, 24, 16) and torch.isfinite(p).all()
-    p = mb.main(["--multi_bodies_method=SimuSolver", "--n_composed=4", "--val_batch_size=5", f"--results_dir={tmp_path}"])
+    rng = np.random.default_rng(0)
+
+    def cond_file(b, n):
+        c = rng.uniform(0.2, 0.8, size=(b, 4, 4 * n)).astype(np.float32)
+        c[..., 2::4] -= 0.5
+        c[..., 3::4] -= 0.5
+        path = str(tmp_path / f"cond_{b}_{n}.npy")
+        np.save(path, c)
+        return path
+
+    common = [f"--results_dir={tmp_path}", "--sample_steps=4"]
+    p = ts.main(["--n_composed=2", "--val_batch_size=3", f"--cond_npy={cond_file(3, 2)}"] + common)          # autoregress (default)
+    assert tuple(p.shape) == (3, 60, 8) and torch.isfinite(p).all()
+    p = ts.main(["--time_compose_method=EBMs_compose", "--n_composed=2", "--val_batch_size=3", f"--cond_npy={cond_file(3, 2)}"] + common)
+    assert tuple(p.shape) == (3, 60, 8) and torch.isfinite(p).all()
+    p = ts.main(["--time_compose_method=SimuSolver", "--n_composed=1", "--val_batch_size=5", f"--cond_npy={cond_file(5, 2)}"] + common)
+    assert tuple(p.shape) == (5, 40, 8) and torch.isfinite(p).all()
+    args = mb.build_parser().parse_args(["--n_composed=2", "--val_batch_size=2", f"--cond_npy={cond_file(2, 4)}"] + common)
+    p = mb.analyse(args, N=6, L=0)                                                                           # EBMs_compose (default), short schedule
+    assert tuple(p.shape) == (2, 20, 16) and torch.isfinite(p).all()
+    p = mb.main(["--multi_bodies_method=SimuSolver", "--n_composed=4", "--val_batch_size=5", f"--cond_npy={cond_file(5, 8)}"] + common)
     assert tuple(p.shape) == (5, 20, 32)
     with pytest.raises(NotImplementedError):
-        ts.main(["--time_compose_method=autoregress"])
+        ts.main(["--time_compose_method=GNS", f"--cond_npy={cond_file(1, 2)}"])
 
 
 def test_initialization_modes(diffusion):
