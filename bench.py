@@ -37,6 +37,20 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_REAL_STDOUT = []          # fd of the real stdout once fd 1 has been pointed at stderr (multi-rank runs)
+
+
+def emit(line):
+    """Print the one JSON line on the real stdout."""
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT[0], text.encode())
+    else:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+
+
 DDPM_STEPS = 1000
 N_BODIES, N_COMPOSED, START = 8, 2, 10
 CAND_PER_GPU = 512
@@ -297,9 +311,13 @@ def run_b200(args, rank, local_rank, world):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL's INFO log (rank / nranks / transport lines) goes to stderr: stdout stays the one JSON line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL's INFO log (version, rank / nranks, transport lines) is wanted on stderr, but NCCL writes it to fd 1: point
+        # fd 1 at stderr for the life of the process and keep the real stdout for the one JSON line (emit() below)
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+        sys.stdout.flush()
+        _REAL_STDOUT.append(os.dup(1))
+        os.dup2(2, 1)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     L = _lib.lib()
@@ -518,7 +536,7 @@ def run_b200(args, rank, local_rank, world):
             "value": cb / (DDPM_STEPS * sec), "unit": "designs/s", "cores": os.cpu_count(), "kind": "port",
             "sample": f"B={cb} candidates x 1 DDPM step of the C4 shape (R={cr}; {WINDOWS * PAIRS * max(cr, 1)} U-Net forwards of batch {cb}) "
                       f"with oracle/sampler_ref.py in the reference's loop form, {time.perf_counter() - t0:.0f} s of CPU work"}
-    print(json.dumps(line))
+    emit(line)
     if args.profile:
         for k, v in sorted(classes.items(), key=lambda kv: -kv[1]["ms"]):
             print(f"# {k:18s} {v['launches']:4d} launches {v['ms']:9.3f} ms", file=sys.stderr)

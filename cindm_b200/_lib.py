@@ -73,6 +73,7 @@ _SIGNATURES = {
     "cindm_sample": (c_int, [c_void_p, POINTER(SampleConfig), c_void_p, c_void_p, c_void_p, c_void_p]),
     "cindm_composed_posterior": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                          c_int, c_void_p]),
+    "cindm_set_initial_state_overwrite": (c_int, [c_void_p, c_void_p, c_int]),
     "cindm_sample_ddim": (c_int, [c_void_p, POINTER(SampleConfig), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
     "cindm_fill_initial_noise": (c_int, [c_void_p, c_int, c_int, c_int, c_uint64, c_int64, c_int, c_void_p]),

@@ -426,6 +426,16 @@ int cindm_sample(cindm_engine* e, const cindm_sample_config* cfg, float* x, cons
     API_END
 }
 
+int cindm_set_initial_state_overwrite(cindm_engine* e, const float* ow, int rows) {
+    API_BEGIN
+    if (!e) return fail(-2, "null engine");
+    if ((ow == nullptr) != (rows <= 0)) return fail(-2, "initial_state_overwrite: pointer and frame count come together");
+    e->overwrite = ow;
+    e->overwrite_rows = ow ? rows : 0;
+    return 0;
+    API_END
+}
+
 int cindm_sample_ddim(cindm_engine* e, const cindm_sample_config* cfg, int n_pairs, const int32_t* times,
                       const int32_t* times_next, const float* coef, float* x, const float* noise, float* x0_out,
                       void* stream) {

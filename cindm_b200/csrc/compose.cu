@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) compose_scatter_posterior_kernel(
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     float v = __fsub_rn(__fmul_rn(A, xv[q]), __fmul_rn(Bc, ev[q]));
-                    v = fminf(fmaxf(v, -1.0f), 1.0f);
+                    v = (v != v) ? v : fminf(fmaxf(v, -1.0f), 1.0f);          // x_start.clamp_(-1, 1): torch.clamp keeps NaN
                     w0[q] += v;
                     wm[q] += __fadd_rn(__fmul_rn(c1, v), __fmul_rn(c2, xv[q]));
                 }

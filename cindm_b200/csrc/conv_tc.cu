@@ -533,6 +533,14 @@ bool occ2_mode() {
     return mode == 1;
 }
 
+// CTA pairs for the N = 128 kernels too (each CTA then stages only half of the B tile: -25 % operand traffic per tile on the
+// L2-fabric-bound 128-channel layers); CINDM_CONV_PAIR128=0 keeps them single-CTA (A/B runs)
+bool pair128_mode() {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("CINDM_CONV_PAIR128"); mode = (e && e[0] == '0') ? 0 : 1; }
+    return mode == 1;
+}
+
 // CTA-pair (cta_group::2) MMA for the N >= 192 kernels; CINDM_CONV_PAIR=0 selects the single-CTA variant (A/B runs)
 bool pair_mode() {
     static int mode = -1;
@@ -556,7 +564,8 @@ int dispatch(const ConvTcLaunch& a, const CUtensorMap& m0, const CUtensorMap& m1
         switch (p.cout) {
             case 64: return occ2_mode() ? launch_instance<T16, 64, 8, EPI_GN_MISH, 1, 2>(m0, m1, mb, mo, p, st)
                                         : launch_instance<T16, 64, 8, EPI_GN_MISH, 1>(m0, m1, mb, mo, p, st);
-            case 128: return launch_instance<T16, 128, 16, EPI_GN_MISH, 1>(m0, m1, mb, mo, p, st);
+            case 128: return pair128_mode() ? launch_instance<T16, 128, 16, EPI_GN_MISH, 2>(m0, m1, mb, mo, p, st)
+                                            : launch_instance<T16, 128, 16, EPI_GN_MISH, 1>(m0, m1, mb, mo, p, st);
             case 256: return pair_mode() ? launch_instance<T16, 256, 32, EPI_GN_MISH, 2>(m0, m1, mb, mo, p, st)
                                          : launch_instance<T16, 256, 32, EPI_GN_MISH, 1>(m0, m1, mb, mo, p, st);
             case 512: return pair_mode() ? launch_instance<T16, 256, 64, EPI_GN_MISH, 2>(m0, m1, mb, mo, p, st)
@@ -567,7 +576,8 @@ int dispatch(const ConvTcLaunch& a, const CUtensorMap& m0, const CUtensorMap& m1
     switch (n_tile) {
         case 64: return occ2_mode() ? launch_instance<T16, 64, 8, EPI_BIAS, 1, 2>(m0, m1, mb, mo, p, st)
                                     : launch_instance<T16, 64, 8, EPI_BIAS, 1>(m0, m1, mb, mo, p, st);
-        case 128: return launch_instance<T16, 128, 8, EPI_BIAS, 1>(m0, m1, mb, mo, p, st);
+        case 128: return pair128_mode() ? launch_instance<T16, 128, 8, EPI_BIAS, 2>(m0, m1, mb, mo, p, st)
+                                        : launch_instance<T16, 128, 8, EPI_BIAS, 1>(m0, m1, mb, mo, p, st);
         case 256: return launch_instance<T16, 256, 8, EPI_BIAS, 1>(m0, m1, mb, mo, p, st);
     }
     return fail(-2, "conv_tc: unsupported N tile");
@@ -637,7 +647,8 @@ static int launch_conv_tc_one(const ConvTcLaunch& a, int parity, cudaStream_t st
     CINDM_TRY(encode_act_map(&m0, a.in0, a.prec, a.S, a.H, a.c0, p.slices_per_tile, p.H, h_stride));
     if (a.in1) CINDM_TRY(encode_act_map(&m1, a.in1, a.prec, a.S, a.H, a.c1, p.slices_per_tile, p.H, h_stride));
     else m1 = m0;
-    const int cg = (a.epilogue == EPI_GN_MISH && n_tile == 256 && pair_mode()) ? 2 : 1;       // the N = 256 GroupNorm kernels run as CTA pairs
+    // the N = 256 GroupNorm kernels and (all) the N = 128 kernels run as CTA pairs
+    const int cg = ((a.epilogue == EPI_GN_MISH && n_tile == 256 && pair_mode()) || (n_tile == 128 && pair128_mode())) ? 2 : 1;
     CINDM_TRY(encode_weight_map(&mb, w.w16[a.prec], a.prec, w.taps * w.cout, w.cin, n_tile / cg));
     // output tile through shared memory + TMA store: whole-row 128-byte bursts instead of 32 scattered 16-byte
     // stores per warp instruction (the transposed conv's interleaved rows keep the direct stores)

@@ -117,6 +117,9 @@ struct cindm_engine {
     // EBM body composition: the unconditional single-body engine (transition_dim 4) attached with
     // cindm_attach_unconditioned; not owned
     cindm_engine* uncond = nullptr;
+    // initial_state_overwrite (cindm_set_initial_state_overwrite): [B][rows][4n] device tensor owned by the caller
+    const float* overwrite = nullptr;
+    int overwrite_rows = 0;
 
     bool use_toeplitz = true;              // H=3 convs as one dense block-Toeplitz GEMM (tcgen05 engine)
     bool use_fused_attn = true;            // LayerNorm + to_qkv + attention core as one kernel (tcgen05 engine)
@@ -206,6 +209,8 @@ struct UpdateLaunch {
     // conditioned models: frames [0, cond_rows) of every candidate are the condition: copied through unchanged, and an
     // explicit noise tensor only covers the T - cond_rows sampled frames
     int cond_rows = 0;
+    // initial_state_overwrite (:1273-1276, :1355-1362): pred = overwrite[b][t] for t < ow_rows, before the noise is added
+    const float* overwrite = nullptr; int ow_rows = 0;
 };
 int launch_update(const UpdateLaunch& u, cudaStream_t st);
 int launch_fill_noise(float* x, int B, int T, int n, uint64_t seed, int64_t cand_off, int t, int draw,

@@ -176,6 +176,7 @@ struct UpdateParams {
     int ddim; const float* ddim_coef; const int* step_dev;
     const float* mean_in; const float* x0_in;
     int cond_rows;
+    const float* overwrite; int ow_rows;
 };
 
 __global__ void __launch_bounds__(256) ddpm_update_kernel(UpdateParams p) {
@@ -254,11 +255,12 @@ __global__ void __launch_bounds__(256) ddpm_update_kernel(UpdateParams p) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             float v = __fsub_rn(__fmul_rn(A, xs[q]), __fmul_rn(Bc, es[q]));                 // (:914-918)
-            v = fminf(fmaxf(v, -1.0f), 1.0f);                                               // clamp_(-1, 1) (:1039)
+            v = (v != v) ? v : fminf(fmaxf(v, -1.0f), 1.0f);                                // clamp_(-1, 1) (:1039); torch.clamp keeps NaN
             float mu = __fadd_rn(__fmul_rn(c1, v), __fmul_rn(c2, xs[q]));                   // (:943-946)
             if (p.mean_in) { v = x0i[q]; mu = mi[q]; }
             x0[q] = v;
             pr[q] = __fsub_rn(mu, g[q]);                                                    // (:1349)
+            if (p.overwrite && tt < p.ow_rows) pr[q] = p.overwrite[((b * p.ow_rows + tt) * p.n + j) * 4 + q];   // (:1361-1362)
             if (p.ddim) {
                 // pred_noise + grad_design_final (:1375), then img = x_start * sqrt(alpha_next) + c * pred_noise + sigma * noise (:1786-1788)
                 const float pn = __fadd_rn(es[q], g[q]);
@@ -287,6 +289,8 @@ int launch_update(const UpdateLaunch& u, cudaStream_t st) {
     p.ddim = u.ddim; p.ddim_coef = u.ddim_coef; p.step_dev = u.step_dev;
     p.mean_in = u.mean_in; p.x0_in = u.x0_in;
     p.cond_rows = u.cond_rows;
+    p.overwrite = u.overwrite; p.ow_rows = u.overwrite ? u.ow_rows : 0;
+    if (u.overwrite && (u.ow_rows <= 0 || u.ow_rows > u.T || u.ddim)) return fail(-2, "initial_state_overwrite: bad frame count (or DDIM)");
     if (u.cond_rows < 0 || u.cond_rows >= u.T) return fail(-2, "cond_rows must be in [0, T)");
     if ((u.mean_in == nullptr) != (u.x0_in == nullptr)) return fail(-2, "composed posterior mean and x_start come together");
     if (u.mean_in && u.ddim) return fail(-5, "DDIM runs on the *-inside composition only (reference ddim_sample :1758-1771)");
@@ -344,7 +348,7 @@ __global__ void __launch_bounds__(256) predict_start_kernel(const float4* __rest
                       __fsub_rn(__fmul_rn(A, a.z), __fmul_rn(Bc, b.z)), __fsub_rn(__fmul_rn(A, a.w), __fmul_rn(Bc, b.w))};
         if (clip) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = fminf(fmaxf(v[q], -1.0f), 1.0f);
+            for (int q = 0; q < 4; ++q) v[q] = (v[q] != v[q]) ? v[q] : fminf(fmaxf(v[q], -1.0f), 1.0f);   // torch.clamp keeps NaN
         }
         x0[i] = make_float4(v[0], v[1], v[2], v[3]);
     }
@@ -469,6 +473,7 @@ static int issue_step(cindm_engine* e, const cindm_sample_config& c, float* bufs
         u.use_philox = noise == nullptr; u.seed = c.seed; u.cand_off = c.candidate_offset;
         u.obj = c.objective;
         u.cond_rows = c.cond_rows;
+        u.overwrite = e->overwrite; u.ow_rows = e->overwrite_rows;
         // the reference re-noises after the last recurrence too and then discards it (:1365-1370):
         // the last evaluation goes straight to the final posterior noise (draw id R)
         u.renoise = (c.recurrence > 0 && !last) ? 1 : 0;
@@ -557,7 +562,7 @@ static int sample_loop_on(cindm_engine* e, const cindm_sample_config& c, float* 
         cindm_sample_config kc = c;
         if (!noise) { kc.t_start = 0; kc.t_end = 0; }
         std::string key(reinterpret_cast<const char*>(&kc), sizeof(kc));
-        const void* ptrs[4] = {x, noise, x0_out, (const void*)st};
+        const void* ptrs[6] = {x, noise, x0_out, (const void*)st, e->overwrite, (const void*)(intptr_t)e->overwrite_rows};
         key.append(reinterpret_cast<const char*>(ptrs), sizeof(ptrs));
         SampleBuffers& sb = e->sb;
         if (!sb.graph_exec || sb.graph_key != key) {

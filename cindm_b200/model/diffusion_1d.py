@@ -411,6 +411,28 @@ class GaussianDiffusion1D:
     def device(self):
         return self.model._device
 
+    def _overwrite(self, eng, initial_state_overwrite, batch, f):
+        """Context manager: initial_state_overwrite [B, k, F] (reference :1273-1276, :1355-1362) set on the engine for the
+        duration of a sampling call."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def scope():
+            if initial_state_overwrite is None:
+                yield
+                return
+            ow = initial_state_overwrite.to(self.device, torch.float32).contiguous()
+            if ow.dim() != 3 or ow.shape[0] != batch or ow.shape[2] != f:
+                raise ValueError(f"initial_state_overwrite must be [B={batch}, k, F={f}], got {tuple(ow.shape)}")
+            L = _lib.lib()
+            _lib.check(L.cindm_set_initial_state_overwrite(eng.handle, _lib.ptr(ow), ow.shape[1]))
+            try:
+                yield
+                torch.cuda.synchronize(self.device)            # `ow` must outlive the launches that read it
+            finally:
+                _lib.check(L.cindm_set_initial_state_overwrite(eng.handle, None, 0))
+        return scope()
+
     def _guard_fp16(self, run):
         """run() -> tensor; re-run in bf16 (or raise) when the fp16 path produced non-finite values (see on_fp16_overflow)."""
         out = run()
@@ -481,8 +503,8 @@ class GaussianDiffusion1D:
                                 n_composed=0, compose_start_step=4, single_model_step=-1, compose_n_bodies=2, noise=None):
         """One reverse step t -> t-1 (reference :1189-1376).  `noise` (optional, [R+1 or 1, B, T, F]) supplies
         the draws the reference would take from torch.randn_like; otherwise Philox is used."""
-        if cond is not None or initial_state_overwrite is not None or not clip_denoised:
-            raise NotImplementedError("cond / initial_state_overwrite / clip_denoised=False are not on the CUDA fast path")
+        if cond is not None or not clip_denoised:
+            raise NotImplementedError("cond / clip_denoised=False are not on the CUDA fast path")
         eng = self.model.engine()
         x = x.to(self.device, torch.float32).contiguous().clone()
         cfg = self._sample_config(x.shape[0], n_composed, compose_start_step, compose_n_bodies, compose_mode, design_fn,
@@ -492,7 +514,7 @@ class GaussianDiffusion1D:
             noise = noise.to(self.device, torch.float32).contiguous()
             draws = cfg.recurrence + 1 if cfg.recurrence > 0 else 1
             assert noise.shape[0] == draws and tuple(noise.shape[1:]) == tuple(x.shape)
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), self._overwrite(eng, initial_state_overwrite, x.shape[0], x.shape[2]):
             _lib.check(_lib.lib().cindm_sample(eng.handle, ctypes.byref(cfg), _lib.ptr(x), _lib.ptr(noise), _lib.ptr(x0),
                                                _lib.stream_ptr(self.device)))
         return x, x0
@@ -763,8 +785,9 @@ class GaussianDiffusion1D:
     def p_sample_loop(self, shape, cond, n_composed=0, compose_start_step=4, compose_n_bodies=2, compose_mode="mean",
                       design_fn=None, design_guidance="standard", initial_state_overwrite=None, initialization_mode=0,
                       initialization_img=None):
-        if cond is not None or initial_state_overwrite is not None:
-            raise NotImplementedError("cond / initial_state_overwrite are not on the CUDA fast path")
+        if cond is not None:
+            raise NotImplementedError("cond is not on the CUDA fast path of p_sample_loop (conditioned models: ddim_sample / "
+                                      "autoregress_time_compose_sample / sample_compose_multibodies)")
         assert compose_start_step < shape[1]                                   # reference :1679
         eng = self.model.engine()
         b = shape[0]
@@ -787,7 +810,8 @@ class GaussianDiffusion1D:
             cfg = self._sample_config(b, n_composed, compose_start_step, compose_n_bodies, compose_mode, design_fn,
                                       design_guidance, self.num_timesteps - 1, 0, self.use_cuda_graph)
             x0 = torch.empty_like(img)
-            _lib.check(L.cindm_sample(eng.handle, ctypes.byref(cfg), _lib.ptr(img), None, _lib.ptr(x0), _lib.stream_ptr(self.device)))
+            with self._overwrite(eng, initial_state_overwrite, b, f):
+                _lib.check(L.cindm_sample(eng.handle, ctypes.byref(cfg), _lib.ptr(img), None, _lib.ptr(x0), _lib.stream_ptr(self.device)))
         self.last_x_start = x0
         return img
 

@@ -199,6 +199,10 @@ int cindm_predict_start(cindm_engine* e, const float* x_dev, const float* eps_de
  * consumes torch.randn_like.  x0_out_dev (optional) receives the last x_start. */
 int cindm_sample(cindm_engine* e, const cindm_sample_config* cfg, float* x_dev, const float* noise_dev,
                  float* x0_out_dev, void* stream);
+/* initial_state_overwrite of p_sample_compose_inside / p_sample_loop (:1273-1276, :1355-1362): ow_dev[B][rows][4n] (device, fp32,
+ * owned by the caller, must stay valid while it is set) replaces the first `rows` frames of pred_img = mu - g in every
+ * evaluation of the following cindm_sample calls, BEFORE the re-noise / final noise is added.  NULL / 0 clears it. */
+int cindm_set_initial_state_overwrite(cindm_engine* e, const float* ow_dev, int rows);
 /* DDIM sampling, `sampling_timesteps < timesteps`: replaces ddim_sample (model/diffusion_1d.py:1723-1804) with the
  * guidance / composition of p_sample_compose_inside in its epsilon-returning mode (:1372-1376).  The host passes the
  * reference's schedule for the run: n_pairs (time, time_next) pairs (:1741-1743; time_next = -1 on the last one) and,

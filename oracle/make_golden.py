@@ -566,7 +566,59 @@ def gen_ebm(sd):
     return {"n_inference": n_inf, "uncond_weights": "init_unet_params(unet_param_shapes(24, 4), seed=7, randomize_affine=True)"}
 
 
+# initial_state_overwrite (:1273-1276, :1355-1362, :1517-1519, :1641-1643): teacher-forced steps with the first k frames of
+# pred_img replaced.  name: (n, nc, start, guidance, compose_mode, coef, cc, B, k, steps)
+OVERWRITE_CASES = {
+    "std_inside_4body": (4, 1, 10, "standard", "mean-inside", 0.2, 0.2, 2, 3, (600, 0)),
+    "rec2_inside_2body": (2, 0, 10, "standard-recurrence-2", "mean-inside", 0.4, 0.1, 2, 4, (500, 499)),
+    "rec2_outside_mean": (2, 1, 10, "standard-recurrence-2", "mean", 0.4, 0.1, 2, 2, (300,)),
+}
+
+
+def gen_overwrite(m, dif, ns):
+    out = {}
+    real_randn_like = torch.randn_like
+    for name, (n, nc, start, guidance, mode, coef, cc, b, k, steps) in OVERWRITE_CASES.items():
+        target = torch.tensor([0.5, 0.5], dtype=float)
+        fn = ns["get_design_fn"](target, last_n_step=1, coef=coef, time_consistency_coef=cc, design_fn_mode="L2")
+        img = seeded((b, HORIZON + nc * start, 4 * n), 2900 + n)
+        ow = seeded((b, k, 4 * n), 2950 + n) * 0.3
+        out[name + ":x_init"] = img.numpy()
+        out[name + ":overwrite"] = ow.numpy()
+        noises = []
+        gen = torch.Generator().manual_seed(6161 + n)
+
+        def logged_randn_like(t, **kw):
+            z = torch.randn(t.shape, generator=gen, dtype=t.dtype)
+            noises.append(z)
+            return z
+
+        torch.randn_like = logged_randn_like
+        try:
+            step_fn = dif.p_sample_compose_inside if "inside" in mode else dif.p_sample_compose_outside
+            for si, t in enumerate(steps):
+                m.grad_mean_list.clear()
+                img, x0 = step_fn(img, None, t, None, design_fn=fn, design_guidance=guidance, compose_mode=mode, n_composed=nc,
+                                  compose_start_step=start, single_model_step=HORIZON, compose_n_bodies=n,
+                                  initial_state_overwrite=ow)
+                out[f"{name}:img_after_{si}"] = img.numpy()
+        finally:
+            torch.randn_like = real_randn_like
+        out[name + ":noise"] = torch.stack(noises).numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "overwrite.npz"), **out)
+    return {k: [list(x) if isinstance(x, tuple) else x for x in v] for k, v in OVERWRITE_CASES.items()}
+
+
 def main():
+    if "--only-overwrite" in sys.argv:
+        torch.set_num_threads(os.cpu_count())
+        sd = init_unet_params(seed=0, randomize_affine=True)
+        m, net, dif = build_reference(sd)
+        meta = json.load(open(os.path.join(GOLDEN, "meta.json")))
+        meta["overwrite_cases"] = gen_overwrite(m, dif, reference_objective_namespace())
+        json.dump(meta, open(os.path.join(GOLDEN, "meta.json"), "w"), indent=1)
+        print("overwrite.npz", os.path.getsize(os.path.join(GOLDEN, "overwrite.npz")))
+        return
     if "--only-ebm" in sys.argv:
         torch.set_num_threads(os.cpu_count())
         sd = init_unet_params(seed=0, randomize_affine=True)
@@ -612,7 +664,9 @@ def main():
     outside_cases = gen_outside(m, dif, ns)
     conditioned = gen_conditioned(sd)
     ebm = gen_ebm(sd)
+    overwrite_cases = gen_overwrite(m, dif, ns)
     meta = {
+        "overwrite_cases": overwrite_cases,
         "ebm": ebm,
         "conditioned": conditioned,
         "ddim_cases": ddim_cases,

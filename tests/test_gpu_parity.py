@@ -709,3 +709,39 @@ def test_long_chain_16bit_tracks_fp32(diffusion):
     assert err < HALF_TOL, err
     assert (d16 - d32).abs().mean() < 1e-2                    # per candidate: 2 px of the 200 px box (seed-to-seed: 0.027)
     assert abs(d16.mean() - d32.mean()) < 5e-3                # no systematic shift of the design metric (s.e. of the mean: 0.003)
+
+
+# ---------------------------------------------------------------------------------------------
+# initial_state_overwrite (reference :1273-1276, :1355-1362, :1517-1519, :1641-1643)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", sorted(META.get("overwrite_cases", {})))
+def test_initial_state_overwrite_vs_reference_steps(diffusion, golden, case):
+    from cindm_b200.model.diffusion_1d import get_design_fn, parse_design_guidance
+    n, nc, start, guidance, mode, coef, cc, b, k, steps = META["overwrite_cases"][case]
+    g = golden("overwrite.npz")
+    fn = get_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, coef=coef, time_consistency_coef=cc)
+    rec = parse_design_guidance(guidance)[1]
+    per_step = rec + 1 if rec else 1
+    noise = torch.from_numpy(g[case + ":noise"])
+    ow = torch.from_numpy(g[case + ":overwrite"])
+    step_fn = diffusion.p_sample_compose_inside if "inside" in mode else diffusion.p_sample_compose_outside
+    for precision, engine, tol in (("fp32", "simt", 2 * FP32_TOL), ("fp16", "tcgen05", HALF_TOL)):
+        set_precision(diffusion, precision, engine)
+        img = torch.from_numpy(g[case + ":x_init"])
+        used = 0
+        for si, t in enumerate(steps):
+            draws = per_step if t > 0 else per_step - 1            # no final draw at t == 0
+            nz = noise[used:used + draws]
+            used += draws
+            if draws < per_step:
+                nz = torch.cat([nz, torch.zeros_like(noise[:1])])
+            img, _ = step_fn(img, None, t, design_fn=fn, design_guidance=guidance, compose_mode=mode, n_composed=nc,
+                             compose_start_step=start, single_model_step=24, compose_n_bodies=n, initial_state_overwrite=ow,
+                             noise=nz)
+            assert rel_l2(img, g[f"{case}:img_after_{si}"]) < tol, (precision, si)
+            img = torch.from_numpy(g[f"{case}:img_after_{si}"])   # teacher forcing
+        assert used == noise.shape[0]
+    set_precision(diffusion, "fp32")
+    # the overwritten frames really are overwrite + noise: at t = 0 (no noise) they equal the overwrite tensor
+    if 0 in steps:
+        assert torch.equal(torch.from_numpy(g[f"{case}:img_after_{len(steps) - 1}"])[:, :k], ow)
