@@ -474,7 +474,10 @@ def run_b200(args, rank, local_rank, world):
     S = WINDOWS * PAIRS * B
     traffic = None
     try:   # DRAM bytes of the same kernel class from the committed ncu capture (profiles/, per launch like `achieved`)
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_evaluation_traffic.json")))
+        prof_path = os.path.join(ROOT, "profiles", "r2_evaluation_traffic.json")
+        if not os.path.exists(prof_path):
+            prof_path = os.path.join(ROOT, "profiles", "r1_evaluation_traffic.json")
+        prof = json.load(open(prof_path))
         for name, c in prof["classes"].items():
             if "conv_tc_kernel" in name:
                 traffic = (c["dram_read_bytes"] + c["dram_write_bytes"]) / c["launches"]
@@ -489,7 +492,7 @@ def run_b200(args, rank, local_rank, world):
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
                     "algorithmic_flop_per_launch_group": c["work"] / c["launches"], "avg_launch_ms": c["ms"] / c["launches"],
                     "share_of_evaluation": c["ms"] / eval_ms, "traffic": traffic,
-                    "traffic_note": "ncu dram__bytes_read+write per conv_tc launch (profiles/r1_evaluation_traffic.json); "
+                    "traffic_note": "ncu dram__bytes_read+write per conv_tc launch (profiles/r2_evaluation_traffic.json); "
                                     "algorithmic HBM bytes per launch are ~264 MB (read + write one 132 MB activation tensor)"}
     elif "conv_simt" in classes:
         c = classes["conv_simt"]

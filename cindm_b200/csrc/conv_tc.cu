@@ -248,7 +248,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         };
         // loop-invariant GroupNorm geometry of this thread's row (generic path: rows of a slice are H consecutive lanes)
         const int sl = min(row / p.H, p.slices_per_tile - 1);     // slice within the tile
-        const int row_in_slice = row - (row / p.H) * p.H;
         const float inv_cnt = 1.0f / (float)(p.H * CPG);
 
         {   // both accumulators start out holding the bias of the first two tiles of this CTA

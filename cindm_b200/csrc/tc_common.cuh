@@ -29,10 +29,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Phase wait; a failed probe backs off with nanosleep so that the single-thread producer / MMA roles and idle epilogue
-// warps do not compete with the working epilogue warps of their SM sub-partition for issue slots (and power).
+// Phase wait.  try_wait carries a suspend-time hint: the hardware parks the thread until the phase completes or the hint
+// (in ns) expires, so waiting roles (the single-thread producer / MMA issuer, idle epilogue warps) issue a handful of
+// instructions per wait instead of polling and do not compete with the working epilogue warps of their SM sub-partition
+// for issue slots (and power).  CINDM_WAIT_SPIN (compile-time) restores the round-1 poll + nanosleep(40) loop for A/B runs.
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
+#ifdef CINDM_WAIT_SPIN
     while (true) {
         uint32_t done;
         asm volatile(
@@ -44,6 +47,17 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
         if (done) break;
         __nanosleep(40);
     }
+#else
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(addr), "r"(parity), "r"(0x989680u) : "memory");
+#endif
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
