@@ -63,3 +63,22 @@ def test_eval_simu_and_fused_scoring_match_oracle():
     # the driver's aggregate MAE (torch L1Loss over cat(frame0, simulated) vs pred) is the mean of the per-sample values
     full = torch.cat([pred_t[:, :1].double(), pred_simu], 1)
     assert float(torch.nn.functional.l1_loss(full, pred_t.double())) == pytest.approx(float(mae.mean()), rel=1e-12)
+
+
+def test_many_contact_worlds_match_oracle_bit_exact():
+    """Crowded and degenerate worlds (discs overlapping, coincident, outside the box): every contact path of the kernel -
+    wall pre-checks with out-of-range coordinates, many simultaneous contacts, cached arbiters - against the C oracle."""
+    from cindm_b200.utils import simulation
+    from oracle import nbody_ref
+    rng = np.random.default_rng(2025)
+    b = 4096
+    s0 = np.zeros((b, 8, 4))
+    s0[:, :, :2] = np.clip(rng.normal(0.5, 0.35, size=(b, 8, 2)), -1.0, 1.0) * 200.0      # generated-like frame 0
+    s0[:, :, 2:] = np.clip(rng.normal(0.0, 0.35, size=(b, 8, 2)), -1.0, 1.0) * 200.0
+    s0[0, :, :2] = 100.0                                                                    # eight coincident discs
+    s0[1, :, 0] = np.linspace(10, 190, 8); s0[1, :, 1] = 5.0                                # a row of discs inside the bottom wall
+    s0[2, :4, :2] = [[0, 0], [200, 0], [0, 200], [200, 200]]                                # discs centred on the corners
+    ref = nbody_ref.rollout(s0, 172, 4)
+    got = simulation(torch.from_numpy(s0), 172, stride=4, device="cuda").cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.array_equal(np.nan_to_num(got), np.nan_to_num(ref))
