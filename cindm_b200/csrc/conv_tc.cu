@@ -93,7 +93,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0;
     // tiles are handed out per cluster: pair-tile t = (m_pair, n_tile); this CTA works on m_tile = m_pair * CG + rank
-    const int num_tiles = ((p.m_tiles + CG - 1) / CG) * p.n_tiles;
+    // the generic GroupNorm kernels with N <= 128 always cover all output channels with ONE N tile: knowing it at compile time
+    // removes four integer divisions per tile from every role's loop
+    constexpr bool ONE_N = (EPI == EPI_GN_MISH) && N_TILE <= 128;
+    const int n_tiles = ONE_N ? 1 : p.n_tiles;
+    const int num_tiles = ((p.m_tiles + CG - 1) / CG) * n_tiles;
     const int tile_first = blockIdx.x / CG, tile_step = gridDim.x / CG;
     const int k_chunks = p.taps * p.k_chunks_per_tap;
 
@@ -129,7 +133,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
-                const int m_pair = tile / p.n_tiles, n_tile = tile - m_pair * p.n_tiles;
+                const int m_pair = tile / n_tiles, n_tile = tile - m_pair * n_tiles;
                 const int m_tile = m_pair * CG + (int)cta_rank;
                 const int s0 = m_tile * p.slices_per_tile;
                 const uint32_t tx_bytes = (uint32_t)(p.rows_used * 128 + kBTileBytes) * CG;   // leader counts both CTAs' bytes
@@ -252,8 +256,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
         {   // both accumulators start out holding the bias of the first two tiles of this CTA
             const int t0 = tile_first, t1 = tile_first + tile_step;
-            if (t0 < num_tiles) init_accumulator(0, t0 % p.n_tiles);
-            if (t1 < num_tiles) init_accumulator(1, t1 % p.n_tiles);
+            if (t0 < num_tiles) init_accumulator(0, t0 % n_tiles);
+            if (t1 < num_tiles) init_accumulator(1, t1 % n_tiles);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -263,7 +267,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
-            const int m_pair = tile / p.n_tiles, n_tile = tile - m_pair * p.n_tiles;
+            const int m_pair = tile / n_tiles, n_tile = tile - m_pair * n_tiles;
             const int m_tile = m_pair * CG + (int)cta_rank;
             const long long s0 = (long long)m_tile * p.slices_per_tile;
             const int n0 = n_tile * N_TILE;
@@ -288,7 +292,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             if (res != nullptr) {
                 const int nt_tile = tile + tile_step;
                 if (nt_tile < num_tiles) {
-                    const int nm_pair = nt_tile / p.n_tiles, nn_tile = nt_tile - nm_pair * p.n_tiles;
+                    const int nm_pair = nt_tile / n_tiles, nn_tile = nt_tile - nm_pair * n_tiles;
                     const long long ns0 = (long long)(nm_pair * CG + (int)cta_rank) * p.slices_per_tile;
                     const long long ngrow = ns0 * p.H + row;
                     const bool nvalid = T3 ? (ns0 + row) < p.S : (row < p.rows_used && (ns0 + sl) < p.S);
@@ -462,7 +466,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             // ---- hand the accumulator back, pre-loaded with the bias of the tile that will use it next ----
             {
                 const int nxt = tile + 2 * tile_step;
-                if (nxt < num_tiles) init_accumulator(acc, nxt % p.n_tiles);
+                if (nxt < num_tiles) init_accumulator(acc, nxt % n_tiles);
             }
             tc_fence_before();
             __syncwarp();
