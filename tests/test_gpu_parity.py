@@ -378,6 +378,27 @@ def test_driver_cli_ddim_from_dataset_initialization(tmp_path):
     assert init["pred"].shape == (4, 34, 8) and np.isfinite(init["pred"]).all()
 
 
+def test_driver_cli_batches_draw_fresh_noise(tmp_path):
+    """every --num_batchs iteration (and every sweep entry) must sample NEW designs, as the reference's fresh
+    torch.randn draws do; all Philox noise is keyed by (seed, candidate, t, draw), so each sample() call gets its own seed."""
+    from cindm_b200.inference.inverse_design_diffusion_1d import main
+    res = main(["--exp_id=test3", "--date_time=00-00", "--compose_n_bodies=2", "--n_composed=0", "--compose_mode=mean-inside",
+                "--design_guidance=standard-recurrence-2", "--design_coef=0.2,0.4", "--consistency_coef=0.2", "--batch_size_list=[4]",
+                "--num_batchs=2", "--sample_steps_list=[8]", "--model_name=Diffusion_cond-0_rollout-24_bodies-2",
+                f"--results_dir={tmp_path}"])
+    assert len(res) == 4                                           # 2 batches x 2 design coefficients
+    preds = [r["pred"] for r in res]
+    for i in range(4):
+        for j in range(i + 1, 4):
+            assert not np.array_equal(preds[i], preds[j]), (i, j)
+    # and the run as a whole is reproducible
+    again = main(["--exp_id=test3", "--date_time=00-00", "--compose_n_bodies=2", "--n_composed=0", "--compose_mode=mean-inside",
+                  "--design_guidance=standard-recurrence-2", "--design_coef=0.2,0.4", "--consistency_coef=0.2", "--batch_size_list=[4]",
+                  "--num_batchs=2", "--sample_steps_list=[8]", "--model_name=Diffusion_cond-0_rollout-24_bodies-2",
+                  f"--results_dir={tmp_path}"])
+    assert all(np.array_equal(a["pred"], b["pred"]) for a, b in zip(res, again))
+
+
 def test_full_size_c4_candidate_independence(diffusion):
     """BASELINE.json's full per-GPU size (C4: 512 candidates, 8 bodies, 3 windows -> 43 008 slices per evaluation) through
     a size-independent property: every candidate is an independent unit, so sampling candidates [100, 164) alone must
