@@ -41,6 +41,9 @@ CHAIN_CASES = {
     "c1_2body_rec3": (2, 0, 10, "standard-recurrence-3", "mean-inside", 0.4, 0.1, 50, 4321),
     # body AND time composition together: 4 bodies (6 pairs) x 2 windows, recurrence
     "4body_w2_rec2": (4, 1, 10, "standard-recurrence-2", "mean-inside", 0.2, 0.2, 24, 2468),
+    # the headline shape (BASELINE.json config 4: 8 bodies, 28 pairs x 3 windows, 44 frames) with the cheap guidance variant:
+    # 84 U-Net forwards per DDPM step on the CPU, ~1.5 h for 16 candidates
+    "c4_8body_w3_std": (8, 2, 10, "standard", "mean-inside", 0.2, 0.2, 16, 8642),
 }
 
 

@@ -32,7 +32,7 @@ META = json.load(open(os.path.join(HERE, "golden", "meta.json")))
 CASES = sorted(META.get("chain_cases", {}))
 
 # CUDA candidates per case (the reference ran 256 / 50 / 24): enough that the reference's sample size dominates the error
-N_GPU = {"c1_2body_std": 4096, "c1_2body_rec3": 2048, "4body_w2_rec2": 512}
+N_GPU = {"c1_2body_std": 4096, "c1_2body_rec3": 2048, "4body_w2_rec2": 512, "c4_8body_w3_std": 512}
 
 
 def candidate_statistics(pred, target=(0.5, 0.5)):
