@@ -536,6 +536,19 @@ bool occ2_mode() {
     return mode == 1;
 }
 
+// N tile of the plain (1x1 / resampling) convs.  Measured per layer (same box, profiles/r2_plain_conv_tiles.md): with a short
+// K loop (1x1 convs from 64 / 128 channels: the attention output projections, two residual convs) the kernel is bound by its
+// epilogue and the 64-column tiles of the two-CTAs-per-SM kernel win (-8..-18 %); with a long K loop (cin >= 256, the 3- / 4-tap
+// resampling convs) re-reading the A tile once per N tile costs more and 128-column CTA pairs win (by 20-35 %).
+// CINDM_CONV_BIAS64=1 / 0 forces 64 / 128 everywhere (A/B runs).
+int plain_n_tile(int cout, int taps, int cin) {
+    static int mode = -2;
+    if (mode == -2) { const char* e = getenv("CINDM_CONV_BIAS64"); mode = !e ? -1 : (e[0] == '1' ? 1 : 0); }
+    if (cout % 128 != 0) return 64;
+    if (mode >= 0) return mode == 1 ? 64 : 128;
+    return taps * cin > 128 ? 128 : 64;
+}
+
 // CTA pairs for the N = 128 kernels too (each CTA then stages only half of the B tile: -25 % operand traffic per tile on the
 // L2-fabric-bound 128-channel layers); CINDM_CONV_PAIR128=0 keeps them single-CTA (A/B runs)
 bool pair128_mode() {
@@ -637,7 +650,7 @@ static int launch_conv_tc_one(const ConvTcLaunch& a, int parity, cudaStream_t st
     p.m_tiles = (int)((a.S + p.slices_per_tile - 1) / p.slices_per_tile);
     int n_tile;
     if (a.epilogue == EPI_GN_MISH) n_tile = w.cout < 256 ? w.cout : 256;
-    else n_tile = (w.cout % 128 == 0) ? 128 : 64;       // N <= 128 kernels write their output tile with TMA
+    else n_tile = plain_n_tile(w.cout, p.taps, w.cin);   // (N <= 128 kernels write their output tile with TMA)
     p.n_tiles = w.cout / n_tile;
     p.k_chunks_per_tap = w.cin / kBlockK;
 
