@@ -485,13 +485,24 @@ def run_b200(args, rank, local_rank, world):
         pass
     if "conv_tc" in classes and classes["conv_tc"]["ms"] > 0:
         c = classes["conv_tc"]
-        achieved = c["work"] / (c["ms"] * 1e-3) / 1e12
+        share = c["ms"] / eval_ms
+        evals_per_step = max(args.recurrence, 1)
+        # `achieved` / `frac`: the class's algorithmic FLOP over its time INSIDE the timed, power-capped step (its share of one
+        # evaluation - CUDA events per launch, ncu agrees on the share - times the step time measured above), against the
+        # SUSTAINED measured peak.  `isolated`: the same launches timed alone right after (burst clocks) against the BURST peak.
+        in_step_ms = share * sec_per_step * 1e3 / evals_per_step            # conv_tc time of one evaluation inside the step
+        achieved = c["work"] / (in_step_ms * 1e-3) / 1e12
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        burst = peaks.get("bf16_tflops", 1590.0)
+        iso = c["work"] / (c["ms"] * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv + GN/Mish epilogue), all layers of one evaluation",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
-                    "algorithmic_flop_per_launch_group": c["work"] / c["launches"], "avg_launch_ms": c["ms"] / c["launches"],
-                    "share_of_evaluation": c["ms"] / eval_ms, "traffic": traffic,
+                    "algorithmic_flop_per_launch_group": c["work"] / c["launches"], "avg_launch_ms": in_step_ms / c["launches"],
+                    "share_of_evaluation": share,
+                    "isolated": {"achieved": iso, "peak": burst, "frac": iso / burst, "avg_launch_ms": c["ms"] / c["launches"],
+                                 "note": "one un-graphed evaluation timed alone with CUDA events per launch; burst peak"},
+                    "traffic": traffic,
                     "traffic_note": "ncu dram__bytes_read+write per conv_tc launch (profiles/r2_evaluation_traffic.json); "
                                     "algorithmic HBM bytes per launch are ~264 MB (read + write one 132 MB activation tensor)"}
     elif "conv_simt" in classes:
