@@ -131,6 +131,7 @@ int cindm_create(const cindm_config* cfg, cindm_engine** out) {
     // A/B switches for measurements (both default on)
     if (const char* v = getenv("CINDM_TOEPLITZ")) e->use_toeplitz = v[0] != '0';
     if (const char* v = getenv("CINDM_FUSED_ATTN")) e->use_fused_attn = v[0] != '0';
+    if (const char* v = getenv("CINDM_FORK_RES")) e->fork_residual = v[0] != '0';
     *out = e;
     return 0;
     API_END
@@ -152,6 +153,9 @@ int cindm_destroy(cindm_engine* e) {
     if (e->sb.ddim_times) cudaFree(e->sb.ddim_times);
     if (e->sb.ddim_coef) cudaFree(e->sb.ddim_coef);
     graph_cache_clear(e);
+    if (e->side_stream) cudaStreamDestroy(e->side_stream);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->sb.capture_stream) cudaStreamDestroy(e->sb.capture_stream);
     if (e->sb.ev_in) cudaEventDestroy(e->sb.ev_in);
     if (e->sb.ev_out) cudaEventDestroy(e->sb.ev_out);

@@ -121,6 +121,12 @@ struct cindm_engine {
     const float* overwrite = nullptr;
     int overwrite_rows = 0;
 
+    // small batches: the 1x1 residual conv of a ResidualTemporalBlock runs on a side stream next to the block's first conv
+    // (fork / join with events; the dependency is captured into the step's CUDA graph like any other edge)
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int fork_residual = -1;                // -1: by slice count; 0 / 1: CINDM_FORK_RES
+
     bool use_toeplitz = true;              // H=3 convs as one dense block-Toeplitz GEMM (tcgen05 engine)
     bool use_fused_attn = true;            // LayerNorm + to_qkv + attention core as one kernel (tcgen05 engine)
     bool taps_enabled = false;

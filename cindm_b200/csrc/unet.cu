@@ -276,6 +276,7 @@ struct Fwd {
     const int* t_dev;
     int prec, engine;
     cudaStream_t st;
+    bool fork = false;                      // run residual 1x1 convs on e->side_stream (small batches)
 
     int record_tap(const std::string& name, const void* ptr, int c, int h) {
         if (!e->taps_enabled) return 0;
@@ -308,7 +309,8 @@ struct Fwd {
 
     // plain conv (1x1, strided, transposed) with bias and optional residual
     int conv_plain(const ConvW& w, const void* in0, int c0, const void* in1, int c1, int in_prec, int Hin, int Hout,
-                   int stride, int pad, int transposed, const void* res, void* out, int out_prec) {
+                   int stride, int pad, int transposed, const void* res, void* out, int out_prec, cudaStream_t on = nullptr) {
+        cudaStream_t st = on ? on : this->st;
         if (engine == CINDM_CONV_TCGEN05 && in_prec != PREC_F32 && out_prec != PREC_F32 &&
             (w.cin % 64) == 0 && (w.cout % 64) == 0) {
             ConvTcLaunch a;
@@ -330,8 +332,19 @@ struct Fwd {
                  void* out) {
         const int cout = r.conv0.cout;
         const float* tb = t_dev ? r.time_bias : r.time_bias + (size_t)t * cout;
-        CINDM_TRY(conv_block(r.conv0, r.gn0, in0, c0, in1, c1, in_prec, H, tb, nullptr, tmp));
         const void* resid = in0;
+        if (r.has_res && fork) {
+            // fork: the residual conv only needs the block input; it runs beside conv0 and is joined before conv1 reads it.
+            // (The fork event also orders it after the previous block's conv1, the last reader of ws.res.)
+            CINDM_CHECK_CUDA(cudaEventRecord(e->ev_fork, st));
+            CINDM_CHECK_CUDA(cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
+            CINDM_TRY(conv_plain(r.res, in0, c0, in1, c1, in_prec, H, H, 1, 0, 0, nullptr, e->ws.res, prec, e->side_stream));
+            CINDM_CHECK_CUDA(cudaEventRecord(e->ev_join, e->side_stream));
+            CINDM_TRY(conv_block(r.conv0, r.gn0, in0, c0, in1, c1, in_prec, H, tb, nullptr, tmp));
+            CINDM_CHECK_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));
+            return conv_block(r.conv1, r.gn1, tmp, cout, nullptr, 0, prec, H, nullptr, e->ws.res, out);
+        }
+        CINDM_TRY(conv_block(r.conv0, r.gn0, in0, c0, in1, c1, in_prec, H, tb, nullptr, tmp));
         if (r.has_res) {
             CINDM_TRY(conv_plain(r.res, in0, c0, in1, c1, in_prec, H, H, 1, 0, 0, nullptr, e->ws.res, prec));
             resid = e->ws.res;
@@ -372,6 +385,16 @@ int unet_forward(cindm_engine* e, const float* slices, int64_t S, int t, const i
     }
     Workspace& w = e->ws;
     Fwd f{e, S, t, t_dev, precision, conv_engine, st};
+    // small batches leave most SMs idle inside every kernel: overlap what is independent (CINDM_FORK_RES=0 / 1 overrides)
+    const bool want_fork = e->fork_residual >= 0 ? e->fork_residual == 1 : S <= 4096;
+    if (want_fork && conv_engine == CINDM_CONV_TCGEN05 && precision != PREC_F32 && !profiling_enabled()) {
+        if (!e->side_stream) {
+            CINDM_CHECK_CUDA(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
+            CINDM_CHECK_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+            CINDM_CHECK_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+        }
+        f.fork = true;
+    }
     const int dim = e->cfg.dim, F = e->cfg.transition_dim;
     int H = e->cfg.horizon;
     const int ch[5] = {F, dim, dim * 2, dim * 4, dim * 8};

@@ -31,8 +31,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 META = json.load(open(os.path.join(HERE, "golden", "meta.json")))
 CASES = sorted(META.get("chain_cases", {}))
 
-# CUDA candidates per case (the reference ran 256 / 50 / 24): enough that the reference's sample size dominates the error
+# CUDA candidates per case (the reference ran 256 / 50 / 24 / 16): enough that the reference's sample size dominates the error.
+# The headline shape (8 bodies x 3 windows: 84 slices per candidate and evaluation) runs fewer candidates on the slow fp32 path.
 N_GPU = {"c1_2body_std": 4096, "c1_2body_rec3": 2048, "4body_w2_rec2": 512, "c4_8body_w3_std": 512}
+N_GPU_FP32 = {"c4_8body_w3_std": 96}
 
 
 def candidate_statistics(pred, target=(0.5, 0.5)):
@@ -95,7 +97,8 @@ def test_final_design_statistics_match_the_reference_sampler(diffusion, golden, 
     dif.precision, dif.conv_engine = precision, engine
     dif.seed, dif.candidate_offset = 1000 + seed, 0
     fn = get_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, coef=coef, time_consistency_coef=cc)
-    pred = dif.sample(batch_size=N_GPU.get(case, 1024), cond=None, n_composed=nc, compose_start_step=start, compose_n_bodies=n,
+    n_gpu = N_GPU_FP32.get(case, N_GPU.get(case, 1024)) if precision == "fp32" else N_GPU.get(case, 1024)
+    pred = dif.sample(batch_size=n_gpu, cond=None, n_composed=nc, compose_start_step=start, compose_n_bodies=n,
                       compose_mode=mode, design_fn=fn, design_guidance=guidance).cpu().numpy()
     assert np.isfinite(pred).all()
     compare(ref_stats, candidate_statistics(pred), f"{case} {precision}/{engine}")
