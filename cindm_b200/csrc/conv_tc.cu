@@ -691,6 +691,15 @@ int launch_conv_tc(const ConvTcLaunch& a, cudaStream_t st) {
     if (a.epilogue == EPI_GN_MISH_T3 && (a.H != 3 || w.taps != 5 || a.mode != TC_SAME || !w.w16t[a.prec]))
         return fail(-2, "conv_tc: the block-Toeplitz path needs H == 3, k == 5 and the repacked operand");
     if (a.mode == TC_UP) {
+        if (a.side) {
+            CINDM_CHECK_CUDA(cudaEventRecord(a.ev_fork, st));
+            CINDM_CHECK_CUDA(cudaStreamWaitEvent(a.side, a.ev_fork, 0));
+            CINDM_TRY(launch_conv_tc_one(a, 1, a.side));
+            CINDM_CHECK_CUDA(cudaEventRecord(a.ev_join, a.side));
+            CINDM_TRY(launch_conv_tc_one(a, 0, st));
+            CINDM_CHECK_CUDA(cudaStreamWaitEvent(st, a.ev_join, 0));
+            return 0;
+        }
         CINDM_TRY(launch_conv_tc_one(a, 0, st));
         return launch_conv_tc_one(a, 1, st);
     }

@@ -26,6 +26,10 @@ struct ConvTcLaunch {
     int mode = TC_SAME;
     int prec = PREC_F16;
     int epilogue = EPI_BIAS;
+    // small batches: the two parity GEMMs of a transposed conv are independent; when `side` is set the odd outputs are
+    // computed on it (event fork / join around it, graph-capturable)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 int launch_conv_tc(const ConvTcLaunch& a, cudaStream_t st);

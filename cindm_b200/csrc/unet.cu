@@ -318,6 +318,7 @@ struct Fwd {
             a.add_vec = nullptr; a.add_res = res; a.out = out; a.S = S; a.H = Hin; a.prec = prec;
             a.epilogue = EPI_BIAS;
             a.mode = transposed ? TC_UP : (stride == 2 ? TC_DOWN : TC_SAME);
+            if (transposed && fork && !on) { a.side = e->side_stream; a.ev_fork = e->ev_fork; a.ev_join = e->ev_join; }
             return launch_conv_tc(a, st);
         }
         ConvLaunch a;
@@ -386,7 +387,7 @@ int unet_forward(cindm_engine* e, const float* slices, int64_t S, int t, const i
     Workspace& w = e->ws;
     Fwd f{e, S, t, t_dev, precision, conv_engine, st};
     // small batches leave most SMs idle inside every kernel: overlap what is independent (CINDM_FORK_RES=0 / 1 overrides)
-    const bool want_fork = e->fork_residual >= 0 ? e->fork_residual == 1 : S <= 4096;
+    const bool want_fork = e->fork_residual >= 0 ? e->fork_residual == 1 : S <= 2048;
     if (want_fork && conv_engine == CINDM_CONV_TCGEN05 && precision != PREC_F32 && !profiling_enabled()) {
         if (!e->side_stream) {
             CINDM_CHECK_CUDA(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
