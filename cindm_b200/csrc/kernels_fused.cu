@@ -3,6 +3,8 @@
 //   head  : final 1x1 conv 64 -> 8 to fp32 eps_pair
 //   attn  : linear-attention core (softmax_n(k), k v^T, ctx^T q) with register-tiled 4x4 outer products
 // They replace generic SIMT GEMM launches whose K or N extent (8 channels) is too small to tile well.
+#include <cstdlib>
+
 #include "engine.h"
 
 namespace cindm {
@@ -542,6 +544,199 @@ __global__ void __launch_bounds__(256, 2) stem_kernel(StemParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Stem on the tensor cores (body-pair model, F = 8): the same block as stem_kernel, one WARP per slice.
+//   conv0 as a GEMM  [24 (32) rows] x [K = 5 taps x 8 channels = 40 (48)] x [64]  with mma.sync.m16n8k16, the A fragments
+//   read straight out of a 16-bit copy of the (zero-padded) slice: A[h][8 tap + c] = x[h + tap - 2][c];
+//   the 1x1 residual conv as a second GEMM with K = 8 (16) on the centre tap.
+// A GroupNorm group (8 channels x 24 positions) is exactly one n8 accumulator tile, so its statistics are a warp reduction.
+// Outputs are staged in shared memory and written with 16-byte row-major stores.  The SIMT stem_kernel spent 1 300 FFMA /
+// LDS instructions per (slice, channel) thread (ncu: issue-active 68 %, 162 M warp instructions per launch at 43 008 slices);
+// here the contraction is 64 MMAs per slice.  Operands are rounded to the activation type (fp16 / bf16) like every other
+// layer's; accumulation, GroupNorm and Mish stay fp32.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
+template <>
+__device__ __forceinline__ void mma_16816<__half>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <>
+__device__ __forceinline__ void mma_16816<__nv_bfloat16>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <typename T>
+__device__ __forceinline__ uint32_t pack_pair(float a, float b) {
+    T lo = from_f32<T>(a), hi = from_f32<T>(b);
+    return (uint32_t)(*reinterpret_cast<unsigned short*>(&lo)) | ((uint32_t)(*reinterpret_cast<unsigned short*>(&hi)) << 16);
+}
+
+constexpr int kStemWarps = 8;
+constexpr int kStemXRows = 40;              // 2 zero rows + 24 positions + zero rows up to the last row a fragment can touch
+constexpr int kStemStageRow = 72;           // halves per staged output row (144 B: 16-byte aligned, conflict-free)
+
+template <typename T>
+__global__ void __launch_bounds__(kStemWarps * 32, 2) stem_mma_kernel(StemParams p) {
+    __shared__ __align__(16) T xs[kStemWarps][kStemXRows][8];
+    __shared__ __align__(16) T stage[kStemWarps][24 * kStemStageRow];
+    __shared__ uint2 bw[3][8][32];          // conv0 B fragments (b0, b1) of k-step ks, n tile nt, per lane
+    __shared__ uint32_t br[8][32];          // residual conv B fragment b0 (its K rows 8..15 are zero)
+    __shared__ float vbias[64], vgamma[64], vbeta[64], vtb[64], vbr[64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    pdl_wait();
+    pdl_trigger();
+    // ---- per-block set-up: fragments of the (rounded) weights, channel vectors, zero padding rows
+    for (int i = threadIdx.x; i < 3 * 8 * 32; i += blockDim.x) {
+        const int l = i & 31, nt = (i >> 5) & 7, ks = i >> 8;
+        const int gg = l >> 2, tt = l & 3, co = nt * 8 + gg;
+        auto wv = [&](int kk) { return kk < 40 ? p.w0[kk * 64 + co] : 0.f; };
+        const int k0 = 16 * ks + 2 * tt;
+        bw[ks][nt][l] = make_uint2(pack_pair<T>(wv(k0), wv(k0 + 1)), pack_pair<T>(wv(k0 + 8), wv(k0 + 9)));
+    }
+    for (int i = threadIdx.x; i < 8 * 32; i += blockDim.x) {
+        const int l = i & 31, nt = i >> 5;
+        const int gg = l >> 2, tt = l & 3, co = nt * 8 + gg;
+        br[nt][l] = pack_pair<T>(p.wr[(2 * tt) * 64 + co], p.wr[(2 * tt + 1) * 64 + co]);
+    }
+    if (threadIdx.x < 64) {
+        const int c = threadIdx.x;
+        vbias[c] = p.b0[c]; vgamma[c] = p.gamma[c]; vbeta[c] = p.beta[c]; vbr[c] = p.br[c];
+        vtb[c] = p.t_dev ? p.tbias[(long long)(*p.t_dev) * 64 + c] : p.tbias[c];
+    }
+    for (int i = lane; i < kStemXRows * 8; i += 32) (&xs[warp][0][0])[i] = from_f32<T>(0.f);
+    __syncthreads();
+    T* xw = &xs[warp][0][0];
+    T* sw = &stage[warp][0];
+    for (long long s = (long long)blockIdx.x * kStemWarps + warp; s < p.S; s += (long long)gridDim.x * kStemWarps) {
+        // ---- the slice: 24 rows x 8 features, fp32 -> 16-bit, into rows 2..25 of the padded copy
+        if (lane < 24) {
+            const int h = lane;
+            float4 v0, v1;
+            if (p.gather) {
+                const int b = (int)(s % p.B);
+                const int wp = (int)(s / p.B);
+                const int pr = wp % p.P, kk = wp / p.P;
+                int ii = 0, rem = pr;
+                while (rem >= p.n - 1 - ii) { rem -= p.n - 1 - ii; ++ii; }
+                const int jj = ii + 1 + rem;
+                const float4* row = reinterpret_cast<const float4*>(p.x) + ((long long)b * p.T + kk * p.start + h) * p.n;
+                v0 = row[ii]; v1 = row[jj];
+            } else {
+                const float4* row = reinterpret_cast<const float4*>(p.x) + (s * 24 + h) * 2;
+                v0 = row[0]; v1 = row[1];
+            }
+            *reinterpret_cast<uint4*>(xw + (h + 2) * 8) =
+                make_uint4(pack_pair<T>(v0.x, v0.y), pack_pair<T>(v0.z, v0.w), pack_pair<T>(v1.x, v1.y), pack_pair<T>(v1.z, v1.w));
+        }
+        __syncwarp();
+        // ---- A fragments: A[row][16 ks + k] = x[row + 2 ks (+1 for k >= 8)][k & 7]; rows = padded rows m + tap
+        uint32_t af[2][3][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks) {
+                const T* base = xw + (mt * 16 + g + 2 * ks) * 8 + 2 * t4;
+                af[mt][ks][0] = *reinterpret_cast<const uint32_t*>(base);
+                af[mt][ks][1] = *reinterpret_cast<const uint32_t*>(base + 8 * 8);
+                af[mt][ks][2] = *reinterpret_cast<const uint32_t*>(base + 8);
+                af[mt][ks][3] = *reinterpret_cast<const uint32_t*>(base + 9 * 8);
+            }
+        // ---- conv0 + GroupNorm + Mish + time bias, four n8 tiles (= four GroupNorm groups) at a time
+#pragma unroll
+        for (int nh = 0; nh < 2; ++nh) {
+            float acc[2][4][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[mt][q][c] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint2 b = bw[ks][nh * 4 + q][lane];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) mma_16816<T>(acc[mt][q], af[mt][ks], b.x, b.y);
+                }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int nt = nh * 4 + q, c0 = nt * 8 + 2 * t4;
+                const float2 bi = *reinterpret_cast<const float2*>(&vbias[c0]);
+                // this thread's six valid outputs of the group: rows g, g + 8, 16 + g (row 24 + g is padding), two channels
+                float y[6] = {acc[0][q][0] + bi.x, acc[0][q][1] + bi.y, acc[0][q][2] + bi.x, acc[0][q][3] + bi.y,
+                              acc[1][q][0] + bi.x, acc[1][q][1] + bi.y};
+                float sum = ((y[0] + y[1]) + (y[2] + y[3])) + (y[4] + y[5]);
+                sum = warp_sum(sum);
+                const float mean = sum * (1.0f / 192.0f);
+                float sq = 0.f;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) { const float d = y[i] - mean; sq = fmaf(d, d, sq); }
+                sq = warp_sum(sq);
+                const float rstd = rsqrtf(sq * (1.0f / 192.0f) + 1e-5f);
+                const float2 ga = *reinterpret_cast<const float2*>(&vgamma[c0]), be = *reinterpret_cast<const float2*>(&vbeta[c0]);
+                const float2 tb = *reinterpret_cast<const float2*>(&vtb[c0]);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int row = i == 0 ? g : (i == 1 ? g + 8 : 16 + g);
+                    const float v0 = mish_fast((y[2 * i] - mean) * rstd * ga.x + be.x) + tb.x;
+                    const float v1 = mish_fast((y[2 * i + 1] - mean) * rstd * ga.y + be.y) + tb.y;
+                    *reinterpret_cast<uint32_t*>(sw + row * kStemStageRow + c0) = pack_pair<T>(v0, v1);
+                }
+            }
+        }
+        __syncwarp();
+        {
+            T* dst = reinterpret_cast<T*>(p.out_b0) + s * 24 * 64;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const int idx = i * 32 + lane, row = idx >> 3, c8 = idx & 7;
+                *reinterpret_cast<uint4*>(dst + row * 64 + c8 * 8) = *reinterpret_cast<const uint4*>(sw + row * kStemStageRow + c8 * 8);
+            }
+        }
+        __syncwarp();
+        // ---- residual 1x1 conv on the centre tap (K = 8 channels, padded to 16 with zeros)
+#pragma unroll
+        for (int nh = 0; nh < 2; ++nh) {
+            float acc[2][4][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[mt][q][c] = 0.f;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                // centre tap = k-step 1, low half (tap 2): the fragment registers already loaded for conv0
+                const uint32_t ar[4] = {af[mt][1][0], af[mt][1][1], 0u, 0u};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) mma_16816<T>(acc[mt][q], ar, br[nh * 4 + q][lane], 0u);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c0 = (nh * 4 + q) * 8 + 2 * t4;
+                const float2 bi = *reinterpret_cast<const float2*>(&vbr[c0]);
+                *reinterpret_cast<uint32_t*>(sw + g * kStemStageRow + c0) = pack_pair<T>(acc[0][q][0] + bi.x, acc[0][q][1] + bi.y);
+                *reinterpret_cast<uint32_t*>(sw + (g + 8) * kStemStageRow + c0) = pack_pair<T>(acc[0][q][2] + bi.x, acc[0][q][3] + bi.y);
+                *reinterpret_cast<uint32_t*>(sw + (16 + g) * kStemStageRow + c0) = pack_pair<T>(acc[1][q][0] + bi.x, acc[1][q][1] + bi.y);
+            }
+        }
+        __syncwarp();
+        {
+            T* dst = reinterpret_cast<T*>(p.out_res) + s * 24 * 64;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const int idx = i * 32 + lane, row = idx >> 3, c8 = idx & 7;
+                *reinterpret_cast<uint4*>(dst + row * 64 + c8 * 8) = *reinterpret_cast<const uint4*>(sw + row * kStemStageRow + c8 * 8);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 int launch_stem(const StemLaunch& a, cudaStream_t st) {
     if (a.S == 0) return 0;
     const int F = a.conv0->cin;
@@ -552,6 +747,17 @@ int launch_stem(const StemLaunch& a, cudaStream_t st) {
     p.tbias = a.tbias; p.t_dev = a.t_dev; p.wr = a.res->w; p.br = a.res->bias;
     p.out_b0 = a.out_b0; p.out_res = a.out_res; p.S = a.S;
     p.gather = a.gather; p.B = a.B; p.n = a.n; p.P = a.n * (a.n - 1) / 2; p.start = a.start; p.T = a.T;
+    static int stem_simt = -1;
+    if (stem_simt < 0) { const char* e = getenv("CINDM_STEM_SIMT"); stem_simt = (e && e[0] == '1') ? 1 : 0; }
+    if (F == 8 && !stem_simt) {
+        if (a.prec != PREC_F16 && a.prec != PREC_BF16) return fail(-2, "stem kernel is built for the 16-bit precisions");
+        long long need = (a.S + kStemWarps - 1) / kStemWarps;
+        const unsigned grid = (unsigned)(need < 148LL * 8 ? need : 148LL * 8);
+        if (a.prec == PREC_F16) CINDM_CHECK_CUDA(launch_chain(stem_mma_kernel<__half>, dim3(grid), dim3(kStemWarps * 32), 0, st, p));
+        else CINDM_CHECK_CUDA(launch_chain(stem_mma_kernel<__nv_bfloat16>, dim3(grid), dim3(kStemWarps * 32), 0, st, p));
+        CINDM_CHECK_LAUNCH();
+        return 0;
+    }
     const unsigned blocks = (unsigned)((a.S + 3) / 4);
     if (a.prec == PREC_F16 && F == 8) CINDM_CHECK_CUDA(launch_chain(stem_kernel<__half, 8>, dim3(blocks), dim3(256), 0, st, p));
     else if (a.prec == PREC_F16) CINDM_CHECK_CUDA(launch_chain(stem_kernel<__half, 4>, dim3(blocks), dim3(256), 0, st, p));
