@@ -583,8 +583,6 @@ class GaussianDiffusion1D:
     def _conditioned_ddim(self, state, chain_blocks, noise, pairs, seed):
         """DDIM loop (reference :1751-1797 without guidance) on state [Bx, conditioned_steps + image_size, F] whose first
         conditioned_steps frames are the condition; returns the final state (x_start on the last pair)."""
-        if not self.is_ddim_sampling and pairs is None and self.sampling_timesteps != self.num_timesteps:
-            raise ValueError("sampling_timesteps must be <= timesteps")
         pairs, coef = self.ddim_schedule(pairs)
         times = torch.tensor([p[0] for p in pairs], dtype=torch.int32)
         times_next = torch.tensor([p[1] for p in pairs], dtype=torch.int32)

@@ -321,3 +321,124 @@ def ddim_sample(sd, tables, img, noise_fn, *, sampling_timesteps, eta=0.0, n_com
         if time_next < 0:
             img = x0
     return img, x0
+
+
+# --------------------------------------------------------------------------- conditioned model
+def model_predictions_cond(sd, tables, x, cond, t, clip_x_start=True, eps_model=None):
+    """model_predictions with conditioned_steps = cond.shape[1] (:951-1031): the model sees cat(cond, x); pred_noise and
+    x_start (predict_start_from_noise :914-918, optionally clamped) are cut back to x's frames (:1028-1030).
+    eps_model(full, t) overrides the plain U-Net (the EBM composition passes gradient())."""
+    k = cond.shape[1]
+    full = torch.cat([cond, x], dim=1)
+    tt = torch.full((full.shape[0],), int(t), dtype=torch.long)
+    eps = eps_model(full, int(t)) if eps_model is not None else unet_ref.unet_forward(sd, full, tt)
+    x0 = tables["sqrt_recip_alphas_cumprod"][t] * full - tables["sqrt_recipm1_alphas_cumprod"][t] * eps
+    if clip_x_start:
+        x0 = x0.clamp(-1.0, 1.0)
+    return eps[:, k:], x0[:, k:]
+
+
+def ddim_coefficients(tables, time, time_next, eta):
+    """alpha_next.sqrt(), c, sigma of one DDIM pair, formed from the fp32 alphas_cumprod like :1778-1782."""
+    alpha, alpha_next = tables["alphas_cumprod"][time], tables["alphas_cumprod"][time_next]
+    sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+    c = (1 - alpha_next - sigma ** 2).sqrt()
+    return alpha_next.sqrt(), c, sigma
+
+
+def ddim_sample_cond(sd, tables, img, cond, noise_fn, *, pairs, eta=0.0):
+    """ddim_sample with cond on a conditioned model (:1751-1797 with design_fn None): one randn_like per pair, the last
+    pair returns x_start."""
+    for time, time_next in pairs:
+        eps, x0 = model_predictions_cond(sd, tables, img, cond, time, True)
+        noise = noise_fn(img.shape)
+        if time_next < 0:
+            img = x0
+            continue
+        a, c, sigma = ddim_coefficients(tables, time, time_next, eta)
+        img = x0 * a + c * eps + sigma * noise
+    return img
+
+
+def autoregress_time_compose(sd, tables, cond, imgs, noise_fn, *, pairs, eta=0.0, conditioned_steps=4):
+    """autoregress_time_compose_sample (:2282-2327, is_single_step_prediction False): window i is sampled with the DDIM-form
+    loop conditioned on the last frames of window i - 1; imgs[i] is window i's initial randn."""
+    out = []
+    for i, img in enumerate(imgs):
+        if i != 0:
+            cond = out[-1][:, -conditioned_steps:]
+        img = ddim_sample_cond(sd, tables, img, cond, noise_fn, pairs=pairs, eta=eta)
+        out.append(img)
+    return torch.cat(out, dim=1)
+
+
+def composing_time(sd, tables, cond, img_infered, noise_fn, *, pairs, eta=0.0, n_composed=2, conditioned_steps=4):
+    """composing_time_sample (:1806-1854): n_composed + 1 blocks denoised together; before every step block i + 1 takes the
+    last conditioned_steps frames of block i's current iterate as its condition (:1827-1829)."""
+    b = cond.shape[0]
+    conds = torch.zeros(((n_composed + 1) * b,) + tuple(cond.shape[1:]))
+    conds[:b] = cond
+    for time, time_next in pairs:
+        for i in range(n_composed):
+            conds[(i + 1) * b:(i + 2) * b] = img_infered[i * b:(i + 1) * b, -conditioned_steps:]
+        noise = noise_fn(img_infered.shape)                       # drawn BEFORE the model call (:1836)
+        eps, x0 = model_predictions_cond(sd, tables, img_infered, conds, time, True)
+        if time_next < 0:
+            img_infered = x0
+            continue
+        a, c, sigma = ddim_coefficients(tables, time, time_next, eta)
+        img_infered = x0 * a + c * eps + sigma * noise
+    first = img_infered[:b]
+    rest = torch.cat([img_infered[(k + 1) * b:(k + 2) * b, -20:] for k in range(n_composed)], dim=1)
+    return first, rest
+
+
+# --------------------------------------------------------------------------- EBM body composition (SURVEY section 8 f3)
+def ebm_gradient(sd_pair, sd_single, x_t, t, n_bodies):
+    """gradient() for t <= 400 (:1856-1982): for every body, the pair model's epsilon for it summed over the pairs that
+    contain it (pairs batched along dim 0 in lexicographic order), minus coef x the unconditional single-body epsilon
+    (coef 1.4 for 4 bodies :1904, 1 for 3 bodies :1961)."""
+    coef = {4: 1.4, 3: 1.0}[n_bodies]
+    b = x_t.shape[0]
+    bodies = [x_t[:, :, 4 * i:4 * i + 4] for i in range(n_bodies)]
+    pairs = [(i, j) for i in range(n_bodies) for j in range(i + 1, n_bodies)]
+    x_in = torch.cat([torch.cat([bodies[i], bodies[j]], dim=2) for i, j in pairs], dim=0)
+    tt = torch.full((x_in.shape[0],), int(t), dtype=torch.long)
+    eps_pair = unet_ref.unet_forward(sd_pair, x_in, tt)
+    t1 = torch.full((b,), int(t), dtype=torch.long)
+    out = []
+    for r in range(n_bodies):
+        acc = None
+        for p, (i, j) in enumerate(pairs):
+            if r == i:
+                term = eps_pair[p * b:(p + 1) * b, :, 0:4]
+            elif r == j:
+                term = eps_pair[p * b:(p + 1) * b, :, 4:8]
+            else:
+                continue
+            acc = term if acc is None else acc + term
+        out.append(acc - coef * unet_ref.unet_forward(sd_single, bodies[r], t1))
+    return torch.cat(out, dim=2)
+
+
+def ebm_p_sample(sd_pair, sd_single, tables, x, cond, t, noise_fn):
+    """p_sample (:1046-1186, no guidance) on a conditioned model whose epsilon is gradient(cat(cond, x), t, 4) (:1002-1003)."""
+    eps, x0 = model_predictions_cond(sd_pair, tables, x, cond, t, False,
+                                     eps_model=lambda full, tt: ebm_gradient(sd_pair, sd_single, full, tt, 4))
+    x0 = x0.clamp(-1.0, 1.0)                                      # p_mean_variance clip_denoised (:1038-1039)
+    mean = tables["posterior_mean_coef1"][t] * x0 + tables["posterior_mean_coef2"][t] * x
+    if t > 0:
+        mean = mean + (0.5 * tables["posterior_log_variance_clipped"][t]).exp() * noise_fn(x.shape)
+    return mean, x0
+
+
+def ula_steps(sd_pair, sd_single, x, t, n_steps, n_bodies, betas_inference, scalar_for_gradient, noise_fn):
+    """sample_step_ULA (:2047-2073): x <- x + grad * ss + randn * sqrt(2 ss), grad = -scalar[t] * gradient() for t > 400."""
+    ss = (betas_inference * 0.035)[t]
+    std = (2 * ss) ** .5
+    for _ in range(n_steps):
+        grad = ebm_gradient(sd_pair, sd_single, x, t, n_bodies)
+        if t > 400:
+            grad = -1 * scalar_for_gradient[t] * grad
+        x = x + grad * ss + noise_fn(grad.shape) * std
+    return x

@@ -134,3 +134,39 @@ def test_unconditioned_ddim_ignores_composition_arguments_without_design_fn(test
     a = dif.sample(batch_size=2)                                               # API defaults: n_composed=2, compose_mode="mean"
     b = dif.ddim_sample((2, 24, 8), None, n_composed=0, compose_n_bodies=2, compose_mode="mean-inside")
     assert tuple(a.shape) == (2, 24, 8) and torch.equal(a, b)
+
+
+def test_conditioned_paths_vs_oracle_on_other_shapes(conditioned, test_weights):
+    """Beyond the golden shapes: odd batch sizes / more windows against the oracle restatement (itself pinned by the goldens)."""
+    from oracle import sampler_ref
+    dif = conditioned
+    tabs = sampler_ref.cosine_schedule_tables()
+    gen = torch.Generator().manual_seed(77)
+    b, nc = 5, 3
+    pairs = [(640, 410), (410, 170), (170, -1)]
+    cond = torch.randn(b, 4, 8, generator=gen) * 0.5
+    imgs = torch.randn(nc + 1, b, 20, 8, generator=gen)
+    noise = torch.randn(nc + 1, len(pairs), 1, b, 20, 8, generator=gen)
+    draws = [z for w in noise for z in w[:, 0]]
+    ref = sampler_ref.autoregress_time_compose(test_weights, tabs, cond, list(imgs), lambda s: draws.pop(0), pairs=pairs, eta=0.4)
+    keep = (dif.sampling_timesteps, dif.ddim_sampling_eta)
+    dif.sampling_timesteps, dif.ddim_sampling_eta = len(pairs), 0.4
+    try:
+        for precision, engine, tol in PRECISIONS:
+            dif.precision, dif.conv_engine = precision, engine
+            out = dif.autoregress_time_compose_sample(b, cond, nc, False, 20 * (nc + 1), noise=noise, img=imgs, pairs=pairs)
+            assert tuple(out.shape) == (b, 20 * (nc + 1), 8)
+            assert rel_l2(out, ref) < 4 * tol, (precision, engine)
+        b2, nc2 = 3, 1
+        cond2 = torch.randn(b2, 4, 8, generator=gen) * 0.5
+        init = torch.randn((nc2 + 1) * b2, 20, 8, generator=gen)
+        nz = torch.randn(len(pairs), 1, (nc2 + 1) * b2, 20, 8, generator=gen)
+        draws = list(nz[:, 0])
+        first, rest = sampler_ref.composing_time(test_weights, tabs, cond2, init, lambda s: draws.pop(0), pairs=pairs, eta=0.4,
+                                                 n_composed=nc2)
+        for precision, engine, tol in PRECISIONS:
+            dif.precision, dif.conv_engine = precision, engine
+            a, r = dif.composing_time_sample((b2, 20, 8), cond2, True, nc2, noise=nz, img=init, pairs=pairs)
+            assert rel_l2(a, first) < 2 * tol and rel_l2(r, rest) < 2 * tol, (precision, engine)
+    finally:
+        dif.sampling_timesteps, dif.ddim_sampling_eta = keep

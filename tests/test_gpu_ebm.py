@@ -113,3 +113,26 @@ def test_sample_compose_multibodies(ebm, golden, precision, engine, tol):
     finally:
         ebm.use_cuda_graph = True
         ebm.betas_inference = keep
+
+
+def test_ebm_paths_vs_oracle_on_other_shapes(ebm, test_weights):
+    """Beyond the golden shapes (odd batch sizes, 3 bodies at a batch other than the reference's hard-coded 20) against the
+    oracle restatement, itself pinned by the goldens (tests/test_oracle_golden.py)."""
+    from oracle import sampler_ref
+    from cindm_b200.model.params import init_unet_params, unet_param_shapes
+    single = init_unet_params(unet_param_shapes(24, 4), seed=7, randomize_affine=True)
+    tabs = sampler_ref.cosine_schedule_tables()
+    gen = torch.Generator().manual_seed(123)
+    x4 = torch.randn(5, 24, 16, generator=gen)
+    x3 = torch.randn(7, 24, 12, generator=gen)
+    ref4 = sampler_ref.ebm_gradient(test_weights, single, x4, 77, 4)
+    ref3 = sampler_ref.ebm_gradient(test_weights, single, x3, 391, 3)
+    cond, x = torch.randn(3, 4, 16, generator=gen) * 0.5, torch.randn(3, 20, 16, generator=gen)
+    nz = torch.randn(1, 3, 20, 16, generator=gen)
+    ref_img, ref_x0 = sampler_ref.ebm_p_sample(test_weights, single, tabs, x, cond, 233, lambda s: nz[0])
+    for precision, engine, tol in PRECISIONS:
+        ebm.precision, ebm.conv_engine = precision, engine
+        assert rel_l2(ebm.gradient(x4, 77, 4), ref4) < tol, (precision, engine)
+        assert rel_l2(ebm.gradient(x3, 391, 3), ref3) < tol, (precision, engine)
+        img, x0 = ebm.p_sample(x, cond, 233, noise=nz)
+        assert rel_l2(img, ref_img) < tol and rel_l2(x0, ref_x0) < tol, (precision, engine)

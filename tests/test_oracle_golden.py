@@ -146,3 +146,59 @@ def test_compose_outside_steps_match_reference(golden, test_weights, case):
         assert rel_l2(img, g[f"{case}:img_after_{si}"]) < 1e-5, (si, t)
         img = torch.from_numpy(g[f"{case}:img_after_{si}"])
     assert not noise
+
+
+# ---- round 2: the conditioned model (f2) and the EBM body composition (f3) restated in oracle/sampler_ref.py, pinned by the
+#      goldens minted from the unmodified reference (oracle/make_golden.py::gen_conditioned / gen_ebm)
+def _pairs(g, key):
+    return [tuple(int(v) for v in p) for p in g[key + ":pairs"]]
+
+
+def test_oracle_conditioned_model_reproduces_the_reference(golden, test_weights):
+    import torch
+    from oracle import sampler_ref
+    g = golden("conditioned.npz")
+    tabs = sampler_ref.cosine_schedule_tables()
+    cond = torch.from_numpy(g["cond"])
+    for t, clip in ((300, True), (980, False)):
+        eps, x0 = sampler_ref.model_predictions_cond(test_weights, tabs, torch.from_numpy(g[f"mp_t{t}:x"]), cond, t, clip)
+        assert torch.allclose(eps, torch.from_numpy(g[f"mp_t{t}:eps"]), atol=1e-6)
+        assert torch.allclose(x0, torch.from_numpy(g[f"mp_t{t}:x0"]), rtol=1e-5, atol=1e-4 if not clip else 1e-6)
+    draws = list(torch.from_numpy(g["ddim:noise"]))
+    img = sampler_ref.ddim_sample_cond(test_weights, tabs, torch.from_numpy(g["ddim:x_init"]), cond, lambda s: draws.pop(0),
+                                       pairs=_pairs(g, "ddim"), eta=float(g["ddim:eta"]))
+    assert not draws and torch.allclose(img, torch.from_numpy(g["ddim:img"]), atol=2e-5)
+    noise = torch.from_numpy(g["auto:noise"])
+    draws = [z for w in noise for z in w]
+    out = sampler_ref.autoregress_time_compose(test_weights, tabs, cond, list(torch.from_numpy(g["auto:x_init"])),
+                                               lambda s: draws.pop(0), pairs=_pairs(g, "auto"), eta=float(g["auto:eta"]))
+    assert not draws and torch.allclose(out, torch.from_numpy(g["auto:out"]), atol=5e-5)
+    draws = list(torch.from_numpy(g["chain:noise"]))
+    first, rest = sampler_ref.composing_time(test_weights, tabs, cond, torch.from_numpy(g["chain:x_init"]), lambda s: draws.pop(0),
+                                             pairs=_pairs(g, "chain"), eta=float(g["chain:eta"]), n_composed=2)
+    assert not draws
+    assert torch.allclose(first, torch.from_numpy(g["chain:img"]), atol=2e-5)
+    assert torch.allclose(rest, torch.from_numpy(g["chain:img_infered"]), atol=5e-5)
+
+
+def test_oracle_ebm_composition_reproduces_the_reference(golden, test_weights):
+    import torch
+    from oracle import sampler_ref
+    from cindm_b200.model.params import init_unet_params, unet_param_shapes
+    g = golden("ebm.npz")
+    single = init_unet_params(unet_param_shapes(24, 4), seed=7, randomize_affine=True)
+    tabs = sampler_ref.cosine_schedule_tables()
+    x4 = torch.from_numpy(g["grad4_t300:x"])
+    assert torch.allclose(sampler_ref.ebm_gradient(test_weights, single, x4, 300, 4), torch.from_numpy(g["grad4_t300:eps"]), atol=2e-6)
+    x3 = torch.from_numpy(g["grad3_t100:x"])
+    assert torch.allclose(sampler_ref.ebm_gradient(test_weights, single, x3, 100, 3), torch.from_numpy(g["grad3_t100:eps"]), atol=2e-6)
+    scalar = torch.from_numpy(g["scalar_for_gradient"])
+    betas_inf = torch.linspace(1000 / 500 * 0.0001, 1000 / 500 * 0.02, 500, dtype=torch.float64)     # linear_beta_schedule(500)
+    draws = list(torch.from_numpy(g["ula:noise"]))
+    y = sampler_ref.ula_steps(test_weights, single, x4, 450, 2, 4, betas_inf, scalar, lambda s: draws.pop(0))
+    assert not draws and torch.allclose(y.float(), torch.from_numpy(g["ula:out"]), atol=5e-6)
+    cond, x = torch.from_numpy(g["ps:cond"]), torch.from_numpy(g["ps:x"])
+    for t in (400, 150, 0):
+        img, x0 = sampler_ref.ebm_p_sample(test_weights, single, tabs, x, cond, t, lambda s, t=t: torch.from_numpy(g[f"ps_t{t}:noise"]))
+        assert torch.allclose(img, torch.from_numpy(g[f"ps_t{t}:img"]), atol=5e-6), t
+        assert torch.allclose(x0, torch.from_numpy(g[f"ps_t{t}:x0"]), atol=5e-6), t
