@@ -8,7 +8,10 @@ one-forward-per-(window, pair) form, x0 / posterior (:914-918, :938-949, :1033-1
 the design-objective guidance through `torch.autograd.grad` (:1314-1349) with the
 driver's objective (/root/reference/inference/inverse_design_diffusion_1d.py:211-258),
 the recurrence / re-noise update (:1284-1376), the 1000-step loop (:1655-1720) and the DDIM
-loop (:1723-1804) with the epsilon-returning mode of the recurrence branch (:1372-1376).
+loop (:1723-1804) with the epsilon-returning mode of the recurrence branch (:1372-1376); the conditioned model's
+samplers (cond path :956-957 / :1028-1030, ddim_sample with cond, autoregress_time_compose_sample :2239-2327,
+composing_time_sample :1806-1854) and the EBM body composition (gradient :1856-1982, p_sample :1046-1186 with
+model_unconditioned, sample_step_ULA :2047-2073).
 
 Noise is ALWAYS supplied by the caller (a callable returning a tensor per draw) so the
 same tensors can be fed to the CUDA path.  Pinned against the live reference and the
