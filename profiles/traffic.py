@@ -26,9 +26,9 @@ def main(path):
         scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}.get(r["Metric Unit"], 1.0)
         d[r["Metric Name"]] = v * scale
     seq = [launches[k] for k in sorted(launches)]
-    stems = [i for i, d in enumerate(seq) if "stem_kernel" in d["name"]]
+    stems = [i for i, d in enumerate(seq) if "stem_kernel" in d["name"] or "stem_mma_kernel" in d["name"]]
     if len(stems) < 2:
-        raise SystemExit("need at least two stem_kernel launches in the capture")
+        raise SystemExit("need at least two stem launches in the capture")
     ev = seq[stems[0]:stems[1]]
     classes = collections.OrderedDict()
     for d in ev:
@@ -44,7 +44,7 @@ def main(path):
     out = {"evaluation_kernels": len(ev), "total_ms": total,
            "classes": collections.OrderedDict(sorted(classes.items(), key=lambda kv: -kv[1]["ms"]))}
     if "--md" in sys.argv:
-        print("One composed-epsilon evaluation (C4 per GPU: S = 43 008 slices) between two consecutive stem_kernel launches.")
+        print("One composed-epsilon evaluation (C4 per GPU: S = 43 008 slices) between two consecutive stem launches.")
         print("ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
               "(serialised, cold-cache: compare SHARES).\n")
         print("| kernel | launches | total ms | share | DRAM read MB | DRAM write MB |\n|---|---|---|---|---|---|")
