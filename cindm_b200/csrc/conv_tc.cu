@@ -703,6 +703,7 @@ int launch_conv_tc(const ConvTcLaunch& a, cudaStream_t st) {
         CINDM_TRY(launch_conv_tc_one(a, 0, st));
         return launch_conv_tc_one(a, 1, st);
     }
+    if (conv_tc_cm_eligible(a)) return launch_conv_tc_cm(a, st);
     return launch_conv_tc_one(a, 0, st);
 }
 

@@ -34,4 +34,9 @@ struct ConvTcLaunch {
 
 int launch_conv_tc(const ConvTcLaunch& a, cudaStream_t st);
 
+// conv_tc_cm.cu: the k = 5 GroupNorm + Mish convs at 64 / 128 (/ 256) channels with a channel-major accumulator
+// (output channels on the TMEM lanes).  launch_conv_tc routes the eligible layers there.
+bool conv_tc_cm_eligible(const ConvTcLaunch& a);
+int launch_conv_tc_cm(const ConvTcLaunch& a, cudaStream_t st);
+
 }  // namespace cindm

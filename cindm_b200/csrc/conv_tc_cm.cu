@@ -1,0 +1,406 @@
+// GroupNorm + Mish temporal convolution with a CHANNEL-MAJOR accumulator (sm_100a, tcgen05 / TMEM / TMA).
+//
+// The same implicit GEMM as conv_tc.cu with the operand roles swapped:
+//
+//   D[co][row] = sum_{tap, ci} W[tap][co][ci] * X_tap[row][ci]        M = output channels, N = 240 rows = whole slices
+//
+// so that a TMEM lane is an output CHANNEL and the columns of one accumulator are (slice, position).  For the epilogue
+// that turns the row-major kernel's costs inside out:
+//   * bias / gamma / beta / time-embedding value of a thread's channel are four registers (the row-major epilogue reads
+//     them from shared memory once per element: ~1.1 LDS.128 per output element-warp);
+//   * a slice's H positions of one channel sit in one thread: per-thread sums, then a shuffle tree over the CPG adjacent
+//     lanes of the channel group give the GroupNorm statistics - no shared-memory partials, no CTA barriers, ONE pass
+//     over the accumulator, every epilogue warp streams through its slices independently;
+//   * normalisation and affine collapse into one FFMA per element (per-(slice, channel) scale / shift).
+// The price: activations are channels-last, so a thread's outputs are 2-byte values C apart; a warp instruction stores 32
+// consecutive channels of one row (64 contiguous bytes, two full sectors).
+//
+// cout = 64 (DUAL): M = 64 MMAs occupy 16 lanes of every 32-lane TMEM sub-partition; two row tiles are accumulated side
+// by side (lane offset 16), so all 128 lanes carry work.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2.. epilogue (EW / 4 per lane quarter, the
+// slices of a tile dealt round-robin among the warps of a quarter).
+#include "conv_tc.h"
+#include "tc_common.cuh"
+
+namespace cindm {
+
+namespace {
+
+constexpr int kRows = 240;                    // rows (slice positions) per tile: 10 x 24 = 20 x 12 = 40 x 6
+constexpr int kXTileBytes = kRows * 128;      // one K block (64 channels) of a row tile
+constexpr int kAccStride = 256;               // TMEM columns between the two accumulators
+
+struct CmParams {
+    const float* bias;        // [cout] or null
+    const float* gamma;       // [cout]
+    const float* beta;        // [cout]
+    const float* add_vec;     // [cout] or [timesteps][cout] when t_dev != null
+    const int* t_dev;
+    const void* add_res;      // [S][H][cout] 16-bit or null
+    void* out;                // [S][H][cout] 16-bit
+    long long S;
+    int cout, c0, c1, taps, k_chunks_per_tap;
+    int m_tiles;              // cout / 128 (1 when DUAL)
+    int row_tiles;            // ceil(S / slices per tile)  (DUAL: pairs of row tiles)
+};
+
+constexpr int cm_stages(bool dual) { return dual ? 3 : 4; }
+constexpr int cm_stage_bytes(bool dual) { return dual ? 64 * 128 + 2 * kXTileBytes : 128 * 128 + kXTileBytes; }
+constexpr size_t cm_smem_bytes(bool dual) { return 1024 + (size_t)cm_stages(dual) * cm_stage_bytes(dual) + (2 * cm_stages(dual) + 4) * 8 + 16; }
+
+// ---- TMEM loads of N consecutive columns of this thread's lane (no wait inside)
+__device__ __forceinline__ void tmem_ld_x2(uint32_t a, float* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(a));
+}
+__device__ __forceinline__ void tmem_ld_x4(uint32_t a, float* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a));
+}
+__device__ __forceinline__ void tmem_ld_x8(uint32_t a, float* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(a));
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t a, float* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
+          "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]) : "r"(a));
+}
+template <int H> __device__ __forceinline__ void tmem_ld_slice(uint32_t a, float (&v)[H]);
+template <> __device__ __forceinline__ void tmem_ld_slice<24>(uint32_t a, float (&v)[24]) { tmem_ld_x16(a, v); tmem_ld_x8(a + 16, v + 16); }
+template <> __device__ __forceinline__ void tmem_ld_slice<12>(uint32_t a, float (&v)[12]) { tmem_ld_x8(a, v); tmem_ld_x4(a + 8, v + 8); }
+template <> __device__ __forceinline__ void tmem_ld_slice<6>(uint32_t a, float (&v)[6]) { tmem_ld_x4(a, v); tmem_ld_x2(a + 4, v + 4); }
+
+// tcgen05.wait::ld that CARRIES the loaded registers: their consumers cannot be scheduled above the wait
+template <int H> __device__ __forceinline__ void tmem_wait_slice(float (&v)[H]);
+template <> __device__ __forceinline__ void tmem_wait_slice<6>(float (&v)[6]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5])::"memory");
+}
+template <> __device__ __forceinline__ void tmem_wait_slice<12>(float (&v)[12]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]),
+                   "+f"(v[10]), "+f"(v[11])::"memory");
+}
+template <> __device__ __forceinline__ void tmem_wait_slice<24>(float (&v)[24]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]),
+                   "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]), "+f"(v[17]), "+f"(v[18]),
+                   "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23])::"memory");
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ------------------------------------------------------------------ the kernel
+// EW epilogue warps (8, 12 or 16); RES: a residual tensor is added last.  COUT == 64 (DUAL): two row tiles per accumulator.  The channel count is a template
+// parameter so that a thread's H outputs (COUT elements apart) are addressed with immediate offsets.
+template <typename T16, int H, int COUT, int EW, bool RES>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
+conv_tc_cm_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x1,
+                  const __grid_constant__ CUtensorMap map_w, const CmParams p) {
+    constexpr bool DUAL = COUT == 64;
+    constexpr int CPG = COUT / 8;                  // channels per GroupNorm group (8 groups)
+    constexpr int kStages = cm_stages(DUAL);
+    constexpr int kStageBytes = cm_stage_bytes(DUAL);
+    constexpr int kWTileBytes = DUAL ? 64 * 128 : 128 * 128;
+    constexpr int SPT = kRows / H;                 // slices per row tile
+    constexpr int PARTS = EW / 4;                  // epilogue warps per TMEM lane quarter
+    constexpr int MC = DUAL ? 64 : 128;            // output channels per MMA
+    constexpr int XT = DUAL ? 2 : 1;               // row tiles per accumulator
+    static_assert(kRows % H == 0, "a tile holds whole slices");
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* tiles = smem;                                             // kStages x (W | X [| X])
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full = empty_bar + kStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = p.row_tiles * p.m_tiles;
+    const int tile_first = blockIdx.x, tile_step = gridDim.x;
+    const int k_chunks = p.taps * p.k_chunks_per_tap;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EW); }
+        fence_barrier_init();
+        tma_prefetch_desc(&map_x0);
+        tma_prefetch_desc(&map_w);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    // everything above depends on nothing; the previous kernel of the chain must be complete before any global access
+    pdl_wait();
+    pdl_trigger();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+                const int rt = tile / p.m_tiles, mt = tile - rt * p.m_tiles;
+                const int s0 = rt * (SPT * XT);
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    for (int kc = 0; kc < p.k_chunks_per_tap; ++kc) {
+                        mbar_wait_backoff(&empty_bar[stage], phase ^ 1);
+                        uint8_t* w_dst = tiles + stage * kStageBytes;
+                        uint8_t* x_dst = w_dst + kWTileBytes;
+                        mbar_expect_tx(&full_bar[stage], (uint32_t)(kWTileBytes + XT * kXTileBytes));
+                        const int ci = kc * kBlockK;
+                        const bool second = ci >= p.c0;
+                        const CUtensorMap* mx = second ? &map_x1 : &map_x0;
+                        const int xc = second ? ci - p.c0 : ci;
+                        tma_load_2d(&map_w, &full_bar[stage], w_dst, ci, tap * COUT + mt * MC);
+                        tma_load_3d(mx, &full_bar[stage], x_dst, xc, tap - p.taps / 2, s0);
+                        if (DUAL) tma_load_3d(mx, &full_bar[stage], x_dst + kXTileBytes, xc, tap - p.taps / 2, s0 + SPT);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (Fmt<T16>::kind << 7) | (Fmt<T16>::kind << 10) |
+                                       ((uint32_t)(kRows >> 3) << 17) | ((uint32_t)(MC >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+                mbar_wait_backoff(&tmem_empty[acc], acc_phase ^ 1);       // the epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
+                for (int kc = 0; kc < k_chunks; ++kc) {
+                    mbar_wait_backoff(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t w_addr = smem_u32(tiles + stage * kStageBytes);
+                    const uint32_t x_addr = w_addr + kWTileBytes;
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        const uint32_t accumulate = (kc | k) ? 1u : 0u;
+                        tc_mma_f16(d_tmem, umma_smem_desc(w_addr + k * 32), umma_smem_desc(x_addr + k * 32), idesc, accumulate);
+                        if (DUAL)
+                            tc_mma_f16(d_tmem + (16u << 16), umma_smem_desc(w_addr + k * 32),
+                                       umma_smem_desc(x_addr + kXTileBytes + k * 32), idesc, accumulate);
+                    }
+                    tc_commit(&empty_bar[stage]);                         // frees the smem stage
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tmem_full[acc]);                               // accumulator ready for the epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // =============================== epilogue ===============================
+        const int q = warp & 3;                                   // TMEM lane quarter this warp may access
+        const int part = (warp - 2) >> 2;                         // which share of the tile's slices
+        T16* out = reinterpret_cast<T16*>(p.out);
+        const T16* res = reinterpret_cast<const T16*>(p.add_res);
+        const float* addv = p.add_vec;
+        if (addv && p.t_dev) addv += (long long)(*p.t_dev) * COUT;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int cl = DUAL ? q * 16 + (lane & 15) : q * 32 + lane;       // channel inside the M tile
+        const int xt = DUAL ? (lane >> 4) : 0;                            // which row tile of the accumulator this lane holds
+        constexpr float inv_cnt = 1.0f / (float)(H * CPG);
+        constexpr float kLog2e = 1.4426950408889634f;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+            const int rt = tile / p.m_tiles, mt = tile - rt * p.m_tiles;
+            const int c = mt * MC + cl;
+            const float bi = p.bias ? p.bias[c] : 0.f, ga = p.gamma[c], be = p.beta[c], ad = addv ? addv[c] : 0.f;
+            const long long s_first = (long long)rt * (SPT * XT) + xt * SPT;      // first slice of this lane's row tile
+            // raw residual values of slice j of this lane's row tile (slices past the end read slice 0: never stored)
+            constexpr int RH = RES ? H : 1;
+            auto res_load = [&](T16 (&r)[RH], int j) {
+                const long long s = s_first + j;
+                const T16* rp = res + ((s < p.S ? s : 0) * H) * COUT + c;
+#pragma unroll
+                for (int h = 0; h < RH; ++h) r[h] = rp[h * COUT];
+            };
+            T16 ra[RH], rb[RH];
+            if (RES) {
+                // the first slice's residual does not depend on the accumulator: fetch it before the wait, and pull the
+                // NEXT tile's residual block (one contiguous range of rows) into L2 a whole tile ahead of its use
+                res_load(ra, part);
+                const int nt = tile + tile_step;
+                if (nt < num_tiles && (nt % p.m_tiles) == 0) {
+                    const long long row0 = (long long)(nt / p.m_tiles) * (kRows * XT);
+                    const char* base = reinterpret_cast<const char*>(res + row0 * COUT);
+                    const long long left = (p.S * H - row0) * COUT * 2;           // bytes up to the end of the tensor
+                    constexpr int kBlock = kRows * XT * COUT * 2;
+                    for (int b = ((warp - 2) * 32 + lane) * 128; b < kBlock && b < left; b += EW * 32 * 128)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + b));
+                }
+            }
+            mbar_wait_backoff(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = lane_addr + (uint32_t)(acc * kAccStride);
+
+            auto compute = [&](float (&v)[H], T16 (&r16)[RH], int j) {
+                const long long s = s_first + j;
+                const bool valid = s < p.S;
+                T16* op = out + (s * H) * COUT + c;
+                // per-thread sums over the H positions (two chains, combined in a fixed order), conv bias folded in
+                float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+                for (int h = 0; h < H; h += 2) {
+                    a0 += v[h]; b0 = fmaf(v[h], v[h], b0);
+                    a1 += v[h + 1]; b1 = fmaf(v[h + 1], v[h + 1], b1);
+                }
+                const float t1 = a0 + a1, t2 = b0 + b1;
+                float s1 = fmaf((float)H, bi, t1);
+                float s2 = fmaf(bi, fmaf((float)H, bi, 2.0f * t1), t2);   // sum (v + b)^2 = sum v^2 + b (2 sum v + H b)
+                // ... over the CPG adjacent lanes of the channel group: fixed shuffle tree, independent of the slice's place
+#pragma unroll
+                for (int o = 1; o < CPG; o <<= 1) {
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                }
+                const float mean = s1 * inv_cnt;
+                const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, s2 * inv_cnt), 0.f) + 1e-5f);
+                const float sc = rstd * ga;                               // x = (v + b - mean) rstd gamma + beta = v sc + sh
+                const float sh = fmaf(bi - mean, sc, be);
+                const float sc2 = sc * kLog2e, sh2 = sh * kLog2e;
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    // mish(x) = x (1 - 2 / (w (w + 2) + 2)),  w = e^x
+                    const float x = fmaf(v[h], sc, sh);
+                    const float w = ex2_approx(fmaf(v[h], sc2, sh2));
+                    const float r = rcp_approx(fmaf(w, w + 2.0f, 2.0f));
+                    float y = fmaf(x, fmaf(r, -2.0f, 1.0f), ad);
+                    if (RES) y += to_f32<T16>(r16[RES ? h : 0]);
+                    if (valid) op[h * COUT] = from_f32<T16>(y);
+                }
+            };
+
+            // slices part, part + PARTS, ...: the TMEM load (and the residual values) of the next one are in flight while
+            // this one is processed
+            float va[H], vb[H];
+            tmem_ld_slice<H>(taddr + part * H, va);
+            for (int j = part; j < SPT; j += 2 * PARTS) {
+                const int j1 = j + PARTS, j2 = j + 2 * PARTS;
+                tmem_wait_slice<H>(va);
+                if (j1 < SPT) {
+                    tmem_ld_slice<H>(taddr + j1 * H, vb);
+                    if (RES) res_load(rb, j1);
+                }
+                compute(va, ra, j);
+                if (j1 < SPT) {
+                    tmem_wait_slice<H>(vb);
+                    if (j2 < SPT) {
+                        tmem_ld_slice<H>(taddr + j2 * H, va);
+                        if (RES) res_load(ra, j2);
+                    }
+                    compute(vb, rb, j1);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+template <typename T16, int H, int COUT, int EW, bool RES>
+int launch_cm(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap& w, const CmParams& p, cudaStream_t st) {
+    auto kern = conv_tc_cm_kernel<T16, H, COUT, EW, RES>;
+    constexpr size_t smem = cm_smem_bytes(COUT == 64);
+    static DeviceOnce once;
+    if (once.first_time()) CINDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles = p.row_tiles * p.m_tiles;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    CINDM_CHECK_CUDA(launch_chain(kern, dim3(grid), dim3(64 + 32 * EW), smem, st, x0, x1, w, p));
+    CINDM_CHECK_LAUNCH();
+    return 0;
+}
+
+// which channel counts take this kernel: bit 0 -> 128, bit 1 -> 64, bit 2 -> 256 / 512.  CINDM_CONV_CM=<mask> (A/B runs)
+int cm_mask() {
+    static int mask = -1;
+    if (mask < 0) { const char* e = getenv("CINDM_CONV_CM"); mask = e ? atoi(e) : 7; }
+    return mask;
+}
+int cm_epilogue_warps() {
+    static int ew = -1;
+    if (ew < 0) { const char* e = getenv("CINDM_CONV_CM_EW"); const int v = e ? atoi(e) : 16; ew = (v == 8 || v == 12) ? v : 16; }
+    return ew;
+}
+
+template <typename T16, int H, int COUT>
+int dispatch_cm2(bool res, const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap& w, const CmParams& p, cudaStream_t st) {
+    // 16 epilogue warps (4 per SM sub-partition) measured best or equal on every shape except H = 24 with a residual, whose two
+    // raw-residual buffers do not fit the 96 registers of an 18-warp CTA (12 warps there).  CINDM_CONV_CM_EW=8|12 overrides.
+    const int ew = (H == 24 && res && cm_epilogue_warps() == 16) ? 12 : cm_epilogue_warps();
+    if (res) {
+        if (ew == 8) return launch_cm<T16, H, COUT, 8, true>(x0, x1, w, p, st);
+        if (ew == 12) return launch_cm<T16, H, COUT, 12, true>(x0, x1, w, p, st);
+        return launch_cm<T16, H, COUT, 16, true>(x0, x1, w, p, st);
+    }
+    if (ew == 8) return launch_cm<T16, H, COUT, 8, false>(x0, x1, w, p, st);
+    if (ew == 12) return launch_cm<T16, H, COUT, 12, false>(x0, x1, w, p, st);
+    return launch_cm<T16, H, COUT, 16, false>(x0, x1, w, p, st);
+}
+
+template <typename T16>
+int dispatch_cm(int H, int cout, bool res, const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap& w, const CmParams& p,
+                cudaStream_t st) {
+    if (cout == 64 && H == 24) return dispatch_cm2<T16, 24, 64>(res, x0, x1, w, p, st);
+    if (cout == 64 && H == 12) return dispatch_cm2<T16, 12, 64>(res, x0, x1, w, p, st);
+    if (cout == 128 && H == 12) return dispatch_cm2<T16, 12, 128>(res, x0, x1, w, p, st);
+    if (cout == 128 && H == 6) return dispatch_cm2<T16, 6, 128>(res, x0, x1, w, p, st);
+    if (cout == 256 && H == 6) return dispatch_cm2<T16, 6, 256>(res, x0, x1, w, p, st);
+    return fail(-2, "conv_tc_cm: no instance for this (channels, H)");
+}
+
+}  // namespace
+
+bool conv_tc_cm_eligible(const ConvTcLaunch& a) {
+    if (a.epilogue != EPI_GN_MISH || a.mode != TC_SAME || !a.w || a.w->taps != 5) return false;
+    const int cout = a.w->cout, H = a.H, m = cm_mask();
+    if (cout == 128 && (H == 12 || H == 6)) return m & 1;
+    if (cout == 64 && (H == 24 || H == 12)) return m & 2;
+    // (256 channels = two M tiles that both stream the row tile: with a long K loop, cin = 512, the row-major CTA-pair kernel wins)
+    if (cout == 256 && H == 6 && a.w->cin <= 256) return m & 4;
+    return false;
+}
+
+int launch_conv_tc_cm(const ConvTcLaunch& a, cudaStream_t st) {
+    const ConvW& w = *a.w;
+    const bool dual = w.cout == 64;
+    CmParams p;
+    p.bias = w.bias; p.gamma = a.gn->gamma; p.beta = a.gn->beta;
+    p.add_vec = a.add_vec; p.t_dev = a.t_dev; p.add_res = a.add_res; p.out = a.out;
+    p.S = a.S; p.cout = w.cout; p.c0 = a.c0; p.c1 = a.in1 ? a.c1 : 0; p.taps = w.taps;
+    p.k_chunks_per_tap = w.cin / kBlockK;
+    const int spt = kRows / a.H;
+    p.m_tiles = dual ? 1 : w.cout / 128;
+    p.row_tiles = (int)((a.S + spt * (dual ? 2 : 1) - 1) / (spt * (dual ? 2 : 1)));
+    char tag[96];
+    snprintf(tag, sizeof tag, "conv_tc same H%d %d->%d k%d gn%s", a.H, w.cin, w.cout, w.taps, a.add_res ? "+res" : "");
+    KernelTimer kt(tag, st, 2.0 * (double)a.S * (double)(5 * a.H - 6) * w.cin * w.cout);
+    CUtensorMap m0, m1, mw;
+    CINDM_TRY(encode_act_map(&m0, a.in0, a.prec, a.S, a.H, a.c0, spt, a.H, 1));
+    if (a.in1) CINDM_TRY(encode_act_map(&m1, a.in1, a.prec, a.S, a.H, a.c1, spt, a.H, 1));
+    else m1 = m0;
+    CINDM_TRY(encode_weight_map(&mw, w.w16[a.prec], a.prec, w.taps * w.cout, w.cin, dual ? 64 : 128));
+    if (a.prec == PREC_F16) return dispatch_cm<__half>(a.H, w.cout, a.add_res != nullptr, m0, m1, mw, p, st);
+    return dispatch_cm<__nv_bfloat16>(a.H, w.cout, a.add_res != nullptr, m0, m1, mw, p, st);
+}
+
+}  // namespace cindm
