@@ -478,9 +478,12 @@ def run_b200(args, rank, local_rank, world):
         if not os.path.exists(prof_path):
             prof_path = os.path.join(ROOT, "profiles", "r1_evaluation_traffic.json")
         prof = json.load(open(prof_path))
+        tb, tl = 0.0, 0          # (conv_tc_kernel + conv_tc_cm_kernel + conv_tc_cm_halo_kernel = the conv_tc class)
         for name, c in prof["classes"].items():
-            if "conv_tc_kernel" in name:
-                traffic = (c["dram_read_bytes"] + c["dram_write_bytes"]) / c["launches"]
+            if "conv_tc" in name:
+                tb += c["dram_read_bytes"] + c["dram_write_bytes"]; tl += c["launches"]
+        if tl:
+            traffic = tb / tl
     except Exception:
         pass
     if "conv_tc" in classes and classes["conv_tc"]["ms"] > 0:

@@ -184,8 +184,9 @@ __device__ __forceinline__ void cm_epilogue(const CmParams& p, uint32_t tmem_bas
                     const float x = fmaf(v[h], sc, sh);
                     const float w = ex2_approx(fmaf(v[h], sc2, sh2));
                     const float r = rcp_approx(fmaf(w, w + 2.0f, 2.0f));
-                    float y = fmaf(x, fmaf(r, -2.0f, 1.0f), ad);
-                    if (RES) y += to_f32<T16>(r16[RES ? h : 0]);
+                    // (a layer adds either the time-embedding row or a residual, so with RES the residual rides in the FMA)
+                    float y = fmaf(x, fmaf(r, -2.0f, 1.0f), RES ? to_f32<T16>(r16[RES ? h : 0]) : ad);
+                    if (RES && addv != nullptr) y += ad;
                     if (valid) op[h * COUT] = from_f32<T16>(y);
                 }
             };

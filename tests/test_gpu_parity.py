@@ -314,9 +314,10 @@ def test_unet_forward_tcgen05_fp16_vs_golden(diffusion, golden, t):
     assert rel_l2(y, g[f"eps_t{t}"]) < HALF_TOL
 
 
-@pytest.mark.parametrize("S", [1, 41, 1500])
+@pytest.mark.parametrize("S", [1, 41, 1500, 6007])
 def test_unet_forward_tcgen05_many_tiles(diffusion, S):
-    """Partial tiles, and more tiles than SMs at H=24 (persistent tile loop), against the fp32 SIMT path."""
+    """Partial tiles, and more tiles than SMs (persistent tile loops: 6007 slices = 334 / 301 / 151 row tiles of the
+    channel-major GroupNorm convs at H = 24 / 12 / 6, the last one ragged), against the fp32 SIMT path."""
     gen = torch.Generator().manual_seed(S)
     x = torch.randn(S, 24, 8, generator=gen)
     t = torch.full((S,), 420, dtype=torch.long)
@@ -329,6 +330,43 @@ def test_unet_forward_tcgen05_many_tiles(diffusion, S):
     per_slice = ((y - ref).flatten(1).norm(dim=1) / ref.flatten(1).norm(dim=1)).max().item()
     assert per_slice < 3 * HALF_TOL
 
+
+
+_VARIANT_SCRIPT = """
+import sys, numpy as np, torch
+from cindm_b200.model.diffusion_1d import GaussianDiffusion1D, TemporalUnet1D
+from cindm_b200.model.params import init_unet_params
+model = TemporalUnet1D(horizon=24, transition_dim=8, cond_dim=False, dim=64, dim_mults=(1, 2, 4, 8), attention=True)
+dif = GaussianDiffusion1D(model, image_size=24, conditioned_steps=0, timesteps=1000, sampling_timesteps=1000)
+model.load_state_dict(init_unet_params(seed=0, randomize_affine=True))
+dif.to("cuda:0")
+x = torch.randn(333, 24, 8, generator=torch.Generator().manual_seed(5))
+t = torch.full((333,), 420, dtype=torch.long)
+out = {}
+for prec, eng in (("fp32", "simt"), ("fp16", "tcgen05"), ("bf16", "tcgen05")):
+    dif.precision, dif.conv_engine = prec, eng
+    model.precision, model.conv_engine = prec, eng
+    out[prec] = model(x, t, None).float().cpu().numpy()
+np.savez(sys.argv[1], **out)
+"""
+
+
+@pytest.mark.parametrize("env", [{"CINDM_CONV_CM": "0"}, {"CINDM_CONV_CM_HALO": "0"}, {"CINDM_CONV_CM_HALO": "1"},
+                                 {"CINDM_CONV_CM_EW": "12"}, {"CINDM_CONV_CM": "3"}])
+def test_conv_tc_kernel_variants_meet_the_same_bar(tmp_path, env):
+    """Every dispatch switch of the GroupNorm convs (row-major kernel only; channel-major without / with halo loads everywhere;
+    12 epilogue warps; 256-channel layers on the row-major kernel) is held to the bar of the shipped configuration.  The
+    switches are read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    out = tmp_path / "variant.npz"
+    e = dict(os.environ, **env)
+    e["PYTHONPATH"] = os.path.dirname(HERE) + os.pathsep + e.get("PYTHONPATH", "")
+    r = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT, str(out)], env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = np.load(out)
+    assert rel_l2(got["fp16"], got["fp32"]) < HALF_TOL
+    assert rel_l2(got["bf16"], got["fp32"]) < 5e-2
 
 @pytest.mark.parametrize("case", sorted(META["compose_cases"]))
 def test_composed_eps_tcgen05_fp16(diffusion, golden, case):
