@@ -1,6 +1,7 @@
 // SIMT (fp32 FMA) kernels of the temporal U-Net: the parity-grade path, plus the small
 // per-slice operators (GroupNorm+Mish, channel LayerNorm, linear attention core) that both
 // precisions share.  Activations are channels-last: [S][H][C].
+#include <cstdlib>
 #include <type_traits>
 
 #include "engine.h"
@@ -120,8 +121,148 @@ __global__ void __launch_bounds__(256) conv1d_simt_kernel(ConvParams p) {
     }
 }
 
+// The same GEMM with a 128 x BN tile (BN = 64 / 128 output channels), 8 x BN/16 accumulators per thread, double-buffered
+// shared memory and register prefetch of the next K chunk (one __syncthreads per chunk): the C4-sized fp32 path.  Every
+// accumulator still sums its products in (tap, ci) order, so results are bit-identical to conv1d_simt_kernel's.
+template <typename InT, typename OutT, int BN>
+__global__ void __launch_bounds__(256, 2) conv1d_simt128_kernel(ConvParams p) {
+    constexpr int BM = 128, BK = 16, TN = BN / 16, AS = BM + 4;
+    __shared__ __align__(16) float As[2][BK][AS];
+    __shared__ __align__(16) float Bs[2][BK][BN];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const long long row0 = (long long)blockIdx.x * BM;
+    const int co0 = blockIdx.y * BN;
+
+    // A-load role: 8 consecutive input channels of one row;  B-load role: TN consecutive output channels of one input channel
+    const int a_row = tid >> 1, a_ci = (tid & 1) * 8;
+    const long long arow = row0 + a_row;
+    const bool arow_ok = arow < p.rows;
+    const long long a_s = arow_ok ? arow / p.Hout : 0;
+    const int a_j = arow_ok ? (int)(arow - a_s * p.Hout) : 0;
+    const int b_ci = tid >> 4, b_co = (tid & 15) * TN;
+
+    const int cpt = (p.cin + BK - 1) / BK;               // K chunks per tap
+    const int nchunks = p.taps * cpt;
+    float av[8], bv[TN];
+
+    auto fetch = [&](int chunk) {                        // global -> registers
+        const int tap = chunk / cpt, ci0 = (chunk - tap * cpt) * BK;
+        int pos;
+        bool pos_ok;
+        if (!p.transposed) {
+            pos = a_j * p.stride + tap - p.pad;
+            pos_ok = pos >= 0 && pos < p.Hin;
+        } else {
+            const int q = a_j + p.pad - tap;
+            pos_ok = q >= 0 && (q % p.stride) == 0;
+            pos = q / p.stride;
+            pos_ok = pos_ok && pos < p.Hin;
+        }
+        pos_ok = pos_ok && arow_ok;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) av[q] = 0.f;
+        const int ci = ci0 + a_ci;
+        if (pos_ok && ci < p.cin) {
+            const InT* src;
+            int cw, cbase;
+            if (ci < p.c0) { src = (const InT*)p.in0; cw = p.c0; cbase = ci; }
+            else           { src = (const InT*)p.in1; cw = p.c1; cbase = ci - p.c0; }
+            const InT* ptr = src + ((a_s * p.Hin + pos) * (long long)cw + cbase);
+            if (std::is_same<InT, float>::value && ci + 8 <= p.cin && (cw & 3) == 0) {
+                const float4 u0 = reinterpret_cast<const float4*>(ptr)[0], u1 = reinterpret_cast<const float4*>(ptr)[1];
+                av[0] = u0.x; av[1] = u0.y; av[2] = u0.z; av[3] = u0.w; av[4] = u1.x; av[5] = u1.y; av[6] = u1.z; av[7] = u1.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (ci + q < p.cin) av[q] = to_f32<InT>(ptr[q]);
+            }
+        }
+        const int bci = ci0 + b_ci;
+#pragma unroll
+        for (int q = 0; q < TN; ++q) bv[q] = 0.f;
+        if (bci < p.cin) {
+            const float4* wp = reinterpret_cast<const float4*>(p.w + ((long long)tap * p.cin + bci) * p.cout + co0 + b_co);
+#pragma unroll
+            for (int q = 0; q < TN / 4; ++q) {
+                const float4 u = wp[q];
+                bv[4 * q] = u.x; bv[4 * q + 1] = u.y; bv[4 * q + 2] = u.z; bv[4 * q + 3] = u.w;
+            }
+        }
+    };
+    auto stash = [&](int buf) {                          // registers -> shared memory
+#pragma unroll
+        for (int q = 0; q < 8; ++q) As[buf][a_ci + q][a_row] = av[q];
+#pragma unroll
+        for (int q = 0; q < TN / 4; ++q)
+            *reinterpret_cast<float4*>(&Bs[buf][b_ci][b_co + 4 * q]) = make_float4(bv[4 * q], bv[4 * q + 1], bv[4 * q + 2], bv[4 * q + 3]);
+    };
+
+    float acc[8][TN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int buf = chunk & 1;
+        if (chunk + 1 < nchunks) fetch(chunk + 1);       // in flight during the FMAs below
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[8], b[TN];
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8 + 4]);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            // a thread's output columns are tx*4 .. +3 of every 64-column half: 16 lanes x 16 B contiguous, conflict-free
+#pragma unroll
+            for (int q = 0; q < TN / 4; ++q) {
+                const float4 u = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 * q + tx * 4]);
+                b[4 * q] = u.x; b[4 * q + 1] = u.y; b[4 * q + 2] = u.z; b[4 * q + 3] = u.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (chunk + 1 < nchunks) stash(buf ^ 1);          // (the other buffer was last read before the previous barrier)
+        __syncthreads();
+    }
+    // ---- epilogue ----
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long r = row0 + ty * 8 + i;
+        if (r >= p.rows) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int co = co0 + 64 * (j >> 2) + tx * 4 + (j & 3);
+            float v = acc[i][j];
+            if (p.bias) v += p.bias[co];
+            if (p.res) v += to_f32<OutT>(((const OutT*)p.res)[r * p.cout + co]);
+            ((OutT*)p.out)[r * p.cout + co] = from_f32<OutT>(v);
+        }
+    }
+}
+
 template <typename InT, typename OutT>
 static int conv_dispatch2(const ConvParams& p, cudaStream_t st) {
+    // the 128-row tile kernel (cout a multiple of 64) for everything but tiny problems; CINDM_SIMT_TILE128=0 keeps the 64 x 64
+    // kernel everywhere (A/B runs; the two are bit-identical)
+    static int tile128 = -1;
+    if (tile128 < 0) { const char* e = getenv("CINDM_SIMT_TILE128"); tile128 = (e && e[0] == '0') ? 0 : 1; }
+    if (tile128 && p.rows >= 512 && p.cout % 64 == 0) {
+        if (p.cout % 128 == 0) {
+            dim3 grid(ceil_div(p.rows, 128), p.cout / 128);
+            conv1d_simt128_kernel<InT, OutT, 128><<<grid, 256, 0, st>>>(p);
+        } else {
+            dim3 grid(ceil_div(p.rows, 128), p.cout / 64);
+            conv1d_simt128_kernel<InT, OutT, 64><<<grid, 256, 0, st>>>(p);
+        }
+        CINDM_CHECK_LAUNCH();
+        return 0;
+    }
     dim3 grid(ceil_div(p.rows, 64), ceil_div(p.cout, 64));
     conv1d_simt_kernel<InT, OutT><<<grid, 256, 0, st>>>(p);
     CINDM_CHECK_LAUNCH();

@@ -368,6 +368,21 @@ def test_conv_tc_kernel_variants_meet_the_same_bar(tmp_path, env):
     assert rel_l2(got["fp16"], got["fp32"]) < HALF_TOL
     assert rel_l2(got["bf16"], got["fp32"]) < 5e-2
 
+
+def test_simt_conv_tile_variants_are_bit_identical(tmp_path):
+    """fp32 path: the 128-row double-buffered conv kernel sums every output in the same (tap, ci) order as the 64 x 64 one."""
+    import subprocess
+    import sys
+    outs = []
+    for flag in ("1", "0"):
+        out = tmp_path / f"simt{flag}.npz"
+        e = dict(os.environ, CINDM_SIMT_TILE128=flag)
+        e["PYTHONPATH"] = os.path.dirname(HERE) + os.pathsep + e.get("PYTHONPATH", "")
+        r = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT, str(out)], env=e, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(np.load(out)["fp32"])
+    assert np.isfinite(outs[0]).all() and np.array_equal(outs[0], outs[1])
+
 @pytest.mark.parametrize("case", sorted(META["compose_cases"]))
 def test_composed_eps_tcgen05_fp16(diffusion, golden, case):
     set_precision(diffusion, "fp16", "tcgen05")
