@@ -121,9 +121,27 @@ __global__ void __launch_bounds__(256) conv1d_simt_kernel(ConvParams p) {
     }
 }
 
+// Packed fp32 FMA (sm_100: fma.rn.f32x2 -> FFMA2): two IEEE fp32 FMAs on a 64-bit register pair per instruction.  Measured on B200
+// (profiles/micro/ffma2_throughput.cu): the same 126 lane-FMA/clk/SM as scalar FFMA at HALF the instruction rate, i.e. it frees
+// every second issue slot of an FMA-bound loop for the shared-memory loads.
+__device__ __forceinline__ unsigned long long f32x2_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f32x2_unpack(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 // The same GEMM with a 128 x BN tile (BN = 64 / 128 output channels), 8 x BN/16 accumulators per thread, double-buffered
 // shared memory and register prefetch of the next K chunk (one __syncthreads per chunk): the C4-sized fp32 path.  Every
-// accumulator still sums its products in (tap, ci) order, so results are bit-identical to conv1d_simt_kernel's.
+// accumulator still sums its products in (tap, ci) order with IEEE fp32 FMAs (packed two rows at a time: FFMA2), so results are
+// bit-identical to conv1d_simt_kernel's.
 template <typename InT, typename OutT, int BN>
 __global__ void __launch_bounds__(256, 2) conv1d_simt128_kernel(ConvParams p) {
     constexpr int BM = 128, BK = 16, TN = BN / 16, AS = BM + 4;
@@ -198,11 +216,12 @@ __global__ void __launch_bounds__(256, 2) conv1d_simt128_kernel(ConvParams p) {
             *reinterpret_cast<float4*>(&Bs[buf][b_ci][b_co + 4 * q]) = make_float4(bv[4 * q], bv[4 * q + 1], bv[4 * q + 2], bv[4 * q + 3]);
     };
 
-    float acc[8][TN];
+    // accumulators as pairs of ROWS (i, i + 1) of one column: the a pair comes straight out of the 16-byte fragment load
+    unsigned long long acc2[4][TN];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < TN; ++j) acc2[i][j] = 0ull;
 
     fetch(0);
     stash(0);
@@ -212,10 +231,10 @@ __global__ void __launch_bounds__(256, 2) conv1d_simt128_kernel(ConvParams p) {
         if (chunk + 1 < nchunks) fetch(chunk + 1);       // in flight during the FMAs below
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
-            float a[8], b[TN];
+            float b[TN];
             const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8]);
             const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8 + 4]);
-            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            const unsigned long long a2[4] = {f32x2_pack(a0.x, a0.y), f32x2_pack(a0.z, a0.w), f32x2_pack(a1.x, a1.y), f32x2_pack(a1.z, a1.w)};
             // a thread's output columns are tx*4 .. +3 of every 64-column half: 16 lanes x 16 B contiguous, conflict-free
 #pragma unroll
             for (int q = 0; q < TN / 4; ++q) {
@@ -223,14 +242,21 @@ __global__ void __launch_bounds__(256, 2) conv1d_simt128_kernel(ConvParams p) {
                 b[4 * q] = u.x; b[4 * q + 1] = u.y; b[4 * q + 2] = u.z; b[4 * q + 3] = u.w;
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int j = 0; j < TN; ++j) {
+                const unsigned long long bb = f32x2_pack(b[j], b[j]);
 #pragma unroll
-                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int i = 0; i < 4; ++i) acc2[i][j] = f32x2_fma(a2[i], bb, acc2[i][j]);
+            }
         }
         if (chunk + 1 < nchunks) stash(buf ^ 1);          // (the other buffer was last read before the previous barrier)
         __syncthreads();
     }
     // ---- epilogue ----
+    float acc[8][TN];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) f32x2_unpack(acc2[i][j], acc[2 * i][j], acc[2 * i + 1][j]);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const long long r = row0 + ty * 8 + i;
