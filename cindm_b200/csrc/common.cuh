@@ -117,6 +117,28 @@ __device__ __forceinline__ float mish_fast(float x) {
     return fmaf(x * r, -2.0f, x);
 }
 
+// Packed fp32 FMA (sm_100: fma.rn.f32x2 -> FFMA2): two IEEE fp32 FMAs on a 64-bit register pair per instruction.  Measured on B200
+// (profiles/micro/ffma2_throughput.cu): the same 126 lane-FMA/clk/SM as scalar FFMA at HALF the instruction rate, i.e. it frees
+// every second issue slot of an FMA-bound loop for the shared-memory loads.
+__device__ __forceinline__ unsigned long long f32x2_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f32x2_unpack(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long f32x2_add(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

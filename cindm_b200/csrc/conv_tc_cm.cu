@@ -157,13 +157,33 @@ __device__ __forceinline__ void cm_epilogue(const CmParams& p, uint32_t tmem_bas
                 const long long s = s_first + j;
                 const bool valid = s < p.S;
                 T16* op = out + (s * H) * COUT + c;
-                // per-thread sums over the H positions (two chains, combined in a fixed order), conv bias folded in
-                float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+                // Packed fp32 (add.f32x2 / fma.f32x2 = two IEEE operations per instruction at half the issue rate, the same
+                // arithmetic throughput): the statistics, x and the ex2 argument of two adjacent positions take one instruction
+                // each (their inputs sit in adjacent registers straight out of tcgen05.ld); everything downstream of the scalar
+                // MUFU results stays scalar (re-packing them costs the moves it would save).  Same operations in the same order
+                // as the scalar form, which H = 24 with a residual keeps (two more live register pairs would spill there).
+                constexpr bool PACKED = !(H == 24 && RES);
+                float a0, a1, b0, b1;
+                unsigned long long v2[PACKED ? H / 2 : 1];
+                if (PACKED) {
+                    unsigned long long a2 = 0ull, b2 = 0ull;
 #pragma unroll
-                for (int h = 0; h < H; h += 2) {
-                    a0 += v[h]; b0 = fmaf(v[h], v[h], b0);
-                    a1 += v[h + 1]; b1 = fmaf(v[h + 1], v[h + 1], b1);
+                    for (int h = 0; h < H; h += 2) {
+                        v2[PACKED ? h >> 1 : 0] = f32x2_pack(v[h], v[h + 1]);
+                        a2 = f32x2_add(a2, v2[PACKED ? h >> 1 : 0]);
+                        b2 = f32x2_fma(v2[PACKED ? h >> 1 : 0], v2[PACKED ? h >> 1 : 0], b2);
+                    }
+                    f32x2_unpack(a2, a0, a1);
+                    f32x2_unpack(b2, b0, b1);
+                } else {
+                    a0 = a1 = b0 = b1 = 0.f;
+#pragma unroll
+                    for (int h = 0; h < H; h += 2) {
+                        a0 += v[h]; b0 = fmaf(v[h], v[h], b0);
+                        a1 += v[h + 1]; b1 = fmaf(v[h + 1], v[h + 1], b1);
+                    }
                 }
+                // per-thread sums (even / odd positions, combined in a fixed order), conv bias folded in
                 const float t1 = a0 + a1, t2 = b0 + b1;
                 float s1 = fmaf((float)H, bi, t1);
                 float s2 = fmaf(bi, fmaf((float)H, bi, 2.0f * t1), t2);   // sum (v + b)^2 = sum v^2 + b (2 sum v + H b)
@@ -177,17 +197,28 @@ __device__ __forceinline__ void cm_epilogue(const CmParams& p, uint32_t tmem_bas
                 const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, s2 * inv_cnt), 0.f) + 1e-5f);
                 const float sc = rstd * ga;                               // x = (v + b - mean) rstd gamma + beta = v sc + sh
                 const float sh = fmaf(bi - mean, sc, be);
-                const float sc2 = sc * kLog2e, sh2 = sh * kLog2e;
+                const float scl = sc * kLog2e, shl = sh * kLog2e;
+                const unsigned long long sc_2 = f32x2_pack(sc, sc), sh_2 = f32x2_pack(sh, sh);
+                const unsigned long long scl_2 = f32x2_pack(scl, scl), shl_2 = f32x2_pack(shl, shl);
 #pragma unroll
-                for (int h = 0; h < H; ++h) {
+                for (int h = 0; h < H; h += 2) {
                     // mish(x) = x (1 - 2 / (w (w + 2) + 2)),  w = e^x
-                    const float x = fmaf(v[h], sc, sh);
-                    const float w = ex2_approx(fmaf(v[h], sc2, sh2));
-                    const float r = rcp_approx(fmaf(w, w + 2.0f, 2.0f));
-                    // (a layer adds either the time-embedding row or a residual, so with RES the residual rides in the FMA)
-                    float y = fmaf(x, fmaf(r, -2.0f, 1.0f), RES ? to_f32<T16>(r16[RES ? h : 0]) : ad);
-                    if (RES && addv != nullptr) y += ad;
-                    if (valid) op[h * COUT] = from_f32<T16>(y);
+                    float xx[2], tt[2];
+                    if (PACKED) {
+                        f32x2_unpack(f32x2_fma(v2[PACKED ? h >> 1 : 0], sc_2, sh_2), xx[0], xx[1]);
+                        f32x2_unpack(f32x2_fma(v2[PACKED ? h >> 1 : 0], scl_2, shl_2), tt[0], tt[1]);
+                    } else {
+                        xx[0] = fmaf(v[h], sc, sh); xx[1] = fmaf(v[h + 1], sc, sh);
+                        tt[0] = fmaf(v[h], scl, shl); tt[1] = fmaf(v[h + 1], scl, shl);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const float w = ex2_approx(tt[u]);
+                        const float r = rcp_approx(fmaf(w, w + 2.0f, 2.0f));
+                        // (a layer adds either the time-embedding row or a residual, so with RES the residual rides in the FMA)
+                        const float y = fmaf(xx[u], fmaf(r, -2.0f, 1.0f), RES ? to_f32<T16>(r16[RES ? h + u : 0]) : ad);
+                        if (valid) op[(h + u) * COUT] = from_f32<T16>(y);
+                    }
                 }
             };
 
@@ -559,6 +590,7 @@ int dispatch_cm(int H, int cout, bool res, bool halo, const CUtensorMap& x0, con
 
 bool conv_tc_cm_eligible(const ConvTcLaunch& a) {
     if (a.epilogue != EPI_GN_MISH || a.mode != TC_SAME || !a.w || a.w->taps != 5) return false;
+    if (a.add_res && a.add_vec) return false;      // (no layer of the U-Net adds both; the row-major kernel handles it)
     const int cout = a.w->cout, H = a.H, m = cm_mask();
     if (cout == 128 && (H == 12 || H == 6)) return m & 1;
     if (cout == 64 && (H == 24 || H == 12)) return m & 2;

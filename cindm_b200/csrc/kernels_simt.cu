@@ -121,23 +121,6 @@ __global__ void __launch_bounds__(256) conv1d_simt_kernel(ConvParams p) {
     }
 }
 
-// Packed fp32 FMA (sm_100: fma.rn.f32x2 -> FFMA2): two IEEE fp32 FMAs on a 64-bit register pair per instruction.  Measured on B200
-// (profiles/micro/ffma2_throughput.cu): the same 126 lane-FMA/clk/SM as scalar FFMA at HALF the instruction rate, i.e. it frees
-// every second issue slot of an FMA-bound loop for the shared-memory loads.
-__device__ __forceinline__ unsigned long long f32x2_pack(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void f32x2_unpack(unsigned long long v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-
 // The same GEMM with a 128 x BN tile (BN = 64 / 128 output channels), 8 x BN/16 accumulators per thread, double-buffered
 // shared memory and register prefetch of the next K chunk (one __syncthreads per chunk): the C4-sized fp32 path.  Every
 // accumulator still sums its products in (tap, ci) order with IEEE fp32 FMAs (packed two rows at a time: FFMA2), so results are
