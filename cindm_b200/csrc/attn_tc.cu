@@ -33,6 +33,7 @@ struct AttnTcParams {
     long long S;
     int H, C;
     int slices_per_tile, rows_used, m_tiles, k_chunks;
+    int reverse;              // walk the M tiles from the last one down (see ConvTcLaunch::reverse)
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
@@ -94,7 +95,8 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             const uint32_t tx_bytes = (uint32_t)(p.rows_used * 128 + 128 * 128);
-            for (int m_tile = blockIdx.x; m_tile < p.m_tiles; m_tile += gridDim.x) {
+            for (int it = blockIdx.x; it < p.m_tiles; it += gridDim.x) {
+                const int m_tile = p.reverse ? p.m_tiles - 1 - it : it;
                 const int s0 = m_tile * p.slices_per_tile;
                 for (int pass = 0; pass < 3; ++pass) {
                     for (int kc = 0; kc < p.k_chunks; ++kc) {
@@ -167,8 +169,8 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         uint4 pre[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
         T16 pre_x0 = (T16)0.f;
         auto prefetch_row = [&](int mt) {
-            if (mt >= p.m_tiles) return;
-            const long long ps0 = (long long)mt * p.slices_per_tile;
+            if (mt >= p.m_tiles) return;                    // (mt = position in the walk)
+            const long long ps0 = (long long)(p.reverse ? p.m_tiles - 1 - mt : mt) * p.slices_per_tile;
             if (row < p.rows_used && (ps0 + row / n) < p.S) {
                 const uint4* xp = reinterpret_cast<const uint4*>(xin + (ps0 * n + row) * (long long)C + cp * (C >> 2));
                 pre[0] = xp[0]; pre[1] = xp[1];
@@ -176,7 +178,8 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
         };
         prefetch_row(blockIdx.x);
-        for (int m_tile = blockIdx.x; m_tile < p.m_tiles; m_tile += gridDim.x) {
+        for (int it = blockIdx.x; it < p.m_tiles; it += gridDim.x) {
+            const int m_tile = p.reverse ? p.m_tiles - 1 - it : it;
             const long long s0 = (long long)m_tile * p.slices_per_tile;
             const bool valid = row < p.rows_used && (s0 + row / n) < p.S;
             // ---- LayerNorm statistics of this thread's row (a quarter of the channels each; shifted sums, fixed order) ----
@@ -241,7 +244,7 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            prefetch_row(m_tile + gridDim.x);
+            prefetch_row(it + gridDim.x);
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");             // the whole q|k|v tile is in shared memory
             // ---- attention core: one (slice, head) task per warp ----
             const long long left = p.S - s0;
@@ -357,13 +360,13 @@ int launch_instance(const CUtensorMap& ma, const CUtensorMap& mb, const AttnTcPa
 
 }  // namespace
 
-int launch_qkv_attn_tc(const AttnW& a, const void* x, void* out, int64_t S, int H, int C, int prec, cudaStream_t st) {
+int launch_qkv_attn_tc(const AttnW& a, const void* x, void* out, int64_t S, int H, int C, int prec, cudaStream_t st, int reverse) {
     if (prec != PREC_F16 && prec != PREC_BF16) return fail(-2, "attn_tc: 16-bit precisions only");
     if (C % 64 || C > 512 || (H != 3 && H != 6 && H != 12 && H != 24)) return fail(-2, "attn_tc: unsupported block shape");
     if (!a.wln16[prec] || !a.wsum[prec]) return fail(-4, "attn_tc: folded LayerNorm operand missing");
     if (S == 0) return 0;
     AttnTcParams p;
-    p.x = x; p.wsum = a.wsum[prec]; p.out = out; p.S = S; p.H = H; p.C = C;
+    p.x = x; p.wsum = a.wsum[prec]; p.out = out; p.S = S; p.H = H; p.C = C; p.reverse = reverse;
     // whole slices per 128-row tile; at H <= 6 a multiple of 4, so that the (slice, head) tasks split evenly over the
     // 16 warps (at H = 12 / 24 the extra tiles that would take cost more than the last, partly filled round of tasks)
     p.slices_per_tile = H <= 6 ? (128 / H) / 4 * 4 : 128 / H;

@@ -56,6 +56,7 @@ struct TcParams {
     int out_mul, out_add;     // output row = tile row * out_mul + out_add (2, parity for the transposed conv)
     int tma_out;              // stage the output tile in shared memory and write it with TMA (N_TILE <= 128 kernels)
     int slices_per_tile, rows_used, m_tiles, n_tiles, k_chunks_per_tap;
+    int reverse;              // walk the (pair-)tiles from the last one down (see ConvTcLaunch::reverse)
 };
 
 // ------------------------------------------------------------------ the kernel
@@ -100,6 +101,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int num_tiles = ((p.m_tiles + CG - 1) / CG) * n_tiles;
     const int tile_first = blockIdx.x / CG, tile_step = gridDim.x / CG;
     const int k_chunks = p.taps * p.k_chunks_per_tap;
+    auto vtile = [&](int t) { return p.reverse ? num_tiles - 1 - t : t; };      // position in the walk -> tile
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -133,7 +135,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
-                const int m_pair = tile / n_tiles, n_tile = tile - m_pair * n_tiles;
+                const int vt = vtile(tile);
+                const int m_pair = vt / n_tiles, n_tile = vt - m_pair * n_tiles;
                 const int m_tile = m_pair * CG + (int)cta_rank;
                 const int s0 = m_tile * p.slices_per_tile;
                 const uint32_t tx_bytes = (uint32_t)(p.rows_used * 128 + kBTileBytes) * CG;   // leader counts both CTAs' bytes
@@ -256,8 +259,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
         {   // both accumulators start out holding the bias of the first two tiles of this CTA
             const int t0 = tile_first, t1 = tile_first + tile_step;
-            if (t0 < num_tiles) init_accumulator(0, t0 % n_tiles);
-            if (t1 < num_tiles) init_accumulator(1, t1 % n_tiles);
+            if (t0 < num_tiles) init_accumulator(0, vtile(t0) % n_tiles);
+            if (t1 < num_tiles) init_accumulator(1, vtile(t1) % n_tiles);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -267,7 +270,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
-            const int m_pair = tile / n_tiles, n_tile = tile - m_pair * n_tiles;
+            const int vt = vtile(tile);
+            const int m_pair = vt / n_tiles, n_tile = vt - m_pair * n_tiles;
             const int m_tile = m_pair * CG + (int)cta_rank;
             const long long s0 = (long long)m_tile * p.slices_per_tile;
             const int n0 = n_tile * N_TILE;
@@ -292,7 +296,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             if (res != nullptr) {
                 const int nt_tile = tile + tile_step;
                 if (nt_tile < num_tiles) {
-                    const int nm_pair = nt_tile / n_tiles, nn_tile = nt_tile - nm_pair * n_tiles;
+                    const int nvt = vtile(nt_tile);
+                    const int nm_pair = nvt / n_tiles, nn_tile = nvt - nm_pair * n_tiles;
                     const long long ns0 = (long long)(nm_pair * CG + (int)cta_rank) * p.slices_per_tile;
                     const long long ngrow = ns0 * p.H + row;
                     const bool nvalid = T3 ? (ns0 + row) < p.S : (row < p.rows_used && (ns0 + sl) < p.S);
@@ -466,7 +471,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             // ---- hand the accumulator back, pre-loaded with the bias of the tile that will use it next ----
             {
                 const int nxt = tile + 2 * tile_step;
-                if (nxt < num_tiles) init_accumulator(acc, nxt % n_tiles);
+                if (nxt < num_tiles) init_accumulator(acc, vtile(nxt) % n_tiles);
             }
             tc_fence_before();
             __syncwarp();
@@ -609,7 +614,7 @@ static int launch_conv_tc_one(const ConvTcLaunch& a, int parity, cudaStream_t st
     p.beta = a.gn ? a.gn->beta : nullptr;
     p.add_vec = a.add_vec; p.t_dev = a.t_dev; p.add_res = a.add_res; p.out = a.out;
     p.S = a.S; p.cout = w.cout; p.c0 = a.c0; p.c1 = a.in1 ? a.c1 : 0; p.cin = w.cin; p.kpp = w.cin / kBlockK;
-    p.out_mul = 1; p.out_add = 0;
+    p.out_mul = 1; p.out_add = 0; p.reverse = a.reverse;
     if (a.epilogue == EPI_GN_MISH_T3) {
         // one dense GEMM: rows = slices, K = 3*cin, N = 3*cout in (group, position, channel) order
         p.H = 1; p.taps = 1; p.tap_hoff[0] = 0; p.tap_wrow[0] = 0;

@@ -26,6 +26,9 @@ struct ConvTcLaunch {
     int mode = TC_SAME;
     int prec = PREC_F16;
     int epilogue = EPI_BIAS;
+    // walk the tiles from the last one down: consecutive layers alternate, so that a layer starts on the part of its input the
+    // previous layer wrote LAST (still in L2) instead of the part written first (long evicted: a tensor is 132 MB, L2 126 MB)
+    int reverse = 0;
     // small batches: the two parity GEMMs of a transposed conv are independent; when `side` is set the odd outputs are
     // computed on it (event fork / join around it, graph-capturable)
     cudaStream_t side = nullptr;

@@ -43,6 +43,7 @@ struct CmParams {
     int m_tiles;              // cout / 128 (1 when DUAL)
     int row_tiles;            // ceil(S / slices per tile)  (DUAL: pairs of row tiles)
     int base_off_mode;        // halo kernel: fill the descriptors' matrix-base-offset field (A/B probe)
+    int reverse;              // walk the tiles from the last one down (see ConvTcLaunch::reverse)
 };
 
 constexpr int cm_stages(bool dual) { return dual ? 3 : 4; }
@@ -122,7 +123,8 @@ __device__ __forceinline__ void cm_epilogue(const CmParams& p, uint32_t tmem_bas
         constexpr float kLog2e = 1.4426950408889634f;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
-            const int rt = tile / p.m_tiles, mt = tile - rt * p.m_tiles;
+            const int vt = p.reverse ? num_tiles - 1 - tile : tile;
+            const int rt = vt / p.m_tiles, mt = vt - rt * p.m_tiles;
             const int c = mt * MC + cl;
             const float bi = p.bias ? p.bias[c] : 0.f, ga = p.gamma[c], be = p.beta[c], ad = addv ? addv[c] : 0.f;
             const long long s_first = (long long)rt * (SPT * XT) + xt * SPT;      // first slice of this lane's row tile
@@ -140,8 +142,9 @@ __device__ __forceinline__ void cm_epilogue(const CmParams& p, uint32_t tmem_bas
                 // NEXT tile's residual block (one contiguous range of rows) into L2 a whole tile ahead of its use
                 res_load(ra, part);
                 const int nt = tile + tile_step;
-                if (nt < num_tiles && (nt % p.m_tiles) == 0) {
-                    const long long row0 = (long long)(nt / p.m_tiles) * (SPT * H * XT);
+                const int nvt = p.reverse ? num_tiles - 1 - nt : nt;
+                if (nt < num_tiles && (nvt % p.m_tiles) == 0) {
+                    const long long row0 = (long long)(nvt / p.m_tiles) * (SPT * H * XT);
                     const char* base = reinterpret_cast<const char*>(res + row0 * COUT);
                     const long long left = (p.S * H - row0) * COUT * 2;           // bytes up to the end of the tensor
                     constexpr int kBlock = SPT * H * XT * COUT * 2;
@@ -303,7 +306,8 @@ conv_tc_cm_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_const
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
-                const int rt = tile / p.m_tiles, mt = tile - rt * p.m_tiles;
+                const int vt = p.reverse ? num_tiles - 1 - tile : tile;
+                const int rt = vt / p.m_tiles, mt = vt - rt * p.m_tiles;
                 const int s0 = rt * (SPT * XT);
                 for (int tap = 0; tap < p.taps; ++tap) {
                     for (int kc = 0; kc < p.k_chunks_per_tap; ++kc) {
@@ -441,7 +445,8 @@ conv_tc_cm_halo_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_
         if (lane == 0) {
             int xs = 0, ws = 0; uint32_t xph = 0, wph = 0;
             for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
-                const int rt = tile / p.m_tiles, mt = tile - rt * p.m_tiles;
+                const int vt = p.reverse ? num_tiles - 1 - tile : tile;
+                const int rt = vt / p.m_tiles, mt = vt - rt * p.m_tiles;
                 const int s0 = rt * (SPT * XT);
                 for (int kc = 0; kc < p.k_chunks_per_tap; ++kc) {
                     const int ci = kc * kBlockK;
@@ -611,6 +616,7 @@ int launch_conv_tc_cm(const ConvTcLaunch& a, cudaStream_t st) {
     const bool halo = (a.H == 24 || a.H == 12) && hm != 0 && (hm != 3 || (w.cout == 64 && a.add_res));
     const int spt = halo ? (a.H == 24 ? HaloGeom<24>::SPT : HaloGeom<12>::SPT) : kRows / a.H;
     p.base_off_mode = hm == 2 ? 1 : 0;
+    p.reverse = a.reverse;
     p.m_tiles = dual ? 1 : w.cout / 128;
     p.row_tiles = (int)((a.S + spt * (dual ? 2 : 1) - 1) / (spt * (dual ? 2 : 1)));
     char tag[96];

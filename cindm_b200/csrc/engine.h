@@ -163,7 +163,7 @@ int launch_gn_mish(const float* in, const NormW& gn, const float* add_vec, const
 int launch_layernorm(const void* in, const float* g, void* out, int64_t rows, int C, int prec, cudaStream_t st);
 int launch_attn_core(const void* qkv, void* out, int64_t S, int n, int prec, cudaStream_t st);
 // LayerNorm + to_qkv + attention core in one tcgen05 kernel: x [S][H][C] -> out [S][H][128] (attn_tc.cu)
-int launch_qkv_attn_tc(const AttnW& a, const void* x, void* out, int64_t S, int H, int C, int prec, cudaStream_t st);
+int launch_qkv_attn_tc(const AttnW& a, const void* x, void* out, int64_t S, int H, int C, int prec, cudaStream_t st, int reverse = 0);
 
 // fused first block (16-bit paths): see kernels_fused.cu
 struct StemLaunch {

@@ -5,6 +5,8 @@
 #include <cmath>
 #include <cstring>
 
+#include <cstdlib>
+#include <unordered_map>
 #include "engine.h"
 #include "conv_tc.h"
 
@@ -277,6 +279,21 @@ struct Fwd {
     int prec, engine;
     cudaStream_t st;
     bool fork = false;                      // run residual 1x1 convs on e->side_stream (small batches)
+    // Tile-walk direction of the tensor-core launches ("snake").  An activation tensor (132 MB at C4) does not fit the 126 MB L2
+    // next to the traffic of the layer that wrote it, but its LAST-written part does: a consumer that walks its tiles in the
+    // opposite direction to the producer of its main input starts on data that is still in L2 instead of re-reading HBM.
+    // wdir[buffer] = direction the buffer was last written in (stem and SIMT kernels: front to back).
+    // CINDM_SNAKE=0 walks every layer front to back (A/B runs).
+    std::unordered_map<const void*, int> wdir;
+    int dir_for(const void* main_input, const void* out) {
+        static int snake = -1;
+        if (snake < 0) { const char* v = getenv("CINDM_SNAKE"); snake = (v && v[0] == '0') ? 0 : 1; }
+        if (!snake) return 0;
+        auto it = wdir.find(main_input);
+        const int d = (it == wdir.end() ? 0 : it->second) ^ 1;
+        wdir[out] = d;
+        return d;
+    }
 
     int record_tap(const std::string& name, const void* ptr, int c, int h) {
         if (!e->taps_enabled) return 0;
@@ -298,6 +315,7 @@ struct Fwd {
             a.add_vec = add_vec; a.t_dev = add_vec ? t_dev : nullptr; a.add_res = add_res; a.out = out; a.S = S;
             a.H = H; a.prec = prec;
             a.epilogue = (H == 3 && w.w16t[prec] != nullptr && e->use_toeplitz) ? EPI_GN_MISH_T3 : EPI_GN_MISH;
+            a.reverse = dir_for(in0, out);
             return launch_conv_tc(a, st);
         }
         ConvLaunch a;
@@ -319,6 +337,7 @@ struct Fwd {
             a.epilogue = EPI_BIAS;
             a.mode = transposed ? TC_UP : (stride == 2 ? TC_DOWN : TC_SAME);
             if (transposed && fork && !on) { a.side = e->side_stream; a.ev_fork = e->ev_fork; a.ev_join = e->ev_join; }
+            a.reverse = dir_for(in0, out);
             return launch_conv_tc(a, st);
         }
         ConvLaunch a;
@@ -358,7 +377,7 @@ struct Fwd {
     // x + to_out(linattn(LayerNorm(x)))
     int attention(const AttnW& a, const void* x, int C, int H, void* out) {
         if (engine == CINDM_CONV_TCGEN05 && prec != PREC_F32 && e->use_fused_attn) {
-            CINDM_TRY(launch_qkv_attn_tc(a, x, e->ws.att, S, H, C, prec, st));
+            CINDM_TRY(launch_qkv_attn_tc(a, x, e->ws.att, S, H, C, prec, st, dir_for(x, e->ws.att)));
             return conv_plain(a.out, e->ws.att, 128, nullptr, 0, prec, H, H, 1, 0, 0, x, out, prec);
         }
         CINDM_TRY(launch_layernorm(x, a.g, e->ws.ln, S * H, C, prec, st));
