@@ -273,12 +273,15 @@ def run_extras(args, torch, _lib, L, dif, model, fn, dev, stream, st, peaks):
         designs[..., 3::4] -= 0.5
         score_designs(designs[:1000])
         stream.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        mae, obj = score_designs(designs)
-        e1.record(stream)
-        stream.synchronize()
-        ms = e0.elapsed_time(e1)
+        times = []                # (median of 5: right after the 4096-candidate run the first calls are 20-30 % slower, clocks recovering)
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            mae, obj = score_designs(designs)
+            e1.record(stream)
+            stream.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = sorted(times)[2]
         gbs = b * (T_TOTAL * 4 * N_BODIES * 4 + 16) / (ms * 1e-3) / 1e9
         out["C5"] = {"ms": ms, "designs_per_sec": b / (ms * 1e-3), "designs": b, "algorithmic_gbs": gbs,
                      "hbm_roofline_frac": gbs / hbm_peak, "nan_designs": int(torch.isnan(mae).sum()),
