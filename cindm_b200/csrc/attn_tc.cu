@@ -227,11 +227,14 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     const int col = pass * 128 + cp * 32;
                     const float4* ws4 = reinterpret_cast<const float4*>(wsum + col);
                     uint32_t packed[16];
+                    // two columns per instruction (packed fp32: mul.f32x2 / fma.f32x2, same IEEE operations as the scalar form)
+                    const unsigned long long sc_2 = f32x2_pack(sc, sc), nm_2 = f32x2_pack(nm, nm);
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
                         const float4 w4 = ws4[i >> 2];
-                        const float y0 = fmaf(v[i], sc, nm * w4.x), y1 = fmaf(v[i + 1], sc, nm * w4.y);
-                        const float y2 = fmaf(v[i + 2], sc, nm * w4.z), y3 = fmaf(v[i + 3], sc, nm * w4.w);
+                        float y0, y1, y2, y3;
+                        f32x2_unpack(f32x2_fma(f32x2_pack(v[i], v[i + 1]), sc_2, f32x2_mul(nm_2, f32x2_pack(w4.x, w4.y))), y0, y1);
+                        f32x2_unpack(f32x2_fma(f32x2_pack(v[i + 2], v[i + 3]), sc_2, f32x2_mul(nm_2, f32x2_pack(w4.z, w4.w))), y2, y3);
                         packed[i >> 1] = pack2<T16>(y0, y1);
                         packed[(i >> 1) + 1] = pack2<T16>(y2, y3);
                     }
