@@ -501,7 +501,7 @@ def run_b200(args, rank, local_rank, world):
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         burst = peaks.get("bf16_tflops", 1590.0)
         iso = c["work"] / (c["ms"] * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv + GN/Mish epilogue), all layers of one evaluation",
+        roofline = {"bound": "tensor", "kernel": "conv_tc class = conv_tc_kernel + conv_tc_cm_kernel + conv_tc_cm_halo_kernel (tcgen05 implicit-GEMM convs with fused GN/Mish epilogues), all 58 launches of one evaluation",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
                     "algorithmic_flop_per_launch_group": c["work"] / c["launches"], "avg_launch_ms": in_step_ms / c["launches"],
@@ -515,7 +515,7 @@ def run_b200(args, rank, local_rank, world):
         c = classes["conv_simt"]
         achieved = c["work"] / (c["ms"] * 1e-3) / 1e12
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        roofline = {"bound": "tensor", "kernel": "conv1d_simt_kernel (fp32 FMA path)", "achieved": achieved, "peak": peak,
+        roofline = {"bound": "tensor", "kernel": "conv1d_simt128_kernel / conv1d_simt_kernel (fp32 FMA path)", "achieved": achieved, "peak": peak,
                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None}
 
     line = {
