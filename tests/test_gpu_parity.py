@@ -352,10 +352,11 @@ np.savez(sys.argv[1], **out)
 
 
 @pytest.mark.parametrize("env", [{"CINDM_CONV_CM": "0"}, {"CINDM_CONV_CM_HALO": "0"}, {"CINDM_CONV_CM_HALO": "1"},
-                                 {"CINDM_CONV_CM_EW": "12"}, {"CINDM_CONV_CM": "3"}])
+                                 {"CINDM_CONV_CM_EW": "12"}, {"CINDM_CONV_CM": "3"}, {"CINDM_SNAKE": "0"}])
 def test_conv_tc_kernel_variants_meet_the_same_bar(tmp_path, env):
     """Every dispatch switch of the GroupNorm convs (row-major kernel only; channel-major without / with halo loads everywhere;
-    12 epilogue warps; 256-channel layers on the row-major kernel) is held to the bar of the shipped configuration.  The
+    12 epilogue warps; 256-channel layers on the row-major kernel; every layer walking its tiles front to back) is held to the bar of
+    the shipped configuration.  The
     switches are read once per process, hence the subprocess."""
     import subprocess
     import sys
