@@ -370,6 +370,22 @@ def test_conv_tc_kernel_variants_meet_the_same_bar(tmp_path, env):
     assert rel_l2(got["bf16"], got["fp32"]) < 5e-2
 
 
+def test_tile_walk_direction_does_not_change_results(tmp_path):
+    """The order in which a persistent kernel walks its tiles is a scheduling choice: outputs are bit-identical."""
+    import subprocess
+    import sys
+    outs = []
+    for flag in ("1", "0"):
+        out = tmp_path / f"snake{flag}.npz"
+        e = dict(os.environ, CINDM_SNAKE=flag)
+        e["PYTHONPATH"] = os.path.dirname(HERE) + os.pathsep + e.get("PYTHONPATH", "")
+        r = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT, str(out)], env=e, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(np.load(out))
+    for key in ("fp16", "bf16"):
+        assert np.array_equal(outs[0][key], outs[1][key]), key
+
+
 def test_simt_conv_tile_variants_are_bit_identical(tmp_path):
     """fp32 path: the 128-row double-buffered conv kernel sums every output in the same (tap, ci) order as the 64 x 64 one."""
     import subprocess
