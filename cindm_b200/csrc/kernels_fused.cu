@@ -772,48 +772,71 @@ int launch_stem(const StemLaunch& a, cudaStream_t st) {
 // Head: final 1x1 conv 64 -> 8 (+bias) from 16-bit activations to fp32 eps_pair [S][24][8]
 // (reference final_conv[1], model/diffusion_1d.py:607).  One thread per (slice, position) row.
 // ------------------------------------------------------------------------------------------
+constexpr int kHeadRows = 512;                 // rows per block: two per thread, so every broadcast weight load feeds two rows
+constexpr int kHeadRowHalves = 64 + 8;         // row stride 144 B: the per-thread 16-byte reads of the second phase are conflict-free
+
 template <typename T, int F>
 __global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ in, const float* __restrict__ w,
                                                    const float* __restrict__ bias, float* __restrict__ out,
                                                    long long rows) {
-    // The block's 256 input rows (128 B each) are staged in shared memory with fully coalesced 16-byte loads (round 1 let
-    // every thread walk its own row: 32 different 128-byte lines per load instruction, 1.9 TB/s); a row stride of 144 B
-    // keeps the per-thread 16-byte reads of the second phase conflict-free.
-    constexpr int kRowHalves = 64 + 8;
-    __shared__ __align__(16) T tile[256 * kRowHalves];
+    // The block's 512 input rows (128 B each) are staged in shared memory with fully coalesced 16-byte loads (round 1 let
+    // every thread walk its own row: 32 different 128-byte lines per load instruction, 1.9 TB/s).  The FMA phase is bound by
+    // the shared-memory loads of the weights (two 16-byte broadcast loads per input channel), so a thread takes TWO rows per
+    // weight load, on packed fp32 FMAs (fma.f32x2: the same IEEE operations, half the issue slots).
+    extern __shared__ __align__(16) unsigned char head_smem[];
+    T* tile = reinterpret_cast<T*>(head_smem);
     __shared__ float sw[64][F];
     __shared__ float sb[F];
     pdl_wait();
     pdl_trigger();
     for (int i = threadIdx.x; i < 64 * F; i += 256) sw[i / F][i % F] = w[i];      // w: [1][64][F]
     if (threadIdx.x < F) sb[threadIdx.x] = bias[threadIdx.x];
-    const long long row0 = (long long)blockIdx.x * 256;
-    const long long n_here = rows - row0 < 256 ? rows - row0 : 256;
+    const long long row0 = (long long)blockIdx.x * kHeadRows;
+    const long long n_here = rows - row0 < kHeadRows ? rows - row0 : kHeadRows;
     const uint4* src = reinterpret_cast<const uint4*>(in + row0 * 64);
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < kHeadRows * 8 / 256; ++it) {
         const int v = it * 256 + threadIdx.x;                     // 16-byte vector index inside the block's rows
         const int r = v >> 3, c = v & 7;
-        if (r < n_here) *reinterpret_cast<uint4*>(tile + r * kRowHalves + c * 8) = src[v];
+        if (r < n_here) *reinterpret_cast<uint4*>(tile + r * kHeadRowHalves + c * 8) = src[v];
     }
     __syncthreads();
     if (threadIdx.x >= n_here) return;
-    float acc[F];
+    const bool two = threadIdx.x + 256 < n_here;                  // (the second row of the last block may not exist)
+    unsigned long long acc_a[F / 2], acc_b[F / 2];
 #pragma unroll
-    for (int o = 0; o < F; ++o) acc[o] = sb[o];
-    const T* rowp = tile + threadIdx.x * kRowHalves;
+    for (int o = 0; o < F; o += 2) acc_a[o >> 1] = acc_b[o >> 1] = f32x2_pack(sb[o], sb[o + 1]);
+    const T* row_a = tile + threadIdx.x * kHeadRowHalves;
+    const T* row_b = tile + (two ? threadIdx.x + 256 : threadIdx.x) * kHeadRowHalves;
 #pragma unroll
     for (int c8 = 0; c8 < 64; c8 += 8) {
-        float v[8];
-        load8<T>(rowp + c8, v);
+        float va[8], vb[8];
+        load8<T>(row_a + c8, va);
+        load8<T>(row_b + c8, vb);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
+        for (int k = 0; k < 8; ++k) {
+            const unsigned long long a2 = f32x2_pack(va[k], va[k]), b2 = f32x2_pack(vb[k], vb[k]);
 #pragma unroll
-            for (int o = 0; o < F; ++o) acc[o] = fmaf(v[k], sw[c8 + k][o], acc[o]);
+            for (int o = 0; o < F; o += 2) {
+                const unsigned long long w2 = f32x2_pack(sw[c8 + k][o], sw[c8 + k][o + 1]);
+                acc_a[o >> 1] = f32x2_fma(a2, w2, acc_a[o >> 1]);
+                acc_b[o >> 1] = f32x2_fma(b2, w2, acc_b[o >> 1]);
+            }
+        }
     }
+    float acc[F];
+#pragma unroll
+    for (int o = 0; o < F; o += 2) f32x2_unpack(acc_a[o >> 1], acc[o], acc[o + 1]);
     float4* dst = reinterpret_cast<float4*>(out + (row0 + threadIdx.x) * F);
 #pragma unroll
     for (int o = 0; o < F; o += 4) dst[o >> 2] = make_float4(acc[o], acc[o + 1], acc[o + 2], acc[o + 3]);
+    if (two) {
+#pragma unroll
+        for (int o = 0; o < F; o += 2) f32x2_unpack(acc_b[o >> 1], acc[o], acc[o + 1]);
+        dst = reinterpret_cast<float4*>(out + (row0 + threadIdx.x + 256) * F);
+#pragma unroll
+        for (int o = 0; o < F; o += 4) dst[o >> 2] = make_float4(acc[o], acc[o + 1], acc[o + 2], acc[o + 3]);
+    }
 }
 
 int launch_head(const void* in, const ConvW& w, float* out, int64_t rows, int prec, cudaStream_t st) {
@@ -821,11 +844,17 @@ int launch_head(const void* in, const ConvW& w, float* out, int64_t rows, int pr
     const int F = w.cout;
     if (F != 8 && F != 4) return fail(-2, "head kernel is built for 8 or 4 output features");
     KernelTimer kt("head", st, (double)rows * (64.0 * elem_size(prec) + 4.0 * F));
-    const unsigned blocks = (unsigned)((rows + 255) / 256);
+    const unsigned blocks = (unsigned)((rows + kHeadRows - 1) / kHeadRows);
+    const size_t smem = (size_t)kHeadRows * kHeadRowHalves * 2;
     if (prec != PREC_F16 && prec != PREC_BF16) return fail(-2, "head kernel is built for the 16-bit precisions");
 #define CINDM_HEAD(T, FF)                                                                                                     \
-    CINDM_CHECK_CUDA(launch_chain(head_kernel<T, FF>, dim3(blocks), dim3(256), 0, st, (const T*)in, (const float*)w.w,      \
-                                  (const float*)w.bias, out, (long long)rows))
+    do {                                                                                                                  \
+        static DeviceOnce once;                                                                                           \
+        if (once.first_time())                                                                                            \
+            CINDM_CHECK_CUDA(cudaFuncSetAttribute(head_kernel<T, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        CINDM_CHECK_CUDA(launch_chain(head_kernel<T, FF>, dim3(blocks), dim3(256), smem, st, (const T*)in, (const float*)w.w,   \
+                                      (const float*)w.bias, out, (long long)rows));                                        \
+    } while (0)
     if (prec == PREC_F16 && F == 8) CINDM_HEAD(__half, 8);
     else if (prec == PREC_F16) CINDM_HEAD(__half, 4);
     else if (F == 8) CINDM_HEAD(__nv_bfloat16, 8);
