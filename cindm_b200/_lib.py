@@ -51,6 +51,7 @@ _SIGNATURES = {
     "cindm_set_schedule": (c_int, [c_void_p, c_void_p, c_int]),
     "cindm_reserve": (c_int, [c_void_p, c_int64, c_int]),
     "cindm_workspace_bytes": (c_int64, [c_int64, c_int]),
+    "cindm_model_workspace_bytes": (c_int64, [c_int, c_int, c_int64, c_int]),
     "cindm_schedule_tables": (c_int, [c_int, c_void_p]),
     "cindm_build_index_maps": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int32), POINTER(c_int32),
                                        POINTER(c_int32), POINTER(c_int32)]),

@@ -121,8 +121,12 @@ int cindm_profile_report(char* buf, int capacity) {
 int cindm_create(const cindm_config* cfg, cindm_engine** out) {
     API_BEGIN
     if (!cfg || !out) return fail(-2, "null argument");
-    if (cfg->dim != 64) return fail(-2, "only Unet_dim=64 is built (dim_mults (1,2,4,8))");
-    if (cfg->horizon != 24) return fail(-2, "only horizon=24 (the 2-body 24-step model) is built");
+    // horizon 24 / dim 64 is the model every 16-bit tensor-core kernel is built for; the reference's other model names
+    // (44-step rollout, Unet_dim 96: inference/inverse_design_diffusion_1d.py:150-154) run on the generic fp32 kernels
+    if (cfg->dim < 16 || cfg->dim > 128 || cfg->dim % 16 != 0)
+        return fail(-2, "Unet_dim must be a multiple of 16 in [16, 128] (dim_mults (1,2,4,8); 64 and 96 are the reference's models)");
+    if (cfg->horizon < 8 || cfg->horizon > 48 || cfg->horizon % 2 != 0)
+        return fail(-2, "horizon must be even and in [8, 48] (24: the 24-step models, 44: the 44-step models)");
     if (cfg->transition_dim != 8 && cfg->transition_dim != 4)
         return fail(-2, "transition_dim must be 8 (two bodies x 4 features) or 4 (the unconditional single-body model)");
     if (cfg->timesteps < 1 || cfg->timesteps > 65535) return fail(-2, "timesteps out of range");
@@ -203,7 +207,10 @@ int cindm_reserve(cindm_engine* e, int64_t max_slices, int precision) {
     API_END
 }
 
-int64_t cindm_workspace_bytes(int64_t max_slices, int precision) { return workspace_bytes(max_slices, precision, 24); }
+int64_t cindm_workspace_bytes(int64_t max_slices, int precision) { return workspace_bytes(max_slices, precision, 24, 64); }
+int64_t cindm_model_workspace_bytes(int horizon, int dim, int64_t max_slices, int precision) {
+    return workspace_bytes(max_slices, precision, horizon, dim);
+}
 
 int cindm_schedule_tables(int timesteps, float* out) {
     API_BEGIN

@@ -234,7 +234,8 @@ int sample_ddim(cindm_engine* e, const cindm_sample_config& c, int n_pairs, cons
 void graph_cache_clear(cindm_engine* e);
 int finalize_weights(cindm_engine* e, cudaStream_t st);
 int reserve_workspace(cindm_engine* e, int64_t S, int prec);
-int64_t workspace_bytes(int64_t S, int prec, int horizon);
+int64_t workspace_bytes(int64_t S, int prec, int horizon, int dim);
+int down_samplings(int horizon);                 // Downsample1d stages of a model with this horizon (reference :549-554)
 // x0_composed: required for (and only used by) CINDM_COMPOSE_MEAN_OUTSIDE, where `eps` receives the composed posterior mean
 // mode CINDM_COMPOSE_EBM: sum over pairs minus ebm_coef * the attached unconditional single-body model (nc must be 0)
 int composed_eps(cindm_engine* e, const float* x, float* eps, int B, int n, int nc, int start, int mode, int t,

@@ -81,7 +81,9 @@ __device__ __forceinline__ void store4<float>(float* p, float a, float b, float 
     *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
 }
 
-template <typename T>
+// SLOTS = position slots of 8 a thread covers in stage 4: 3 for n <= 24 (every level of the 24-step model), 6 for n <= 48
+// (the 44-step models); every accumulator sums in the same order either way.
+template <typename T, int SLOTS = 3>
 __global__ void __launch_bounds__(256) attn_core_tiled_kernel(const T* __restrict__ qkv, T* __restrict__ out, int n,
                                                               long long S) {
     extern __shared__ __align__(16) float sm[];
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(256) attn_core_tiled_kernel(const T* __restric
     float* ctx = sk;                         // [4][32][36], written over k/v once they are consumed
     const int tid = threadIdx.x;
     const int h = tid >> 6, l = tid & 63;
-    constexpr int kMaxVec = 5;               // n*48 <= 1152 16-byte vectors per slice, <= 5 per thread
+    constexpr int kMaxVec = (SLOTS * 8 * 48 + 255) / 256;    // n*48 <= 1152 (2304) 16-byte vectors per slice, <= 5 (9) per thread
     constexpr int kVecStride = (int)(sizeof(T) * 8 / 16);
     const int nvec = n * 48;
     uint4 raw[kMaxVec];
@@ -174,20 +176,22 @@ __global__ void __launch_bounds__(256) attn_core_tiled_kernel(const T* __restric
                     make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
         }
         __syncthreads();
-        // ---- 4. out[e][j] = sum_d ctx[d][e] q[d][j]; thread = 4 channels x positions {ng, ng+8, ng+16}
+        // ---- 4. out[e][j] = sum_d ctx[d][e] q[d][j]; thread = 4 channels x positions {ng, ng+8, ng+16, ...}
         {
             const int be = l & 7, ng = l >> 3;
-            float acc[3][4];
+            float acc[SLOTS][4];
+            bool on[SLOTS];
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
+            for (int k = 0; k < SLOTS; ++k) {
+                on[k] = ng + 8 * k < n;
 #pragma unroll
                 for (int b = 0; b < 4; ++b) acc[k][b] = 0.f;
-            const bool on[3] = {ng < n, ng + 8 < n, ng + 16 < n};
+            }
 #pragma unroll 4
             for (int d = 0; d < 32; ++d) {
                 const float4 c4 = *reinterpret_cast<const float4*>(ctx + (h * 32 + d) * kCtxRow + 4 * be);
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
+                for (int k = 0; k < SLOTS; ++k) {
                     if (!on[k]) continue;
                     const float qv = sq[(ng + 8 * k) * kAttnRow + h * 32 + d];
                     acc[k][0] = fmaf(c4.x, qv, acc[k][0]);
@@ -198,7 +202,7 @@ __global__ void __launch_bounds__(256) attn_core_tiled_kernel(const T* __restric
             }
             T* dst = out + s * (long long)n * 128;
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
+            for (int k = 0; k < SLOTS; ++k)
                 if (on[k]) store4<T>(dst + (ng + 8 * k) * 128 + h * 32 + 4 * be, acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
         }
         __syncthreads();                     // shared memory is rewritten by the next slice
@@ -403,7 +407,8 @@ static int launch_attn_mma(const T* qkv, T* out, int64_t S, int n, cudaStream_t 
 
 int launch_attn_core(const void* qkv, void* out, int64_t S, int n, int prec, cudaStream_t st) {
     if (S == 0) return 0;
-    if (n > 24) return fail(-2, "attention core supports at most 24 positions");
+    if (n > 48) return fail(-2, "attention core supports at most 48 positions");
+    if (n > 24 && prec != PREC_F32) return fail(-2, "the 16-bit attention core supports at most 24 positions");
     KernelTimer kt("attn_core", st, (double)S * n * 512.0 * elem_size(prec));
     if (prec == PREC_F16) return launch_attn_mma<__half>((const __half*)qkv, (__half*)out, S, n, st);
     if (prec == PREC_BF16) return launch_attn_mma<__nv_bfloat16>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, S, n, st);
@@ -414,6 +419,8 @@ int launch_attn_core(const void* qkv, void* out, int64_t S, int n, int prec, cud
         CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_tiled_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_tiled_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_tiled_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        CINDM_CHECK_CUDA(cudaFuncSetAttribute(attn_core_tiled_kernel<float, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)attn_smem_bytes(48)));
     }
     // persistent grid: as many CTAs as fit on the machine at this shared-memory footprint
     int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
@@ -425,7 +432,10 @@ int launch_attn_core(const void* qkv, void* out, int64_t S, int n, int prec, cud
     long long want = (long long)sms * per_sm;
     const unsigned grid = (unsigned)(S < want ? S : want);
     switch (prec) {
-        case PREC_F32: attn_core_tiled_kernel<float><<<grid, 256, smem, st>>>((const float*)qkv, (float*)out, n, S); break;
+        case PREC_F32:
+            if (n > 24) attn_core_tiled_kernel<float, 6><<<grid, 256, smem, st>>>((const float*)qkv, (float*)out, n, S);
+            else attn_core_tiled_kernel<float><<<grid, 256, smem, st>>>((const float*)qkv, (float*)out, n, S);
+            break;
         case PREC_F16: attn_core_tiled_kernel<__half><<<grid, 256, smem, st>>>((const __half*)qkv, (__half*)out, n, S); break;
         case PREC_BF16:
             attn_core_tiled_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, n, S);

@@ -17,6 +17,17 @@ int launch_temb_table(const float* w1, const float* b1, const float* w3, const f
 int launch_block_time_bias(const float* temb, const float* w, const float* b, float* out, int dim, int cout,
                            int timesteps, cudaStream_t st);
 
+// Number of Downsample1d / Upsample1d stages the reference builds for a horizon (model/diffusion_1d.py:549-554, :575-599):
+// three when horizon % 8 == 0 (24 -> 12 -> 6 -> 3), two when only % 4 (the 44-step models: 44 -> 22 -> 11, and the 512-channel
+// level stays at 11 positions), one when only % 2; the other levels keep nn.Identity in those slots.
+int down_samplings(int horizon) {
+    if (horizon <= 0) return 0;
+    if (horizon % 8 == 0) return 3;
+    if (horizon % 4 == 0) return 2;
+    if (horizon % 2 == 0) return 1;
+    return 0;
+}
+
 namespace {
 
 struct Uploader {
@@ -175,7 +186,8 @@ struct Uploader {
 int finalize_weights(cindm_engine* e, cudaStream_t st) {
     if (e->finalized) return fail(-4, "weights already finalized");
     const int dim = e->cfg.dim, T = e->cfg.timesteps, F = e->cfg.transition_dim;
-    if (e->cfg.horizon % 8 != 0) return fail(-2, "horizon must be a multiple of 8");
+    const int n_down = down_samplings(e->cfg.horizon);
+    if (n_down == 0) return fail(-2, "horizon must be even (the reference defines no U-Net for odd horizons, :549-554)");
     Uploader up{e, st};
     // time_mlp -> temb table [T][dim]
     float* w1 = up.vec("time_mlp.1.weight", (int64_t)4 * dim * dim);
@@ -193,7 +205,7 @@ int finalize_weights(cindm_engine* e, cudaStream_t st) {
         up.resblock(e->downs_rb[i][0], p + ".0", ch[i], ch[i + 1], i == 3);
         up.resblock(e->downs_rb[i][1], p + ".1", ch[i + 1], ch[i + 1], i == 3);
         up.attn(e->downs_at[i], p + ".2", ch[i + 1]);
-        if (i < 3) up.conv(e->down_conv[i], p + ".3.conv", ch[i + 1], ch[i + 1], 3, true);
+        if (i < n_down) up.conv(e->down_conv[i], p + ".3.conv", ch[i + 1], ch[i + 1], 3, true);
     }
     up.resblock(e->mid_rb[0], "mid_block1", ch[4], ch[4], true);
     up.attn(e->mid_at, "mid_attn", ch[4]);
@@ -204,7 +216,7 @@ int finalize_weights(cindm_engine* e, cudaStream_t st) {
         up.resblock(e->ups_rb[i][0], p + ".0", co * 2, co, i == 0);
         up.resblock(e->ups_rb[i][1], p + ".1", co, ci, i == 0);
         up.attn(e->ups_at[i], p + ".2", ci);
-        up.conv(e->up_conv[i], p + ".3.conv", ci, ci, 4, true, /*transposed=*/true);
+        if (i >= 3 - n_down) up.conv(e->up_conv[i], p + ".3.conv", ci, ci, 4, true, /*transposed=*/true);
     }
     up.conv(e->final_block, "final_conv.0.block.0", dim, dim, 5, true);
     e->final_gn.gamma = up.vec("final_conv.0.block.2.weight", dim);
@@ -219,9 +231,22 @@ int finalize_weights(cindm_engine* e, cudaStream_t st) {
 
 // ---------------------------------------------------------------------------------------------
 
-int64_t workspace_bytes(int64_t S, int prec, int horizon) {
+// Positions x channels of the largest activation tensor of one slice.  With three down-samplings (horizon % 8 == 0) every level
+// holds horizon * dim values; a model that keeps its resolution on the lower levels (horizon % 4 / % 2, reference :549-554)
+// holds more there: level l has dim * 2^l channels at horizon / 2^min(l, n_down) positions.
+int64_t act_elems_per_slice(int horizon, int dim) {
+    const int n_down = down_samplings(horizon);
+    int64_t best = 0;
+    for (int l = 0; l < 4; ++l) {
+        const int64_t v = (int64_t)(horizon >> (l < n_down ? l : n_down)) * dim * (1 << l);
+        if (v > best) best = v;
+    }
+    return best;
+}
+
+int64_t workspace_bytes(int64_t S, int prec, int horizon, int dim) {
     const size_t es = elem_size(prec);
-    const int64_t per_act = S * (int64_t)horizon * 64;       // C*H is constant across levels (= horizon*dim)
+    const int64_t per_act = S * act_elems_per_slice(horizon, dim);
     auto al = [](int64_t b) { return (b + 1023) / 1024 * 1024; };
     int64_t total = 0;
     total += 3 * al(per_act * es);                  // act[3]
@@ -236,7 +261,6 @@ int64_t workspace_bytes(int64_t S, int prec, int horizon) {
 
 int reserve_workspace(cindm_engine* e, int64_t S, int prec) {
     if (prec < 0 || prec > 2) return fail(-2, "bad precision");
-    if (e->cfg.dim != 64) return fail(-2, "workspace layout assumes dim == 64");
     Workspace& w = e->ws;
     if (w.base && w.max_slices >= S && w.precision == prec) return 0;
     if (w.base) {
@@ -247,8 +271,8 @@ int reserve_workspace(cindm_engine* e, int64_t S, int prec) {
     }
     const int H = e->cfg.horizon;
     const size_t es = elem_size(prec);
-    const int64_t per_act = S * (int64_t)H * 64;
-    size_t bytes = (size_t)workspace_bytes(S, prec, H);
+    const int64_t per_act = S * act_elems_per_slice(H, e->cfg.dim);
+    size_t bytes = (size_t)workspace_bytes(S, prec, H, e->cfg.dim);
     CINDM_CHECK_CUDA(cudaMalloc(&w.base, bytes));
     w.bytes = bytes;
     char* p = (char*)w.base;
@@ -398,6 +422,10 @@ int unet_forward(cindm_engine* e, const float* slices, int64_t S, int t, const i
         return fail(-6, "workspace not reserved for this slice count / precision (call cindm_reserve)");
     if (conv_engine == CINDM_CONV_TCGEN05 && precision == PREC_F32)
         return fail(-2, "the tcgen05 conv engine needs a 16-bit precision");
+    if (precision != PREC_F32 && !(e->cfg.horizon == 24 && e->cfg.dim == 64))
+        return fail(-2, "the 16-bit kernels (fused stem / head, tcgen05 convs) are built for the horizon-24, dim-64 model; "
+                        "other models (44-step, Unet_dim 96) run with precision fp32 on the simt engine");
+    const int n_down = down_samplings(e->cfg.horizon);
     if (e->taps_enabled) {
         for (void* p : e->tap_allocs) cudaFree(p);
         e->tap_allocs.clear();
@@ -464,7 +492,7 @@ int unet_forward(cindm_engine* e, const float* slices, int64_t S, int t, const i
             cur = w.act[out_i]; cur_i = out_i;
         }
         CINDM_TRY(f.record_tap("downs." + std::to_string(i) + ".2", cur, ch[i + 1], H));
-        if (i < 3) {
+        if (i < n_down) {
             out_i = next_buf(cur_i, -1);
             CINDM_TRY(f.conv_plain(e->down_conv[i], cur, ch[i + 1], nullptr, 0, precision, H, H / 2, 2, 1, 0, nullptr,
                                    w.act[out_i], precision));
@@ -474,7 +502,7 @@ int unet_forward(cindm_engine* e, const float* slices, int64_t S, int t, const i
         }
         x_in = cur;
     }
-    // here cur == skip[2] (512 @ H/8); it is both the mid input and the first up-block's skip
+    // here cur == skip[2] (dim*8 channels at the lowest resolution); it is both the mid input and the first up-block's skip
     {
         int tmp_i = next_buf(cur_i, -1), out_i = next_buf(cur_i, tmp_i);
         CINDM_TRY(f.resblock(e->mid_rb[0], cur, ch[4], nullptr, 0, precision, H, w.act[tmp_i], w.act[out_i]));
@@ -505,6 +533,7 @@ int unet_forward(cindm_engine* e, const float* slices, int64_t S, int t, const i
         CINDM_TRY(f.attention(e->ups_at[i], cur, ci, H, w.act[out_i]));
         cur = w.act[out_i]; cur_i = out_i;
         CINDM_TRY(f.record_tap("ups." + std::to_string(i) + ".2", cur, ci, H));
+        if (i < 3 - n_down) continue;          // nn.Identity in the Upsample1d slot (:585, :594)
         out_i = next_buf(cur_i, -1);
         CINDM_TRY(f.conv_plain(e->up_conv[i], cur, ci, nullptr, 0, precision, H, H * 2, 2, 1, 1, nullptr, w.act[out_i],
                                precision));

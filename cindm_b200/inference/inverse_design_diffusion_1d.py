@@ -84,6 +84,7 @@ def build_parser():
 
 
 FAST_PATH_MODELS = ("Diffusion_cond-0_rollout-24_bodies-2", "Diffusion_cond-0_rollout-24_bodies-2_more_collision")
+GENERIC_PATH_MODELS = ("Diffusion_cond-0_rollout-44_bodies-2", "Diffusion_cond-0_rollout-44_bodies-2_Unet_dim-96")
 
 
 def model_horizon(args):
@@ -94,8 +95,10 @@ def model_horizon(args):
     message that says which names are."""
     if args.model_name in FAST_PATH_MODELS:
         return 24, 0
-    if args.model_name in ("Diffusion_cond-0_rollout-44_bodies-2", "Diffusion_cond-0_rollout-44_bodies-2_Unet_dim-96"):
-        raise NotImplementedError("the 44-step models use a different U-Net layout (horizon % 8 != 0): not on the CUDA fast path")
+    if args.model_name in GENERIC_PATH_MODELS:
+        # (:150-154) horizon 44: two down-samplings, 44 -> 22 -> 11 -> 11 (model/diffusion_1d.py:549-554); --Unet_dim stays the
+        # user's flag, as in the reference.  These run on the generic fp32 CUDA kernels (see main()).
+        return 44, 0
     if args.model_name in ("basic_model", "single_step_model"):
         raise NotImplementedError(
             f"model_name {args.model_name!r} is a conditioned model (conditioned_steps=4): this driver samples with cond=None; "
@@ -185,6 +188,13 @@ def run(args):
         # reference Trainer1D checkpoints hold optimizer / EMA / GradScaler state next to "model" (:2635-2647)
         ckpt = torch.load(args.checkpoint, map_location="cpu", weights_only=False)
         diffusion.load_state_dict(ckpt["model"])
+    if not model.tensor_core_model and (args.precision, args.conv_engine) != ("fp32", "simt"):
+        # the 16-bit tensor-core kernels are built for the horizon-24, dim-64 model; the 44-step / Unet_dim-96 models run on
+        # the generic fp32 CUDA kernels (still the GPU library: there is no CPU path)
+        if rank == 0:
+            print(f"model horizon {model.horizon}, Unet_dim {model.dim}: --precision {args.precision} --conv_engine "
+                  f"{args.conv_engine} is built for horizon 24 / Unet_dim 64 only; running --precision fp32 --conv_engine simt")
+        args.precision, args.conv_engine = "fp32", "simt"
     diffusion.precision, diffusion.conv_engine = args.precision, args.conv_engine
     diffusion.seed = args.seed
     output_steps = rollout_steps + args.n_composed * args.compose_start_step

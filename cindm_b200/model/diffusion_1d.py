@@ -201,9 +201,15 @@ class TemporalUnet1D:
         self.dim_mults = tuple(dim_mults)
         self.attention = attention
         self._shapes = unet_param_shapes(horizon, transition_dim, dim, self.dim_mults, attention)
-        if dim != 64 or self.dim_mults != (1, 2, 4, 8) or horizon != 24 or transition_dim not in (8, 4):
-            raise NotImplementedError("CUDA fast path is built for horizon=24, dim=64, dim_mults=(1,2,4,8) and transition_dim 8 "
-                                      "(body-pair model) or 4 (unconditional single-body model)")
+        if self.dim_mults != (1, 2, 4, 8) or transition_dim not in (8, 4):
+            raise NotImplementedError("the CUDA path is built for dim_mults=(1,2,4,8) and transition_dim 8 (body-pair model) "
+                                      "or 4 (unconditional single-body model)")
+        if horizon % 2 or not 8 <= horizon <= 48 or dim % 16 or not 16 <= dim <= 128:
+            raise NotImplementedError("the CUDA path is built for even horizons in [8, 48] and Unet_dim a multiple of 16 in "
+                                      "[16, 128] (the reference's models: horizon 24 / 44, dim 64 / 96)")
+        # horizon 24, dim 64 is the model the 16-bit tensor-core kernels are built for; every other model (the 44-step and
+        # Unet_dim-96 models of inference/inverse_design_diffusion_1d.py:150-154) runs on the generic fp32 CUDA kernels
+        self.tensor_core_model = horizon == 24 and dim == 64
         self._params = init_unet_params(self._shapes, seed=seed)
         self._device = torch.device("cpu")
         self._engine = None

@@ -15,10 +15,24 @@ import math
 import torch
 
 
+def down_samplings(horizon):
+    """Downsample1d / Upsample1d stages of a 4-level model (reference model/diffusion_1d.py:549-554, :575-599): 3 when
+    horizon % 8 == 0, 2 when only % 4 (the 44-step models: 44 -> 22 -> 11 -> 11), 1 when only % 2; the remaining slots hold
+    nn.Identity and own no parameters.  Odd horizons are undefined in the reference (`is_last` is never bound)."""
+    if horizon % 8 == 0:
+        return 3
+    if horizon % 4 == 0:
+        return 2
+    if horizon % 2 == 0:
+        return 1
+    raise ValueError(f"horizon {horizon}: the reference defines TemporalUnet1D for even horizons only")
+
+
 def unet_param_shapes(horizon=24, transition_dim=8, dim=64, dim_mults=(1, 2, 4, 8), attention=True):
     """OrderedDict name -> shape, in the reference's registration order (time_mlp, downs, ups, mid, final)."""
-    if horizon % 8 != 0:
-        raise NotImplementedError("only horizon % 8 == 0 (three down/up-samplings) is on the B200 fast path")
+    if len(dim_mults) != 4:
+        raise NotImplementedError("dim_mults of length 4 (every CinDM model uses (1, 2, 4, 8))")
+    n_down = down_samplings(horizon)
     if not attention:
         raise NotImplementedError("attention=False is not used by any CinDM inference entry point")
     dims = [transition_dim] + [dim * m for m in dim_mults]
@@ -53,15 +67,16 @@ def unet_param_shapes(horizon=24, transition_dim=8, dim=64, dim_mults=(1, 2, 4, 
         rtb(f"downs.{i}.0", ci, co)
         rtb(f"downs.{i}.1", co, co)
         attn(f"downs.{i}.2", co)
-        if i < n_res - 1:
+        if i < n_down:
             shapes[f"downs.{i}.3.conv.weight"] = (co, co, 3)
             shapes[f"downs.{i}.3.conv.bias"] = (co,)
     for i, (ci, co) in enumerate(reversed(in_out[1:])):
         rtb(f"ups.{i}.0", co * 2, co)
         rtb(f"ups.{i}.1", co, ci)
         attn(f"ups.{i}.2", ci)
-        shapes[f"ups.{i}.3.conv.weight"] = (ci, ci, 4)
-        shapes[f"ups.{i}.3.conv.bias"] = (ci,)
+        if i >= n_res - 1 - n_down:
+            shapes[f"ups.{i}.3.conv.weight"] = (ci, ci, 4)
+            shapes[f"ups.{i}.3.conv.bias"] = (ci,)
     mid = dims[-1]
     rtb("mid_block1", mid, mid)
     attn("mid_attn", mid)

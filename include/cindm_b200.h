@@ -49,9 +49,11 @@ enum { CINDM_OBJ_L2 = 0, CINDM_OBJ_L2SQUARE = 1 };
 enum { CINDM_GUIDE_NONE = 0, CINDM_GUIDE_STANDARD = 1, CINDM_GUIDE_STANDARD_ALPHA = 2 };
 
 typedef struct {
-    int horizon;        /* 24: TemporalUnet1D(horizon=...)            model/diffusion_1d.py:521 */
+    int horizon;        /* 24: TemporalUnet1D(horizon=...)            model/diffusion_1d.py:521.  Even, 8..48: 24 is the model the
+                           16-bit tensor-core kernels are built for; the 44-step models (inverse_design_diffusion_1d.py:150-154)
+                           and any other even horizon run with CINDM_PREC_F32 on CINDM_CONV_SIMT */
     int transition_dim; /* 8 : two bodies x (x,y,vx,vy); 4: the unconditional single-body model  :522 */
-    int dim;            /* 64: Unet_dim                                                     :524 */
+    int dim;            /* 64: Unet_dim (:524); a multiple of 16 up to 128 (96: the "_Unet_dim-96" model), fp32 / simt when != 64 */
     int timesteps;      /* 1000: GaussianDiffusion1D(timesteps=...)                         :810 */
 } cindm_config;
 
@@ -114,7 +116,10 @@ int cindm_finalize_weights(cindm_engine* e, void* stream);
 int cindm_set_schedule(cindm_engine* e, const float* tables13, int timesteps);
 /* allocate the activation workspace for up to max_slices slices per forward */
 int cindm_reserve(cindm_engine* e, int64_t max_slices, int precision);
-int64_t cindm_workspace_bytes(int64_t max_slices, int precision);
+int64_t cindm_workspace_bytes(int64_t max_slices, int precision);      /* the horizon-24, dim-64 model */
+/* the same for any model cindm_create accepts (TemporalUnet1D(horizon, dim), model/diffusion_1d.py:519-608: the level
+ * structure follows horizon % 8 / % 4 / % 2, :549-554) */
+int64_t cindm_model_workspace_bytes(int horizon, int dim, int64_t max_slices, int precision);
 
 /* ---- host-side helpers ------------------------------------------------------------------- */
 /* cosine_beta_schedule + derived buffers (model/diffusion_1d.py:470-480, :853-897): writes

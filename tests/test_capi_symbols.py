@@ -95,12 +95,27 @@ def test_state_dict_layout_matches_reference_keys():
         dif.load_state_dict({k: v for k, v in sd.items() if k != "model.final_conv.1.bias"})
 
 
+def test_workspace_size_follows_the_level_structure(library):
+    """Host-only: a horizon % 8 model holds horizon * dim values per slice on every level; the 44-step models keep 11 positions
+    on the 512-channel level (11 * 8 * dim > 44 * dim), so their activation buffers are sized by that level."""
+    from cindm_b200 import _lib
+    L = _lib.lib()
+    assert L.cindm_model_workspace_bytes(24, 64, 1000, 0) == L.cindm_workspace_bytes(1000, 0)
+    per_slice = lambda h, d: (L.cindm_model_workspace_bytes(h, d, 4096, 0) - L.cindm_model_workspace_bytes(h, d, 2048, 0)) / 2048
+    # 9 activation-sized fp32 buffers + qkv (384) + att (128) + slices / eps_pair (2 x 8) per position
+    assert per_slice(24, 64) == pytest.approx(4 * (9 * 24 * 64 + 24 * (384 + 128 + 16)), rel=1e-3)
+    assert per_slice(44, 64) == pytest.approx(4 * (9 * 11 * 512 + 44 * (384 + 128 + 16)), rel=1e-3)
+    assert per_slice(44, 96) == pytest.approx(4 * (9 * 11 * 768 + 44 * (384 + 128 + 16)), rel=1e-3)
+
+
 def test_c_abi_reports_errors_instead_of_throwing(library):
     """Argument validation happens before any CUDA call: negative code + message, nothing thrown across the boundary."""
     from cindm_b200 import _lib
     L = _lib.lib()
     handle = ctypes.c_void_p()
-    for bad in (_lib.Config(44, 8, 64, 1000), _lib.Config(24, 8, 96, 1000), _lib.Config(24, 16, 64, 1000), _lib.Config(24, 8, 64, 0)):
+    # odd horizon (undefined in the reference, :549-554), horizon / dim out of range, a dim GroupNorm(8) cannot split, ...
+    for bad in (_lib.Config(45, 8, 64, 1000), _lib.Config(64, 8, 64, 1000), _lib.Config(24, 8, 100, 1000), _lib.Config(24, 8, 256, 1000),
+                _lib.Config(24, 16, 64, 1000), _lib.Config(24, 8, 64, 0)):
         rc = L.cindm_create(ctypes.byref(bad), ctypes.byref(handle))
         assert rc < 0 and L.cindm_last_error()
     assert L.cindm_create(None, ctypes.byref(handle)) < 0

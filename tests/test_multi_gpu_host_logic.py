@@ -90,9 +90,10 @@ def test_cli_keeps_reference_flags_and_defaults():
     assert model_horizon(paper) == (24, 0)
     assert guidance_list(paper) == ["standard-recurrence-10"]
     assert paper.is_test is True
-    with pytest.raises(NotImplementedError):
-        paper.model_name = "Diffusion_cond-0_rollout-44_bodies-2"
-        model_horizon(paper)
+    # the 44-step models (:150-154): rollout 44, no condition frames; --Unet_dim stays the user's flag as in the reference
+    for name in ("Diffusion_cond-0_rollout-44_bodies-2", "Diffusion_cond-0_rollout-44_bodies-2_Unet_dim-96"):
+        paper.model_name = name
+        assert model_horizon(paper) == (44, 0)
 
 
 def test_stale_script_flags_are_kept():

@@ -202,3 +202,57 @@ def test_oracle_ebm_composition_reproduces_the_reference(golden, test_weights):
         img, x0 = sampler_ref.ebm_p_sample(test_weights, single, tabs, x, cond, t, lambda s, t=t: torch.from_numpy(g[f"ps_t{t}:noise"]))
         assert torch.allclose(img, torch.from_numpy(g[f"ps_t{t}:img"]), atol=5e-6), t
         assert torch.allclose(x0, torch.from_numpy(g[f"ps_t{t}:x0"]), atol=5e-6), t
+
+
+# ---- the reference's other model shapes (44-step rollout, Unet_dim 96; oracle/make_golden_models.py) ------------------------
+
+MODEL_CASES = META["model_cases"]["models"]
+
+
+def model_weights(case):
+    from cindm_b200.model.params import init_unet_params, unet_param_shapes
+    c = MODEL_CASES[case]
+    return init_unet_params(unet_param_shapes(c["horizon"], 8, c["dim"]), seed=0, randomize_affine=True)
+
+
+@pytest.mark.parametrize("case", sorted(MODEL_CASES))
+def test_other_model_shapes_match_reference(golden, case):
+    """TemporalUnet1D for horizon % 8 != 0 keeps its resolution on the lower levels (reference :549-554, :575-599); the key
+    inventory of `unet_param_shapes` was accepted by the reference's strict load_state_dict when the fixture was minted."""
+    from cindm_b200.model.params import down_samplings
+    g = golden("unet_models.npz")
+    c = MODEL_CASES[case]
+    sd = model_weights(case)
+    assert len(sd) == c["keys"] and sum(v.numel() for v in sd.values()) == c["params"]
+    x = torch.from_numpy(g[case + ":x"])
+    for t in (37, 812):
+        y = unet_ref.unet_forward(sd, x, torch.full((x.shape[0],), t, dtype=torch.long))
+        assert rel_l2(y, g[f"{case}:eps_t{t}"]) < 1e-6, t
+    taps = {}
+    unet_ref.unet_forward(sd, x[:2], torch.full((2,), 37, dtype=torch.long), taps=taps)       # the fixture's own batch of two
+    names = [k.split(":tap:")[1] for k in g.files if k.startswith(case + ":tap:")]
+    assert len(names) == 31 - 2 * (3 - down_samplings(c["horizon"]))     # one tap per parametrised block
+    for name in names:
+        assert rel_l2(taps[name], g[f"{case}:tap:{name}"]) < 1e-6, name
+
+
+@pytest.mark.parametrize("case", sorted(k for k in MODEL_CASES if MODEL_CASES[k]["horizon"] > 10))
+def test_other_model_shapes_sampler_matches_reference(golden, case):
+    g = golden("unet_models.npz")
+    hor = MODEL_CASES[case]["horizon"]
+    sd = model_weights(case)
+    n, nc, start, mode, b, t = META["model_cases"]["compose"]
+    eps = sampler_ref.composed_eps(sd, torch.from_numpy(g[case + ":compose_x"]), t, nc, start, n, mode, horizon=hor)
+    assert rel_l2(eps, g[case + ":compose_eps"]) < 1e-6
+    n, nc, start, guidance, mode, coef, cc, b, steps = META["model_cases"]["traj"]
+    tabs = sampler_ref.cosine_schedule_tables()
+    fn = sampler_ref.make_design_fn(torch.tensor([0.5, 0.5], dtype=torch.float64), 1, coef, cc, "L2")
+    noise = list(torch.from_numpy(g[case + ":traj_noise"]))
+    img = torch.from_numpy(g[case + ":traj_x_init"])
+    for si, t in enumerate(steps):
+        img, _ = sampler_ref.p_sample_step(sd, tabs, img, t, lambda shape: noise.pop(0), n_composed=nc, compose_start_step=start,
+                                           compose_n_bodies=n, compose_mode=mode, design_fn=fn, design_guidance=guidance,
+                                           horizon=hor)
+        assert rel_l2(img, g[f"{case}:traj_img_after_{si}"]) < 1e-5, (si, t)
+        img = torch.from_numpy(g[f"{case}:traj_img_after_{si}"])
+    assert not noise
