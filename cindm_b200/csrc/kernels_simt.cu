@@ -22,96 +22,113 @@ struct ConvParams {
     int c0, c1, cin, cout, taps, Hin, Hout, stride, pad, transposed;
 };
 
-template <typename InT, typename OutT>
+// BM x BN tile (64 x 64, or 32 x 32 for launches that would otherwise leave most SMs without a CTA), 256 threads, each a
+// BM/16 x BN/16 register tile; shared memory is double-buffered and the next K chunk is fetched into registers while the
+// current one is multiplied (one __syncthreads per chunk: with few CTAs per SM the K loop is latency-bound otherwise).
+// Every accumulator sums its products in (tap, ci) order whatever the tile, so all instances (and the 128-row kernel below)
+// give bit-identical results.
+template <typename InT, typename OutT, int BM = 64, int BN = 64>
 __global__ void __launch_bounds__(256) conv1d_simt_kernel(ConvParams p) {
-    __shared__ float As[16][64 + 4];
-    __shared__ float Bs[16][64];
+    constexpr int TM = BM / 16, TN = BN / 16, BK = 16;
+    __shared__ float As[2][BK][BM + 4];
+    __shared__ float Bs[2][BK][BN];
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
-    const long long row0 = (long long)blockIdx.x * 64;
-    const int co0 = blockIdx.y * 64;
+    const long long row0 = (long long)blockIdx.x * BM;
+    const int co0 = blockIdx.y * BN;
 
-    // A-load role: 4 consecutive input channels of one row
-    const int a_row = tid >> 2, a_ci = (tid & 3) * 4;
+    // A-load role: TM consecutive input channels of one row
+    const int a_row = tid / (16 / TM), a_ci = (tid % (16 / TM)) * TM;
     const long long arow = row0 + a_row;
     const bool arow_ok = arow < p.rows;
     const long long a_s = arow_ok ? arow / p.Hout : 0;
     const int a_j = arow_ok ? (int)(arow - a_s * p.Hout) : 0;
-    // B-load role: 4 consecutive output channels of one input channel
-    const int b_ci = tid >> 4, b_co = (tid & 15) * 4;
+    // B-load role: TN consecutive output channels of one input channel
+    const int b_ci = tid >> 4, b_co = (tid & 15) * TN;
 
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int cpt = (p.cin + BK - 1) / BK;               // K chunks per tap
+    const int nchunks = p.taps * cpt;
+    float av[TM], bv[TN];
 
-    for (int tap = 0; tap < p.taps; ++tap) {
+    auto fetch = [&](int chunk) {                        // global -> registers
+        const int tap = chunk / cpt, ci0 = (chunk - tap * cpt) * BK;
         int pos;
         bool pos_ok;
         if (!p.transposed) {
             pos = a_j * p.stride + tap - p.pad;
             pos_ok = pos >= 0 && pos < p.Hin;
         } else {
-            int q = a_j + p.pad - tap;
+            const int q = a_j + p.pad - tap;
             pos_ok = q >= 0 && (q % p.stride) == 0;
             pos = q / p.stride;
             pos_ok = pos_ok && pos < p.Hin;
         }
         pos_ok = pos_ok && arow_ok;
-        for (int ci0 = 0; ci0 < p.cin; ci0 += 16) {
-            // ---- stage A (transposed into As[ci][row]) ----
-            float av[4] = {0.f, 0.f, 0.f, 0.f};
-            if (pos_ok && ci0 + a_ci < p.cin) {
-                int ci = ci0 + a_ci;
-                const InT* src;
-                int cw, cbase;
-                if (ci < p.c0) { src = (const InT*)p.in0; cw = p.c0; cbase = ci; }
-                else           { src = (const InT*)p.in1; cw = p.c1; cbase = ci - p.c0; }
-                const InT* ptr = src + ((a_s * p.Hin + pos) * (long long)cw + cbase);
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (ci + q < p.cin) av[q] = to_f32<InT>(ptr[q]);
-            }
+        for (int q = 0; q < TM; ++q) av[q] = 0.f;
+        const int ci = ci0 + a_ci;
+        if (pos_ok && ci < p.cin) {
+            const InT* src;
+            int cw, cbase;
+            if (ci < p.c0) { src = (const InT*)p.in0; cw = p.c0; cbase = ci; }
+            else           { src = (const InT*)p.in1; cw = p.c1; cbase = ci - p.c0; }
+            const InT* ptr = src + ((a_s * p.Hin + pos) * (long long)cw + cbase);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) As[a_ci + q][a_row] = av[q];
-            // ---- stage B ----
-            {
-                int ci = ci0 + b_ci;
-                float bv[4] = {0.f, 0.f, 0.f, 0.f};
-                if (ci < p.cin) {
-                    const float* wp = p.w + ((long long)tap * p.cin + ci) * p.cout + co0 + b_co;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (co0 + b_co + q < p.cout) bv[q] = wp[q];
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) Bs[b_ci][b_co + q] = bv[q];
-            }
-            __syncthreads();
-#pragma unroll
-            for (int kk = 0; kk < 16; ++kk) {
-                float a[4], b[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-            }
-            __syncthreads();
+            for (int q = 0; q < TM; ++q)
+                if (ci + q < p.cin) av[q] = to_f32<InT>(ptr[q]);
         }
+        const int bci = ci0 + b_ci;
+#pragma unroll
+        for (int q = 0; q < TN; ++q) bv[q] = 0.f;
+        if (bci < p.cin) {
+            const float* wp = p.w + ((long long)tap * p.cin + bci) * p.cout + co0 + b_co;
+#pragma unroll
+            for (int q = 0; q < TN; ++q)
+                if (co0 + b_co + q < p.cout) bv[q] = wp[q];
+        }
+    };
+    auto stash = [&](int buf) {                          // registers -> shared memory (A transposed into As[ci][row])
+#pragma unroll
+        for (int q = 0; q < TM; ++q) As[buf][a_ci + q][a_row] = av[q];
+#pragma unroll
+        for (int q = 0; q < TN; ++q) Bs[buf][b_ci][b_co + q] = bv[q];
+    };
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int buf = chunk & 1;
+        if (chunk + 1 < nchunks) fetch(chunk + 1);       // in flight during the FMAs below
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = As[buf][kk][ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) b[j] = Bs[buf][kk][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (chunk + 1 < nchunks) stash(buf ^ 1);          // (the other buffer was last read before the previous barrier)
+        __syncthreads();
     }
     // ---- epilogue ----
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        long long r = row0 + ty * 4 + i;
+    for (int i = 0; i < TM; ++i) {
+        long long r = row0 + ty * TM + i;
         if (r >= p.rows) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int co = co0 + tx * 4 + j;
+        for (int j = 0; j < TN; ++j) {
+            int co = co0 + tx * TN + j;
             if (co >= p.cout) continue;
             float v = acc[i][j];
             if (p.bias) v += p.bias[co];
@@ -255,25 +272,47 @@ __global__ void __launch_bounds__(256, 2) conv1d_simt128_kernel(ConvParams p) {
     }
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+
 template <typename InT, typename OutT>
 static int conv_dispatch2(const ConvParams& p, cudaStream_t st) {
-    // the 128-row tile kernel (cout a multiple of 64) for everything but tiny problems; CINDM_SIMT_TILE128=0 keeps the 64 x 64
-    // kernel everywhere (A/B runs; the two are bit-identical)
-    static int tile128 = -1;
-    if (tile128 < 0) { const char* e = getenv("CINDM_SIMT_TILE128"); tile128 = (e && e[0] == '0') ? 0 : 1; }
-    if (tile128 && p.rows >= 512 && p.cout % 64 == 0) {
-        if (p.cout % 128 == 0) {
-            dim3 grid(ceil_div(p.rows, 128), p.cout / 128);
-            conv1d_simt128_kernel<InT, OutT, 128><<<grid, 256, 0, st>>>(p);
-        } else {
-            dim3 grid(ceil_div(p.rows, 128), p.cout / 64);
-            conv1d_simt128_kernel<InT, OutT, 64><<<grid, 256, 0, st>>>(p);
-        }
-        CINDM_CHECK_LAUNCH();
-        return 0;
+    // Tile by the number of CTAs a launch gets (all tiles are bit-identical): the 128-row double-buffered kernel (cout a
+    // multiple of 64) when it gets at least MIN128 = SMs / 2 CTAs, else 64 x 64 when that gets MIN64 = SMs, else 32 x 32
+    // (thresholds swept in profiles/r2_simt_tile_sweep.json) -- at small slice
+    // counts (C1, the 44-step models' fp32 path) a 64 x 64 grid is 10-24 CTAs on 148 SMs.  A/B switches, read per launch:
+    // CINDM_SIMT_TILE128=0 never uses the 128-row kernel, CINDM_SIMT_TILE32=0 never the 32 x 32 tile (the round-1 dispatch:
+    // 128 rows from 512 rows up, else 64 x 64); CINDM_SIMT_MIN128 / CINDM_SIMT_MIN64 override the CTA thresholds.
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     }
-    dim3 grid(ceil_div(p.rows, 64), ceil_div(p.cout, 64));
-    conv1d_simt_kernel<InT, OutT><<<grid, 256, 0, st>>>(p);
+    const int tile128 = env_int("CINDM_SIMT_TILE128", 1), tile32 = env_int("CINDM_SIMT_TILE32", 1);
+    const int min128 = tile32 ? env_int("CINDM_SIMT_MIN128", sms / 2) : 0;
+    const int min64 = tile32 ? env_int("CINDM_SIMT_MIN64", sms) : 0;
+    if (tile128 && p.rows >= 512 && p.cout % 64 == 0) {
+        const int bn = p.cout % 128 == 0 ? 128 : 64;
+        const long long ctas = (long long)ceil_div(p.rows, 128) * (p.cout / bn);
+        if (ctas >= min128) {
+            dim3 grid(ceil_div(p.rows, 128), p.cout / bn);
+            if (bn == 128) conv1d_simt128_kernel<InT, OutT, 128><<<grid, 256, 0, st>>>(p);
+            else conv1d_simt128_kernel<InT, OutT, 64><<<grid, 256, 0, st>>>(p);
+            CINDM_CHECK_LAUNCH();
+            return 0;
+        }
+    }
+    const long long ctas64 = (long long)ceil_div(p.rows, 64) * ceil_div(p.cout, 64);
+    if (ctas64 < min64) {
+        dim3 grid(ceil_div(p.rows, 32), ceil_div(p.cout, 32));
+        conv1d_simt_kernel<InT, OutT, 32, 32><<<grid, 256, 0, st>>>(p);
+    } else {
+        dim3 grid(ceil_div(p.rows, 64), ceil_div(p.cout, 64));
+        conv1d_simt_kernel<InT, OutT, 64, 64><<<grid, 256, 0, st>>>(p);
+    }
     CINDM_CHECK_LAUNCH();
     return 0;
 }

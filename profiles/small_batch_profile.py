@@ -1,6 +1,6 @@
 """Per-kernel CUDA-event timings of ONE composed evaluation at a small slice count (C1: 50 slices by default).
 
-    python profiles/small_batch_profile.py [batch] [n_bodies] [n_composed]
+    python profiles/small_batch_profile.py [batch] [n_bodies] [n_composed] [precision engine]     (default fp16 tcgen05)
 """
 import ctypes
 import os
@@ -22,8 +22,10 @@ def main():
     dif = GaussianDiffusion1D(model, image_size=24, conditioned_steps=0, timesteps=1000, sampling_timesteps=1000)
     model.load_state_dict(init_unet_params(seed=0))
     dif.to("cuda:0")
-    dif.precision, dif.conv_engine = "fp16", "tcgen05"
-    model.precision, model.conv_engine = "fp16", "tcgen05"
+    prec = sys.argv[4] if len(sys.argv) > 4 else "fp16"
+    engine = sys.argv[5] if len(sys.argv) > 5 else "tcgen05"
+    dif.precision, dif.conv_engine = prec, engine
+    model.precision, model.conv_engine = prec, engine
     L = _lib.lib()
     x = torch.randn(b, 24 + 10 * nc, 4 * n, device="cuda")
     for rep in range(3):
