@@ -20,6 +20,7 @@ struct ConvParams {
     const void* in0; const void* in1; const float* w; const float* bias; const void* res; void* out;
     long long rows;          // S * Hout
     int c0, c1, cin, cout, taps, Hin, Hout, stride, pad, transposed;
+    int pos_major;           // 128-row kernel only: a tile holds ONE output position of 128 consecutive slices (see there)
 };
 
 // BM x BN tile (64 x 64, or 32 x 32 for launches that would otherwise leave most SMs without a CTA), 256 threads, each a
@@ -149,19 +150,33 @@ __global__ void __launch_bounds__(256, 2) conv1d_simt128_kernel(ConvParams p) {
     __shared__ __align__(16) float Bs[2][BK][BN];
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
-    const long long row0 = (long long)blockIdx.x * BM;
     const int co0 = blockIdx.y * BN;
+    // Row tiles.  Default: 128 consecutive rows of the flattened (slice, position) index.  pos_major (stride-1 same-length
+    // convs): tile = output position j = blockIdx.x % H of the 128 slices s0 .. s0 + 127.  Every row of the tile then reads
+    // input position j + tap - pad, so a tap that falls outside [0, H) is zero padding for the WHOLE tile and its K chunks are
+    // skipped: at H = 3 only 9 of the 15 (position, tap) blocks of a k = 5 conv exist (27 % of the network's dense MACs are
+    // such zeros).  A skipped product is fmaf(0, w, acc) = acc, so the results stay bit-identical.
+    const int tile_j = p.pos_major ? (int)(blockIdx.x % p.Hout) : 0;
+    const long long s0 = p.pos_major ? (long long)(blockIdx.x / p.Hout) * BM : 0;
+    const long long row0 = (long long)blockIdx.x * BM;
+    const long long n_slices = p.rows / p.Hout;
 
     // A-load role: 8 consecutive input channels of one row;  B-load role: TN consecutive output channels of one input channel
     const int a_row = tid >> 1, a_ci = (tid & 1) * 8;
     const long long arow = row0 + a_row;
-    const bool arow_ok = arow < p.rows;
-    const long long a_s = arow_ok ? arow / p.Hout : 0;
-    const int a_j = arow_ok ? (int)(arow - a_s * p.Hout) : 0;
+    const bool arow_ok = p.pos_major ? (s0 + a_row < n_slices) : (arow < p.rows);
+    const long long a_s = !arow_ok ? 0 : (p.pos_major ? s0 + a_row : arow / p.Hout);
+    const int a_j = !arow_ok ? 0 : (p.pos_major ? tile_j : (int)(arow - a_s * p.Hout));
     const int b_ci = tid >> 4, b_co = (tid & 15) * TN;
 
     const int cpt = (p.cin + BK - 1) / BK;               // K chunks per tap
-    const int nchunks = p.taps * cpt;
+    int c_begin = 0, c_end = p.taps * cpt;
+    if (p.pos_major) {                                   // taps with 0 <= tile_j + tap - pad < Hin: a contiguous range
+        const int tap_lo = p.pad - tile_j > 0 ? p.pad - tile_j : 0;
+        const int tap_hi = p.Hin + p.pad - tile_j < p.taps ? p.Hin + p.pad - tile_j : p.taps;
+        c_begin = tap_lo * cpt;
+        c_end = tap_hi * cpt;
+    }
     float av[8], bv[TN];
 
     auto fetch = [&](int chunk) {                        // global -> registers
@@ -223,12 +238,12 @@ __global__ void __launch_bounds__(256, 2) conv1d_simt128_kernel(ConvParams p) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc2[i][j] = 0ull;
 
-    fetch(0);
+    fetch(c_begin);
     stash(0);
     __syncthreads();
-    for (int chunk = 0; chunk < nchunks; ++chunk) {
-        const int buf = chunk & 1;
-        if (chunk + 1 < nchunks) fetch(chunk + 1);       // in flight during the FMAs below
+    for (int chunk = c_begin; chunk < c_end; ++chunk) {
+        const int buf = (chunk - c_begin) & 1;
+        if (chunk + 1 < c_end) fetch(chunk + 1);         // in flight during the FMAs below
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
             float b[TN];
@@ -248,7 +263,7 @@ __global__ void __launch_bounds__(256, 2) conv1d_simt128_kernel(ConvParams p) {
                 for (int i = 0; i < 4; ++i) acc2[i][j] = f32x2_fma(a2[i], bb, acc2[i][j]);
             }
         }
-        if (chunk + 1 < nchunks) stash(buf ^ 1);          // (the other buffer was last read before the previous barrier)
+        if (chunk + 1 < c_end) stash(buf ^ 1);            // (the other buffer was last read before the previous barrier)
         __syncthreads();
     }
     // ---- epilogue ----
@@ -259,7 +274,12 @@ __global__ void __launch_bounds__(256, 2) conv1d_simt128_kernel(ConvParams p) {
         for (int j = 0; j < TN; ++j) f32x2_unpack(acc2[i][j], acc[2 * i][j], acc[2 * i + 1][j]);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const long long r = row0 + ty * 8 + i;
+        long long r = row0 + ty * 8 + i;
+        if (p.pos_major) {
+            const long long sl = s0 + ty * 8 + i;
+            if (sl >= n_slices) continue;
+            r = sl * p.Hout + tile_j;
+        }
         if (r >= p.rows) continue;
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
@@ -296,11 +316,18 @@ static int conv_dispatch2(const ConvParams& p, cudaStream_t st) {
     const int min64 = tile32 ? env_int("CINDM_SIMT_MIN64", sms) : 0;
     if (tile128 && p.rows >= 512 && p.cout % 64 == 0) {
         const int bn = p.cout % 128 == 0 ? 128 : 64;
-        const long long ctas = (long long)ceil_div(p.rows, 128) * (p.cout / bn);
+        // position-major tiles (skip the all-padding taps) where they save >= 1/8 of the taps and the slices fill the tiles:
+        // k = 5 at H <= 6 (CINDM_SIMT_POSMAJOR=0: never)
+        const long long n_slices = p.rows / p.Hout;
+        ConvParams q = p;
+        q.pos_major = env_int("CINDM_SIMT_POSMAJOR", 1) && !p.transposed && p.stride == 1 && p.Hin == p.Hout && p.taps >= 3 &&
+                      p.Hout <= 2 * (p.taps - 1) && n_slices >= 1024;
+        const int row_tiles = q.pos_major ? ceil_div(n_slices, 128) * p.Hout : ceil_div(p.rows, 128);
+        const long long ctas = (long long)row_tiles * (p.cout / bn);
         if (ctas >= min128) {
-            dim3 grid(ceil_div(p.rows, 128), p.cout / bn);
-            if (bn == 128) conv1d_simt128_kernel<InT, OutT, 128><<<grid, 256, 0, st>>>(p);
-            else conv1d_simt128_kernel<InT, OutT, 64><<<grid, 256, 0, st>>>(p);
+            dim3 grid(row_tiles, p.cout / bn);
+            if (bn == 128) conv1d_simt128_kernel<InT, OutT, 128><<<grid, 256, 0, st>>>(q);
+            else conv1d_simt128_kernel<InT, OutT, 64><<<grid, 256, 0, st>>>(q);
             CINDM_CHECK_LAUNCH();
             return 0;
         }
@@ -334,6 +361,7 @@ int launch_conv_simt(const ConvLaunch& a, cudaStream_t st) {
     p.cin = a.w->cin; p.cout = a.w->cout; p.taps = a.w->taps;
     p.Hin = a.Hin; p.Hout = a.Hout; p.stride = a.stride; p.pad = a.pad; p.transposed = a.transposed;
     p.rows = a.S * a.Hout;
+    p.pos_major = 0;
     if (p.c0 + p.c1 != p.cin) return fail(-2, "conv: input channels do not match the weight");
     if (p.in1 && (p.c0 % 16) != 0) return fail(-2, "conv: concat split must be a multiple of 16 channels");
     if (p.rows == 0) return 0;

@@ -20,12 +20,17 @@ SETTINGS = {                       # name: environment
     "min128=74 min64=148": {"CINDM_SIMT_MIN128": "74", "CINDM_SIMT_MIN64": "148"},
     "min128=148 min64=296": {"CINDM_SIMT_MIN128": "148", "CINDM_SIMT_MIN64": "296"},
 }
-KEYS = ("CINDM_SIMT_TILE32", "CINDM_SIMT_MIN128", "CINDM_SIMT_MIN64")
+# large slice counts: position-major tiles of the 128-row kernel (taps that are all zero padding skipped) on / off
+SETTINGS_BIG = {
+    "row-major tiles (CINDM_SIMT_POSMAJOR=0)": {"CINDM_SIMT_POSMAJOR": "0"},
+    "default (position-major at H <= 8)": {},
+}
+KEYS = ("CINDM_SIMT_TILE32", "CINDM_SIMT_MIN128", "CINDM_SIMT_MIN64", "CINDM_SIMT_POSMAJOR")
 
 
 def main():
     out = {}
-    for hor, dim, sizes in ((24, 64, (50, 150, 500, 1500, 3000)), (44, 64, (50, 500)), (44, 96, (50,))):
+    for hor, dim, sizes in ((24, 64, (50, 150, 500, 1500, 3000, 43008)), (44, 64, (50, 500, 3000)), (44, 96, (50,))):
         model = TemporalUnet1D(horizon=hor, transition_dim=8, cond_dim=False, dim=dim, dim_mults=(1, 2, 4, 8), attention=True)
         dif = GaussianDiffusion1D(model, image_size=hor, conditioned_steps=0, timesteps=1000, sampling_timesteps=1000)
         model.load_state_dict(init_unet_params(unet_param_shapes(hor, 8, dim), seed=0, randomize_affine=True))
@@ -35,7 +40,7 @@ def main():
             t = torch.full((S,), 420, dtype=torch.long)
             ref = None
             row = {}
-            for name, env in SETTINGS.items():
+            for name, env in (SETTINGS_BIG if S >= 3000 else SETTINGS).items():
                 for k in KEYS:
                     os.environ.pop(k, None)
                 os.environ.update(env)

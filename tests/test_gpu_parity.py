@@ -400,6 +400,34 @@ def test_simt_conv_tile_variants_are_bit_identical(tmp_path):
         outs.append(np.load(out)["fp32"])
     assert np.isfinite(outs[0]).all() and np.array_equal(outs[0], outs[1])
 
+@pytest.mark.parametrize("slices", [37, 1100])
+def test_simt_dispatch_switches_are_bit_identical(diffusion, slices):
+    """fp32 path: the tile of a conv launch is chosen by its CTA count (32 x 32, 64 x 64, 128 rows; row-major or
+    position-major 128-row tiles that skip the all-padding taps).  Every choice sums each output in the same (tap, ci)
+    order, so a candidate's result cannot depend on the batch it was sampled in.  The switches are read per launch."""
+    set_precision(diffusion, "fp32")
+    x = torch.randn(slices, 24, 8, generator=torch.Generator().manual_seed(slices))
+    t = torch.full((slices,), 420, dtype=torch.long)
+    keys = ("CINDM_SIMT_TILE32", "CINDM_SIMT_TILE128", "CINDM_SIMT_MIN128", "CINDM_SIMT_MIN64", "CINDM_SIMT_POSMAJOR")
+    saved = {k: os.environ.pop(k, None) for k in keys}
+    outs = []
+    try:
+        for env in ({}, {"CINDM_SIMT_POSMAJOR": "0"}, {"CINDM_SIMT_TILE32": "0"}, {"CINDM_SIMT_TILE128": "0"},
+                    {"CINDM_SIMT_MIN128": "1000000", "CINDM_SIMT_MIN64": "1000000"}, {"CINDM_SIMT_MIN128": "1", "CINDM_SIMT_MIN64": "1"}):
+            for k in keys:
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            outs.append(diffusion.model(x, t, None).cpu())
+    finally:
+        for k in keys:
+            os.environ.pop(k, None)
+            if saved[k] is not None:
+                os.environ[k] = saved[k]
+    assert torch.isfinite(outs[0]).all()
+    for o in outs[1:]:
+        assert torch.equal(outs[0], o)
+
+
 @pytest.mark.parametrize("case", sorted(META["compose_cases"]))
 def test_composed_eps_tcgen05_fp16(diffusion, golden, case):
     set_precision(diffusion, "fp16", "tcgen05")
