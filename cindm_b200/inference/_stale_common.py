@@ -62,6 +62,26 @@ def build_diffusion(args, device):
     return diffusion
 
 
+def build_single_step_diffusion(args, device):
+    """The single-step model of inference_1d_composing_time_steps.py:180-199: horizon = 2 * conditioned_steps (4 condition +
+    4 rollout frames), image_size = conditioned_steps.  A horizon-8 U-Net is not one the 16-bit tensor-core kernels are built
+    for: it runs on the generic fp32 CUDA kernels whatever --precision says (announced)."""
+    k = args.conditioned_steps
+    setup_seed(args.seed)
+    model = TemporalUnet1D(horizon=2 * k, transition_dim=2 * args.num_features, cond_dim=False, dim=64,
+                           dim_mults=(1, 2, 4, 8), attention=args.attention, seed=args.seed)
+    diffusion = GaussianDiffusion1D(model, image_size=k, conditioned_steps=k, timesteps=1000,
+                                    sampling_timesteps=args.sample_steps, loss_type="l1").to(device)
+    if args.checkpoint_path_single_step:
+        ckpt = torch.load(args.checkpoint_path_single_step, map_location="cpu", weights_only=False)
+        diffusion.load_state_dict(ckpt["model"])
+    if not model.tensor_core_model and (args.precision, args.conv_engine) != ("fp32", "simt"):
+        print(f"single-step model (horizon {2 * k}): running --precision fp32 --conv_engine simt "
+              f"(--precision {args.precision} --conv_engine {args.conv_engine} is built for the horizon-24 model)")
+    diffusion.precision, diffusion.conv_engine, diffusion.seed = "fp32", "simt", args.seed
+    return diffusion
+
+
 def load_condition(args, n_bodies, output_steps):
     """cond [B, conditioned_steps, n_bodies*4] (normalised): --cond_npy, else the first unshuffled batch of the reference's
     dataset (the reference shuffles its DataLoader, inference_1d_composing_time_steps.py:165; any batch of the split serves)."""

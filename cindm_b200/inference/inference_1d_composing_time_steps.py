@@ -1,7 +1,8 @@
 """Flag-compatible mirror of the reference's inference/inference_1d_composing_time_steps.py (flags :25-67).
 
 `--time_compose_method autoregress` (the default, reference :179-217) samples n_composed + 1 chained 20-frame windows with
-GaussianDiffusion1D.autoregress_time_compose_sample on the conditioned 4 + 20-frame model; `EBMs_compose` (:171-178, whose
+GaussianDiffusion1D.autoregress_time_compose_sample on the conditioned 4 + 20-frame model (`--is_single_step_prediction True`:
+rollout_steps * (1 + n_composed) / 4 chained 4-frame windows on the 4 + 4-frame model, :180-206); `EBMs_compose` (:171-178, whose
 `sample(is_composing_time=True)` call is broken at the reference's HEAD) runs the method that branch was written for,
 composing_time_sample: all windows denoised together with the conditions chained at every step; `SimuSolver` (:330-347) rolls
 the CUDA ground-truth simulator.  direct / GNS / Forward_model need other models (out of scope) and raise."""
@@ -30,7 +31,10 @@ def analyse(args):
     cond = common.load_condition(args, n_bodies, r * (nc + 1)).to(device)
     b = cond.shape[0]
     if args.time_compose_method == "autoregress":
-        diffusion = common.build_diffusion(args, device)
+        # (:180-199) the single-step model: conditioned_steps condition frames + conditioned_steps rollout frames (horizon 8),
+        # loaded from --checkpoint_path_single_step; it runs on the generic fp32 CUDA kernels
+        diffusion = (common.build_single_step_diffusion(args, device) if args.is_single_step_prediction
+                     else common.build_diffusion(args, device))
         y = diffusion.autoregress_time_compose_sample(batch_size=b, cond=cond, n_composed=nc,
                                                       is_single_step_prediction=args.is_single_step_prediction,
                                                       prediction_steps=r * (1 + nc))

@@ -8,8 +8,10 @@ include/cindm_b200.h (hand-written sm_100a CUDA).  PyTorch only owns device memo
 
 Fast-path subset (anything else raises NotImplementedError — there is no silent fallback):
 objective 'pred_noise'; compose_mode in {mean-inside, sum-inside, mean, noise_sum}; design_guidance in {standard,
-standard-alpha}[-recurrence-K]; DDPM (sampling_timesteps == timesteps) or DDIM; model horizon 24, dim 64, attention=True.
-conditioned_steps = 0 with cond = None is the inverse-design path; conditioned_steps = k > 0 (image_size + k = 24, the
+standard-alpha}[-recurrence-K]; DDPM (sampling_timesteps == timesteps) or DDIM; attention=True; model horizon 24, dim 64 on
+the 16-bit tensor-core kernels, any even horizon in [8, 48] / dim multiple of 16 (the 44-step, Unet_dim-96 and single-step
+models) on the generic fp32 kernels.
+conditioned_steps = 0 with cond = None is the inverse-design path; conditioned_steps = k > 0 (image_size + k = horizon, the
 "basic model": 4 condition frames + 20 rollout frames) is the conditioned model behind model_predictions / ddim_sample
 with cond, autoregress_time_compose_sample and composing_time_sample.
 """
@@ -625,17 +627,29 @@ class GaussianDiffusion1D:
                                         noise=None, img=None, pairs=None):
         """Chained windows (reference :2239-2327): window i is sampled with the DDIM-form loop over every (time, time_next)
         pair, conditioned on the last conditioned_steps frames of window i - 1 (the given cond for i = 0); returns
-        [B, (n_composed + 1) * rollout_steps, F].  Optional parity inputs: img [windows, B, rollout, F] (the reference's
-        per-window randn) and noise [windows, pairs, 1, B, rollout, F] (its per-pair randn_like)."""
-        if is_single_step_prediction:
-            raise NotImplementedError("is_single_step_prediction needs the cond-4 / rollout-4 model (horizon 8): not on the CUDA fast path")
+        [B, (n_composed + 1) * rollout_steps, F].  is_single_step_prediction (:2252-2291, meant for the cond-4 / rollout-4
+        model, horizon 8): ceil(prediction_steps / conditioned_steps) windows into [B, prediction_steps, F] instead.
+        Optional parity inputs: img [windows, B, rollout, F] (the reference's per-window randn) and noise
+        [windows, pairs, 1, B, rollout, F] (its per-pair randn_like)."""
         k, r = self.conditioned_steps, self.rollout_steps
         if not k:
             raise NotImplementedError("autoregress_time_compose_sample runs on a conditioned model (conditioned_steps > 0)")
+        if is_single_step_prediction:
+            windows, total = -(-prediction_steps // k), prediction_steps
+            if windows * r > total:
+                # the reference fails here too: its `img_composed[:, i*r:(i+1)*r] = img` (:2289) no longer fits
+                raise ValueError(f"is_single_step_prediction: {windows} windows of {r} frames do not fit prediction_steps="
+                                 f"{prediction_steps} (the reference's slice assignment :2289 raises); it is meant for the model "
+                                 "with rollout_steps == conditioned_steps")
+            if windows * r < total:
+                raise NotImplementedError("is_single_step_prediction with rollout_steps < conditioned_steps leaves the tail of "
+                                          "the reference's output at its initial randn: not reproduced")
+        else:
+            windows, total = n_composed + 1, (n_composed + 1) * r
         cond = cond.to(self.device, torch.float32)
         b, f = cond.shape[0], cond.shape[2]
-        out = torch.empty((b, (n_composed + 1) * r, f), device=self.device, dtype=torch.float32)
-        for i in range(n_composed + 1):
+        out = torch.empty((b, total, f), device=self.device, dtype=torch.float32)
+        for i in range(windows):
             seed = self._window_seed(i)
             frames = self._initial_frames(b, r, f, seed, None if img is None else img[i])
             state = torch.cat([cond[:, -k:], frames], dim=1).contiguous()

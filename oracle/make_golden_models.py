@@ -11,7 +11,9 @@ This script imports the UNMODIFIED reference (oracle/ref_shim.py), builds those 
 
   * epsilon for a seeded batch of slices at two timesteps, and every block's activation for two slices (forward hooks);
   * a composed epsilon (`model_predictions`, 4 bodies, two windows, mean-inside) on that model;
-  * a teacher-forced `p_sample_compose_inside` trajectory with the recorded `randn_like` draws (guidance, recurrence).
+  * a teacher-forced `p_sample_compose_inside` trajectory with the recorded `randn_like` draws (guidance, recurrence);
+and, for the single-step model of inference/inference_1d_composing_time_steps.py:180-206 (4 condition + 4 rollout frames,
+horizon 8), a whole `autoregress_time_compose_sample(is_single_step_prediction=True)` run with its draws recorded.
 
 -> tests/golden/unet_models.npz (+ the "model_cases" entry of tests/golden/meta.json).
 """
@@ -132,16 +134,75 @@ def gen_model(name, horizon, dim, ns, out):
     return {"horizon": horizon, "dim": dim, "params": n_params, "keys": len(net.state_dict())}
 
 
+SINGLE_STEP = {"horizon": 8, "dim": 64, "conditioned_steps": 4, "batch": 2, "prediction_steps": 12, "pairs": 3, "eta": 0.3,
+               "grid_timesteps": 500}
+
+
+def gen_single_step(out):
+    """autoregress_time_compose_sample(is_single_step_prediction=True) (model/diffusion_1d.py:2252-2291) on the cond-4 /
+    rollout-4 model.  As in make_golden.gen_conditioned the DDIM grid is built from num_timesteps = 500 on the reference
+    OBJECT (code untouched): at t = 999 x_start amplifies fp32 rounding by 2e4 and a whole-run golden would be useless."""
+    c = SINGLE_STEP
+    m = ref_shim.load()
+    k = c["conditioned_steps"]
+    sd = init_unet_params(unet_param_shapes(c["horizon"], 8, c["dim"]), seed=0, randomize_affine=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = m.TemporalUnet1D(horizon=c["horizon"], transition_dim=8, cond_dim=False, dim=c["dim"], dim_mults=(1, 2, 4, 8),
+                               attention=True)
+        dif = m.GaussianDiffusion1D(net, image_size=k, conditioned_steps=k, timesteps=1000, sampling_timesteps=c["pairs"],
+                                    loss_type="l1", ddim_sampling_eta=c["eta"])
+    net.load_state_dict(sd)
+    dif.eval()
+    dif.num_timesteps = c["grid_timesteps"]
+    cond = seeded((c["batch"], k, 8), 61) * 0.5
+    real_randn_like, real_randn = torch.randn_like, torch.randn
+    gen = torch.Generator().manual_seed(62)
+    draws = []
+
+    def logged_randn_like(t, **kw):
+        z = real_randn(t.shape, generator=gen, dtype=t.dtype)
+        draws.append(z)
+        return z
+
+    def logged_randn(*shape, **kw):
+        shape = tuple(shape[0]) if len(shape) == 1 and not isinstance(shape[0], int) else tuple(shape)
+        z = real_randn(shape, generator=gen)
+        draws.append(z)
+        return z
+
+    torch.randn_like, torch.randn = logged_randn_like, logged_randn
+    try:
+        m.grad_mean_list.clear()
+        with torch.no_grad():
+            y = dif.autoregress_time_compose_sample(batch_size=c["batch"], cond=cond, n_composed=1,
+                                                    is_single_step_prediction=True, prediction_steps=c["prediction_steps"])
+    finally:
+        torch.randn_like, torch.randn = real_randn_like, real_randn
+    windows = c["prediction_steps"] // k
+    per = 1 + c["pairs"]
+    assert len(draws) == 1 + windows * per                       # img_composed, then per window: img + one draw per pair
+    times = torch.linspace(-1, c["grid_timesteps"] - 1, steps=c["pairs"] + 1)
+    times = list(reversed(times.int().tolist()))
+    out["single:cond"] = cond.numpy()
+    out["single:x_init"] = torch.stack([draws[1 + w * per] for w in range(windows)]).numpy()
+    out["single:noise"] = torch.stack([torch.stack(draws[2 + w * per: 1 + (w + 1) * per]) for w in range(windows)]).numpy()
+    out["single:out"] = y.numpy()
+    out["single:pairs"] = np.asarray(list(zip(times[:-1], times[1:])), dtype=np.int32)
+    return dict(c, windows=windows)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     ns = reference_objective_namespace()
     out, info = {}, {}
+    single = gen_single_step(out)
     for name, (horizon, dim) in MODEL_CASES.items():
         info[name] = gen_model(name, horizon, dim, ns, out)
         print(name, info[name])
     np.savez_compressed(os.path.join(GOLDEN, "unet_models.npz"), **out)
     meta = json.load(open(os.path.join(GOLDEN, "meta.json")))
-    meta["model_cases"] = {"models": info, "compose": list(COMPOSE), "traj": [list(v) if isinstance(v, tuple) else v for v in TRAJ]}
+    meta["model_cases"] = {"models": info, "compose": list(COMPOSE), "traj": [list(v) if isinstance(v, tuple) else v for v in TRAJ],
+                           "single_step": single}
     json.dump(meta, open(os.path.join(GOLDEN, "meta.json"), "w"), indent=1)
     print("unet_models.npz", os.path.getsize(os.path.join(GOLDEN, "unet_models.npz")))
 

@@ -94,7 +94,8 @@ def test_autoregress_time_compose_sample(conditioned, golden, precision, engine,
         free = dif.autoregress_time_compose_sample(3, torch.from_numpy(g["cond"])[:1].repeat(3, 1, 1), 1)
         assert tuple(free.shape) == (3, 40, 8) and torch.isfinite(free).all()
         assert not torch.equal(free[:, :20], free[:, 20:])
-        with pytest.raises(NotImplementedError):
+        # single-step prediction on THIS model (20-frame windows every 4 frames) overruns its output in the reference too (:2289)
+        with pytest.raises(ValueError, match="do not fit"):
             dif.autoregress_time_compose_sample(2, torch.from_numpy(g["cond"]), 1, is_single_step_prediction=True)
     finally:
         dif.sampling_timesteps, dif.ddim_sampling_eta = keep

@@ -159,3 +159,35 @@ def test_driver_cli_with_the_44_step_model_names(tmp_path):
     assert np.isfinite(rec["pred"]).all() and np.abs(rec["pred"]).max() <= 1.0
     rec = main(common + ["--model_name=Diffusion_cond-0_rollout-44_bodies-2_Unet_dim-96", "--Unet_dim=96"])[0]
     assert rec["pred"].shape == (4, 44, 8) and np.isfinite(rec["pred"]).all()
+
+
+def test_single_step_autoregression_vs_reference(golden, tmp_path):
+    """`--is_single_step_prediction` (inference_1d_composing_time_steps.py:180-206): the cond-4 / rollout-4 model (horizon 8,
+    U-Net levels of 8 / 4 / 2 / 1 positions) chained over ceil(prediction_steps / 4) windows, against a whole run of the
+    reference's autoregress_time_compose_sample with its draws replayed; then the driver mirror with the flag."""
+    from cindm_b200.model.diffusion_1d import GaussianDiffusion1D, TemporalUnet1D
+    from cindm_b200.model.params import init_unet_params, unet_param_shapes
+    c = META["model_cases"]["single_step"]
+    g = golden("unet_models.npz")
+    k = c["conditioned_steps"]
+    model = TemporalUnet1D(horizon=c["horizon"], transition_dim=8, cond_dim=False, dim=c["dim"], dim_mults=(1, 2, 4, 8), attention=True)
+    dif = GaussianDiffusion1D(model, image_size=k, conditioned_steps=k, timesteps=1000, sampling_timesteps=c["pairs"],
+                              loss_type="l1", ddim_sampling_eta=c["eta"])
+    model.load_state_dict(init_unet_params(unet_param_shapes(c["horizon"], 8, c["dim"]), seed=0, randomize_affine=True))
+    dif.to("cuda:0")
+    pairs = [tuple(int(v) for v in p) for p in g["single:pairs"]]
+    noise = torch.from_numpy(g["single:noise"]).unsqueeze(2)                      # [windows, pairs, 1, B, 4, 8]
+    out = dif.autoregress_time_compose_sample(c["batch"], torch.from_numpy(g["single:cond"]), 1, True, c["prediction_steps"],
+                                              noise=noise, img=torch.from_numpy(g["single:x_init"]), pairs=pairs)
+    assert tuple(out.shape) == (c["batch"], c["prediction_steps"], 8)
+    for w in range(c["windows"]):                                                  # errors chain from window to window
+        assert rel_l2(out[:, k * w:k * (w + 1)], g["single:out"][:, k * w:k * (w + 1)]) < 2e-5 * (w + 1), w
+    free = dif.autoregress_time_compose_sample(3, torch.from_numpy(g["single:cond"])[:1].repeat(3, 1, 1), 1, True, 40)
+    assert tuple(free.shape) == (3, 40, 8) and torch.isfinite(free).all() and not torch.equal(free[:, :4], free[:, 4:8])
+
+    from cindm_b200.inference import inference_1d_composing_time_steps as ts
+    cond_file = tmp_path / "cond.npy"
+    np.save(cond_file, g["single:cond"])
+    y = ts.main(["--is_single_step_prediction=True", "--n_composed=1", "--sample_steps=5", f"--cond_npy={cond_file}",
+                 f"--results_dir={tmp_path}", "--val_batch_size=2"])
+    assert tuple(y.shape) == (2, 40, 8) and torch.isfinite(y).all()

@@ -256,3 +256,22 @@ def test_other_model_shapes_sampler_matches_reference(golden, case):
         assert rel_l2(img, g[f"{case}:traj_img_after_{si}"]) < 1e-5, (si, t)
         img = torch.from_numpy(g[f"{case}:traj_img_after_{si}"])
     assert not noise
+
+
+def test_oracle_single_step_autoregression_reproduces_the_reference(golden):
+    """autoregress_time_compose_sample(is_single_step_prediction=True) on the cond-4 / rollout-4 model (horizon 8: levels of
+    8, 4, 2 and 1 positions): three chained 4-frame windows, every draw replayed in the reference's order."""
+    from cindm_b200.model.params import init_unet_params, unet_param_shapes
+    c = META["model_cases"]["single_step"]
+    g = golden("unet_models.npz")
+    sd = init_unet_params(unet_param_shapes(c["horizon"], 8, c["dim"]), seed=0, randomize_affine=True)
+    tabs = sampler_ref.cosine_schedule_tables()
+    pairs = [tuple(int(v) for v in p) for p in g["single:pairs"]]
+    noise = [z for w in torch.from_numpy(g["single:noise"]) for z in w]
+    out = sampler_ref.autoregress_time_compose(sd, tabs, torch.from_numpy(g["single:cond"]), list(torch.from_numpy(g["single:x_init"])),
+                                               lambda shape: noise.pop(0), pairs=pairs, eta=c["eta"],
+                                               conditioned_steps=c["conditioned_steps"])
+    assert not noise and tuple(out.shape) == (c["batch"], c["prediction_steps"], 8)
+    k = c["conditioned_steps"]
+    for w in range(c["windows"]):
+        assert rel_l2(out[:, k * w:k * (w + 1)], g["single:out"][:, k * w:k * (w + 1)]) < 1e-5 * (w + 1), w
