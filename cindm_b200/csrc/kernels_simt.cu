@@ -28,9 +28,10 @@ struct ConvParams {
 // current one is multiplied (one __syncthreads per chunk: with few CTAs per SM the K loop is latency-bound otherwise).
 // Every accumulator sums its products in (tap, ci) order whatever the tile, so all instances (and the 128-row kernel below)
 // give bit-identical results.
-template <typename InT, typename OutT, int BM = 64, int BN = 64>
+template <typename InT, typename OutT, int BM = 64, int BN = 64, int BK = 16>
 __global__ void __launch_bounds__(256) conv1d_simt_kernel(ConvParams p) {
-    constexpr int TM = BM / 16, TN = BN / 16, BK = 16;
+    constexpr int TM = BM / 16, TN = BN / 16;
+    constexpr int AE = BM * BK / 256, BE = BK * BN / 256;       // elements of the A / B chunk one thread moves
     __shared__ float As[2][BK][BM + 4];
     __shared__ float Bs[2][BK][BN];
     const int tid = threadIdx.x;
@@ -38,18 +39,18 @@ __global__ void __launch_bounds__(256) conv1d_simt_kernel(ConvParams p) {
     const long long row0 = (long long)blockIdx.x * BM;
     const int co0 = blockIdx.y * BN;
 
-    // A-load role: TM consecutive input channels of one row
-    const int a_row = tid / (16 / TM), a_ci = (tid % (16 / TM)) * TM;
+    // A-load role: AE consecutive input channels of one row
+    const int a_row = tid / (BK / AE), a_ci = (tid % (BK / AE)) * AE;
     const long long arow = row0 + a_row;
     const bool arow_ok = arow < p.rows;
     const long long a_s = arow_ok ? arow / p.Hout : 0;
     const int a_j = arow_ok ? (int)(arow - a_s * p.Hout) : 0;
-    // B-load role: TN consecutive output channels of one input channel
-    const int b_ci = tid >> 4, b_co = (tid & 15) * TN;
+    // B-load role: BE consecutive output channels of one input channel
+    const int b_ci = tid / (BN / BE), b_co = (tid % (BN / BE)) * BE;
 
     const int cpt = (p.cin + BK - 1) / BK;               // K chunks per tap
     const int nchunks = p.taps * cpt;
-    float av[TM], bv[TN];
+    float av[AE], bv[BE];
 
     auto fetch = [&](int chunk) {                        // global -> registers
         const int tap = chunk / cpt, ci0 = (chunk - tap * cpt) * BK;
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(256) conv1d_simt_kernel(ConvParams p) {
         }
         pos_ok = pos_ok && arow_ok;
 #pragma unroll
-        for (int q = 0; q < TM; ++q) av[q] = 0.f;
+        for (int q = 0; q < AE; ++q) av[q] = 0.f;
         const int ci = ci0 + a_ci;
         if (pos_ok && ci < p.cin) {
             const InT* src;
@@ -75,24 +76,24 @@ __global__ void __launch_bounds__(256) conv1d_simt_kernel(ConvParams p) {
             else           { src = (const InT*)p.in1; cw = p.c1; cbase = ci - p.c0; }
             const InT* ptr = src + ((a_s * p.Hin + pos) * (long long)cw + cbase);
 #pragma unroll
-            for (int q = 0; q < TM; ++q)
+            for (int q = 0; q < AE; ++q)
                 if (ci + q < p.cin) av[q] = to_f32<InT>(ptr[q]);
         }
         const int bci = ci0 + b_ci;
 #pragma unroll
-        for (int q = 0; q < TN; ++q) bv[q] = 0.f;
+        for (int q = 0; q < BE; ++q) bv[q] = 0.f;
         if (bci < p.cin) {
             const float* wp = p.w + ((long long)tap * p.cin + bci) * p.cout + co0 + b_co;
 #pragma unroll
-            for (int q = 0; q < TN; ++q)
+            for (int q = 0; q < BE; ++q)
                 if (co0 + b_co + q < p.cout) bv[q] = wp[q];
         }
     };
     auto stash = [&](int buf) {                          // registers -> shared memory (A transposed into As[ci][row])
 #pragma unroll
-        for (int q = 0; q < TM; ++q) As[buf][a_ci + q][a_row] = av[q];
+        for (int q = 0; q < AE; ++q) As[buf][a_ci + q][a_row] = av[q];
 #pragma unroll
-        for (int q = 0; q < TN; ++q) Bs[buf][b_ci][b_co + q] = bv[q];
+        for (int q = 0; q < BE; ++q) Bs[buf][b_ci][b_co + q] = bv[q];
     };
 
     float acc[TM][TN];
@@ -335,10 +336,12 @@ static int conv_dispatch2(const ConvParams& p, cudaStream_t st) {
     const long long ctas64 = (long long)ceil_div(p.rows, 64) * ceil_div(p.cout, 64);
     if (ctas64 < min64) {
         dim3 grid(ceil_div(p.rows, 32), ceil_div(p.cout, 32));
-        conv1d_simt_kernel<InT, OutT, 32, 32><<<grid, 256, 0, st>>>(p);
+        // 64-channel K chunks where they divide the input channels (no zero-padded chunk tail), else 16
+        if (p.cin % 64 == 0) conv1d_simt_kernel<InT, OutT, 32, 32, 64><<<grid, 256, 0, st>>>(p);
+        else conv1d_simt_kernel<InT, OutT, 32, 32, 16><<<grid, 256, 0, st>>>(p);
     } else {
         dim3 grid(ceil_div(p.rows, 64), ceil_div(p.cout, 64));
-        conv1d_simt_kernel<InT, OutT, 64, 64><<<grid, 256, 0, st>>>(p);
+        conv1d_simt_kernel<InT, OutT, 64, 64, 16><<<grid, 256, 0, st>>>(p);
     }
     CINDM_CHECK_LAUNCH();
     return 0;
