@@ -58,8 +58,19 @@ def build_diffusion(args, device):
     if args.checkpoint_path_basic_model:
         ckpt = torch.load(args.checkpoint_path_basic_model, map_location="cpu", weights_only=False)
         diffusion.load_state_dict(ckpt["model"])
-    diffusion.precision, diffusion.conv_engine, diffusion.seed = args.precision, args.conv_engine, args.seed
+    precision, engine = select_kernels(model, args)
+    diffusion.precision, diffusion.conv_engine, diffusion.seed = precision, engine, args.seed
     return diffusion
+
+
+def select_kernels(model, args):
+    """(--precision, --conv_engine) as given for the horizon-24 / dim-64 model; any other model shape (other
+    --conditioned_steps / --rollout_steps, the single-step model) runs on the generic fp32 CUDA kernels, announced."""
+    if model.tensor_core_model or (args.precision, args.conv_engine) == ("fp32", "simt"):
+        return args.precision, args.conv_engine
+    print(f"model horizon {model.horizon}: running --precision fp32 --conv_engine simt "
+          f"(--precision {args.precision} --conv_engine {args.conv_engine} is built for the horizon-24, dim-64 model)")
+    return "fp32", "simt"
 
 
 def build_single_step_diffusion(args, device):
@@ -75,10 +86,8 @@ def build_single_step_diffusion(args, device):
     if args.checkpoint_path_single_step:
         ckpt = torch.load(args.checkpoint_path_single_step, map_location="cpu", weights_only=False)
         diffusion.load_state_dict(ckpt["model"])
-    if not model.tensor_core_model and (args.precision, args.conv_engine) != ("fp32", "simt"):
-        print(f"single-step model (horizon {2 * k}): running --precision fp32 --conv_engine simt "
-              f"(--precision {args.precision} --conv_engine {args.conv_engine} is built for the horizon-24 model)")
-    diffusion.precision, diffusion.conv_engine, diffusion.seed = "fp32", "simt", args.seed
+    precision, engine = select_kernels(model, args)
+    diffusion.precision, diffusion.conv_engine, diffusion.seed = precision, engine, args.seed
     return diffusion
 
 

@@ -118,3 +118,35 @@ def test_every_sample_call_gets_its_own_philox_stream():
     assert len(set(seeds)) == len(seeds)
     assert sample_stream_seed(7, 0) == 7                       # the first call of a run keeps the user's seed
     assert all(0 <= s < 2 ** 64 for s in seeds)
+
+
+def test_other_model_shapes_host_logic():
+    """Host side of the model shapes beyond horizon 24 / dim 64 (no GPU): key inventories follow the reference's level structure,
+    unsupported shapes are refused up front, the older drivers pick the fp32 kernels for them, and the single-step window
+    arithmetic is checked before anything is launched."""
+    from types import SimpleNamespace
+    import torch
+    from cindm_b200.inference._stale_common import select_kernels
+    from cindm_b200.model.diffusion_1d import GaussianDiffusion1D, TemporalUnet1D
+    from cindm_b200.model.params import down_samplings, unet_param_shapes
+    assert [down_samplings(h) for h in (24, 8, 44, 20, 10)] == [3, 3, 2, 2, 1]
+    with pytest.raises(ValueError):
+        down_samplings(45)
+    assert len(unet_param_shapes(24, 8, 64)) == 234                      # + 13 schedule buffers = the 247-key state dict
+    k44 = unet_param_shapes(44, 8, 64)
+    assert len(k44) == 230 and "downs.2.3.conv.weight" not in k44 and "ups.0.3.conv.weight" not in k44
+    assert "downs.1.3.conv.weight" in k44 and "ups.1.3.conv.weight" in k44 and k44["mid_block1.blocks.0.block.0.weight"] == (512, 512, 5)
+    assert unet_param_shapes(44, 8, 96)["downs.3.1.blocks.1.block.0.weight"] == (768, 768, 5)
+    for bad in (dict(horizon=45), dict(horizon=64), dict(dim=100), dict(dim_mults=(1, 2, 4))):
+        kw = dict(horizon=24, transition_dim=8, cond_dim=False, dim=64, dim_mults=(1, 2, 4, 8), attention=True)
+        kw.update(bad)
+        with pytest.raises((NotImplementedError, ValueError)):
+            TemporalUnet1D(**kw)
+    fast, slow = SimpleNamespace(tensor_core_model=True, horizon=24), SimpleNamespace(tensor_core_model=False, horizon=8)
+    args = SimpleNamespace(precision="fp16", conv_engine="tcgen05")
+    assert select_kernels(fast, args) == ("fp16", "tcgen05") and select_kernels(slow, args) == ("fp32", "simt")
+    model = TemporalUnet1D(horizon=24, transition_dim=8, cond_dim=False, dim=64, dim_mults=(1, 2, 4, 8), attention=True)
+    assert model.tensor_core_model
+    dif = GaussianDiffusion1D(model, image_size=20, conditioned_steps=4, timesteps=1000, sampling_timesteps=4)
+    with pytest.raises(ValueError, match="do not fit"):                  # 10 windows of 20 frames into 40: the reference's :2289 fails too
+        dif.autoregress_time_compose_sample(2, torch.zeros(2, 4, 8), 1, is_single_step_prediction=True, prediction_steps=40)
