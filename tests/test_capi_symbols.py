@@ -21,6 +21,25 @@ def declared_symbols():
     return sorted(set(re.findall(r"\b(cindm_[a-z0-9_]+)\s*\(", text)))
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/cindm_b200.h must compile as C99 (no C++, no torch types) and a C program that
+    links the library must resolve every entry point it names."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not on PATH")
+    src = tmp_path / "use_header.c"
+    calls = "\n".join(f"    p[{i}] = (void*){name};" for i, name in enumerate(declared_symbols()))
+    src.write_text('#include "cindm_b200.h"\n#include <stdio.h>\nint main(void) {\n'
+                   f"    void* p[{len(declared_symbols())}];\n{calls}\n"
+                   '    cindm_config c = {24, 8, 64, 1000};\n    printf("%d %p\\n", c.horizon + cindm_version(), p[0]);\n    return 0;\n}\n')
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-Wno-pedantic", "-I", inc, "-fsyntax-only", str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_header_and_binding_agree():
     from cindm_b200 import _lib
     assert declared_symbols() == _lib.exported_symbols()
