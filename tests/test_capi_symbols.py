@@ -75,6 +75,31 @@ def test_host_only_entry_points(library):
     assert list(cover) == [1] * 10 + [2] * 10 + [3] * 4 + [2] * 10 + [1] * 10
 
 
+def test_index_maps_host_entry_point_vs_oracle_property(library):
+    """cindm_build_index_maps is pure host code: window starts, lexicographic pair list and cover counts equal the oracle's
+    (itself pinned to maps recovered by probing the reference, tests/golden/index_maps.npz) for ANY body count, window count,
+    window stride and model horizon -- 24, the 44-step models, the single-step model."""
+    from hypothesis import given, settings, strategies as st
+    from cindm_b200 import _lib
+    from oracle import sampler_ref
+    L = _lib.lib()
+
+    @settings(max_examples=200, deadline=None)
+    @given(n=st.integers(2, 10), nc=st.integers(0, 6), horizon=st.sampled_from([8, 10, 20, 24, 44, 48]), data=st.data())
+    def check(n, nc, horizon, data):
+        start = data.draw(st.integers(1, horizon - 1))                    # the reference asserts compose_start_step < horizon (:1679)
+        ref = sampler_ref.index_maps(n, nc, start, horizon)
+        W, P, T = nc + 1, n * (n - 1) // 2, horizon + nc * start
+        win, pi, pj, cover = (ctypes.c_int32 * W)(), (ctypes.c_int32 * P)(), (ctypes.c_int32 * P)(), (ctypes.c_int32 * T)()
+        _lib.check(L.cindm_build_index_maps(n, nc, start, horizon, win, pi, pj, cover))
+        assert list(win) == ref["win_t0"]
+        assert list(zip(pi, pj)) == ref["pairs"]
+        assert list(cover) == ref["cover"] and ref["t_total"] == T
+        assert sum(cover) == W * horizon                                  # every window row is counted exactly once
+
+    check()
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     from cindm_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)
