@@ -97,3 +97,44 @@ def test_split_sizes_and_clipping(tmp_path):
         NBodyDataset(dataset="nbody-4", dataset_path=str(tmp_path))
     with pytest.raises(IndexError):
         train.get(train.len())
+
+
+def test_generator_draws_initial_states_in_the_reference_order(golden):
+    """cindm_b200.data.nbody_simulation consumes Python's `random` exactly like the reference's generator (add_body per body,
+    then the colour draws): the fixture was minted by executing the reference's own statements (oracle/make_golden_generator.py),
+    so a seeded run starts from the states the reference would start from.  Flags and file name as in the reference."""
+    import random
+    from cindm_b200.data import nbody_simulation as gen
+    g = golden("nbody_generator.npz")
+    for name in (k for k in g.files if ":" not in k):
+        seed, n = int(name.split("_")[0][4:]), int(name.split("_n")[1])
+        random.seed(seed)
+        states = gen.sample_initial_states(g[name].shape[0], n)
+        assert np.array_equal(states, g[name]), name
+        assert random.random() == float(g[name + ":next_random"])          # same number of draws consumed
+        assert states[..., :2].min() >= 20 and states[..., :2].max() <= 180 and np.all(states[..., :2] == np.round(states[..., :2]))
+    args = gen.build_parser().parse_args([])
+    assert (args.n_bodies, args.n_simulations, args.vx, args.vy) == (2, 2, 100, 100)          # data/nbody_simulation.py:23-30
+    assert gen.trajectory_filename("dataset/nbody_dataset", 2, 2, 100) == \
+        "dataset/nbody_dataset/nbody-2/speed-100/trajectory_balls_2_simu_2_steps_1000.npy"   # :50
+    with pytest.raises(ValueError):
+        gen.main(["--n_bodies=9"])
+
+
+@pytest.mark.gpu
+def test_generator_end_to_end_on_the_cuda_rollout(tmp_path, golden):
+    """The generator CLI: file in the reference's layout, frame 0 = the drawn states, every later frame bit-identical to the
+    C oracle's rollout, and readable by the dataset reader the sampling driver uses."""
+    from cindm_b200.data import NBodyDataset, nbody_simulation as gen
+    from oracle import nbody_ref
+    path = gen.main(["--n_bodies=4", "--n_simulations=5", "--seed=123", f"--dataset_root={tmp_path}"])
+    assert path == str(tmp_path / "nbody-4" / "speed-100" / "trajectory_balls_4_simu_5_steps_1000.npy")
+    data = np.load(path)
+    assert data.shape == (5, 1000, 4, 4) and data.dtype == np.float64 and np.isfinite(data).all()
+    states = golden("nbody_generator.npz")["seed123_n4"]
+    assert np.array_equal(data[:, 0], states)
+    assert np.array_equal(data, nbody_ref.rollout(states, 1000, 1))
+    assert data[..., :2].min() > 15.0 and data[..., :2].max() < 185.0        # centres stay inside the walls up to one step's penetration
+    ds = NBodyDataset(dataset="nbody-4", input_steps=4, output_steps=24, time_interval=4, is_y_diff=False, is_train=False,
+                      is_testdata=False, data=data)
+    assert len(ds) > 0
