@@ -150,3 +150,22 @@ def test_other_model_shapes_host_logic():
     dif = GaussianDiffusion1D(model, image_size=20, conditioned_steps=4, timesteps=1000, sampling_timesteps=4)
     with pytest.raises(ValueError, match="do not fit"):                  # 10 windows of 20 frames into 40: the reference's :2289 fails too
         dif.autoregress_time_compose_sample(2, torch.zeros(2, 4, 8), 1, is_single_step_prediction=True, prediction_steps=40)
+
+
+def test_ddim_schedule_host_logic_matches_the_oracle():
+    """The DDIM (time, time_next) grid and per-pair coefficients are formed on the host and handed to the C ABI: they equal
+    the oracle's (pinned to whole reference ddim_sample runs) bit for bit, the NaN of the discarded last pair included."""
+    import torch
+    from oracle import sampler_ref
+    from cindm_b200.model.diffusion_1d import GaussianDiffusion1D, TemporalUnet1D
+    model = TemporalUnet1D(horizon=24, transition_dim=8, cond_dim=False, dim=64, dim_mults=(1, 2, 4, 8), attention=True)
+    tabs = sampler_ref.cosine_schedule_tables()
+    for steps, eta in ((3, 0.0), (8, 0.5), (50, 1.0), (250, 0.3), (999, 0.0)):
+        dif = GaussianDiffusion1D(model, image_size=24, conditioned_steps=0, timesteps=1000, sampling_timesteps=steps,
+                                  ddim_sampling_eta=eta)
+        pairs, coef = dif.ddim_schedule()
+        assert pairs == sampler_ref.ddim_time_pairs(1000, steps) and len(pairs) == steps and pairs[-1][1] == -1
+        for i, (t, tn) in enumerate(pairs):
+            a, c, sigma = sampler_ref.ddim_coefficients(tabs, t, tn, eta)
+            want = torch.stack([a, c, sigma]).to(torch.float32)
+            assert torch.equal(coef[i].isnan(), want.isnan()) and torch.equal(coef[i].nan_to_num(7.0), want.nan_to_num(7.0)), (steps, i)
