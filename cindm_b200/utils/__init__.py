@@ -2,7 +2,6 @@
 rollout kernel instead of pymunk.  Names and argument meaning follow the reference:
 simulation (utils.py:1071-1125), eval_simu (:1127-1148), caculate_confidence_interval (:1215-1239),
 setup_seed (:1257-1262), get_item_1d layout (:203-223)."""
-import ctypes
 import random
 
 import numpy as np
