@@ -40,6 +40,24 @@ def test_header_is_plain_c(tmp_path):
     assert r.returncode == 0, r.stderr
 
 
+def test_c_program_links_and_runs_the_host_entry_points(library, tmp_path):
+    """examples/host_entry_points.c: a C99 consumer of the shared library (schedule tables, index maps, error reporting:
+    the entry points that need no GPU) builds against include/cindm_b200.h and passes its own known-answer checks."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not on PATH")
+    exe = tmp_path / "host_entry_points"
+    libdir = os.path.dirname(library)
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "host_entry_points.c"), "-o", str(exe), "-L", libdir, "-lcindm_b200",
+                        f"-Wl,-rpath,{libdir}", "-lm"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("ok:"), r.stdout + r.stderr
+
+
 def test_header_and_binding_agree():
     from cindm_b200 import _lib
     assert declared_symbols() == _lib.exported_symbols()
